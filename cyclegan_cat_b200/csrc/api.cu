@@ -1,0 +1,265 @@
+// C ABI of libcyclegan_b200.so: library init, model builder, single-net forward/backward.
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "kernels.h"
+#include "net.h"
+
+std::atomic<long long> g_launches{0};
+static thread_local char g_err[1024] = "";
+
+void cg_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* cg_last_error(void) { return g_err; }
+extern "C" int cg_version(void) { return 100; }
+
+extern "C" int cg_init(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cg_set_error("no CUDA device: %s (libcyclegan_b200 has no CPU fallback)", cudaGetErrorString(e));
+        return CG_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { cg_set_error("device %d out of range (%d devices)", device, n); return CG_ERR_INVALID; }
+    cudaDeviceProp p;
+    CG_CUDA(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10) {
+        cg_set_error("device %d is sm_%d%d; this library contains sm_100a code only", device, p.major, p.minor);
+        return CG_ERR_INVALID;
+    }
+    CG_CUDA(cudaSetDevice(device));
+    return CG_OK;
+}
+
+extern "C" int cg_launch_count(int64_t* launches, int reset) {
+    if (launches) *launches = g_launches.load();
+    if (reset) g_launches.store(0);
+    return CG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// model builder
+// ------------------------------------------------------------------------------------------
+extern "C" int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode, cg_net_t* out) {
+    if (!layers || n_layers <= 0 || !out) { cg_set_error("cg_net_create: null/empty layer list"); return CG_ERR_INVALID; }
+    if (mode != CG_MODE_BF16 && mode != CG_MODE_FP32_CHECK) { cg_set_error("unknown mode %d", mode); return CG_ERR_INVALID; }
+    cg_net_s* net = new cg_net_s();
+    net->mode = mode;
+    net->layers.resize(n_layers);
+    net->chan.assign(n_layers + 1, 0);
+    net->n_consumers.assign(n_layers + 1, 0);
+    net->has_buffer.assign(n_layers + 1, 1);
+    net->dep_params.assign(n_layers + 1, 0);
+    auto fail = [&](const char* what, int i) {
+        cg_set_error("cg_net_create: layer %d: %s", i, what);
+        delete net;
+        return CG_ERR_INVALID;
+    };
+    // input channels = cin of the first consumer of tensor 0
+    for (int i = 0; i < n_layers; ++i)
+        if (layers[i].in0 == 0) { net->chan[0] = layers[i].cin; break; }
+    if (net->chan[0] <= 0) return fail("tensor 0 is never consumed", 0);
+    long long off = 0;
+    for (int i = 0; i < n_layers; ++i) {
+        LayerInfo& L = net->layers[i];
+        L.d = layers[i];
+        L.out_t = i + 1;
+        const cg_layer_desc& d = L.d;
+        if (d.in0 < 0 || d.in0 > i) return fail("in0 is not an earlier tensor", i);
+        const bool two = d.op == CG_OP_ADD || d.op == CG_OP_CONCAT;
+        if (two && (d.in1 < 0 || d.in1 > i)) return fail("in1 is not an earlier tensor", i);
+        if (net->chan[d.in0] != d.cin) return fail("cin does not match the producer's channels", i);
+        net->n_consumers[d.in0]++;
+        if (two) net->n_consumers[d.in1]++;
+        bool params_here = false;
+        auto add_var = [&](int role, int ndim, int s0, int s1, int s2, int s3) {
+            cg_var_info v;
+            v.layer = i; v.role = role; v.ndim = ndim;
+            v.shape[0] = s0; v.shape[1] = s1; v.shape[2] = s2; v.shape[3] = s3;
+            v.offset = off;
+            long long n = 1;
+            for (int q = 0; q < ndim; ++q) n *= v.shape[q];
+            off += n;
+            net->vars.push_back(v);
+            params_here = true;
+            return v.offset;
+        };
+        switch (d.op) {
+            case CG_OP_CONV:
+            case CG_OP_CONVT:
+                if (d.k < 1 || d.k > 15 || (d.stride != 1 && d.stride != 2) || d.cout < 1) return fail("bad conv geometry", i);
+                if (d.op == CG_OP_CONVT && !d.same) return fail("Conv2DTranspose supports padding='same' only", i);
+                net->chan[i + 1] = d.cout;
+                L.w_off = d.op == CG_OP_CONV ? add_var(0, 4, d.k, d.k, d.cin, d.cout) : add_var(0, 4, d.k, d.k, d.cout, d.cin);
+                if (d.has_bias) L.b_off = add_var(1, 1, d.cout, 0, 0, 0);
+                break;
+            case CG_OP_INORM:
+                net->chan[i + 1] = d.cin;
+                if (d.affine) { L.g_off = add_var(2, 1, d.cin, 0, 0, 0); L.be_off = add_var(3, 1, d.cin, 0, 0, 0); }
+                break;
+            case CG_OP_ACT:
+                if (d.act < CG_ACT_RELU || d.act > CG_ACT_SIGMOID) return fail("unknown activation", i);
+                net->chan[i + 1] = d.cin;
+                break;
+            case CG_OP_RPAD:
+                if (d.pad < 1) return fail("reflect pad must be >= 1", i);
+                net->chan[i + 1] = d.cin;
+                break;
+            case CG_OP_ADD:
+                if (net->chan[d.in1] != d.cin) return fail("Add of different channel counts", i);
+                net->chan[i + 1] = d.cin;
+                break;
+            case CG_OP_CONCAT:
+                net->chan[i + 1] = d.cin + net->chan[d.in1];
+                if (d.cout != net->chan[i + 1]) return fail("cout != sum of concat inputs", i);
+                break;
+            case CG_OP_AVGPOOL:
+            case CG_OP_UPSAMPLE: net->chan[i + 1] = d.cin; break;
+            default: return fail("unknown op", i);
+        }
+        net->dep_params[i + 1] = params_here || net->dep_params[d.in0] || (two && net->dep_params[d.in1]);
+    }
+    net->n_params = off;
+    // fold ReLU / LeakyReLU into the instance norm that feeds only them
+    for (int i = 0; i + 1 < n_layers; ++i) {
+        LayerInfo& L = net->layers[i];
+        LayerInfo& A = net->layers[i + 1];
+        if (L.d.op == CG_OP_INORM && A.d.op == CG_OP_ACT && A.d.in0 == i + 1 && net->n_consumers[i + 1] == 1 &&
+            (A.d.act == CG_ACT_RELU || A.d.act == CG_ACT_LEAKY)) {
+            L.out_t = i + 2;
+            L.fused_act = A.d.act;
+            L.fused_slope = A.d.slope;
+            A.skipped = true;
+            net->has_buffer[i + 1] = 0;
+        }
+    }
+    *out = net;
+    return CG_OK;
+}
+
+static std::mutex g_single_mu;
+struct SingleCall;
+static std::vector<std::pair<cg_net_t, SingleCall*>> g_single;
+static void single_forget(cg_net_t net);
+extern "C" void cg_net_destroy(cg_net_t net) {
+    if (!net) return;
+    single_forget(net);
+    delete net;
+}
+
+extern "C" int cg_net_param_floats(cg_net_t net, int64_t* n) {
+    if (!net || !n) { cg_set_error("null argument"); return CG_ERR_INVALID; }
+    *n = net->n_params;
+    return CG_OK;
+}
+extern "C" int cg_net_var_count(cg_net_t net, int* n) {
+    if (!net || !n) { cg_set_error("null argument"); return CG_ERR_INVALID; }
+    *n = (int)net->vars.size();
+    return CG_OK;
+}
+extern "C" int cg_net_var_info(cg_net_t net, int i, cg_var_info* out) {
+    if (!net || !out || i < 0 || i >= (int)net->vars.size()) { cg_set_error("bad variable index %d", i); return CG_ERR_INVALID; }
+    *out = net->vars[i];
+    return CG_OK;
+}
+extern "C" int cg_net_out_shape(cg_net_t net, int N, int H, int W, int out[4]) {
+    if (!net || !out) { cg_set_error("null argument"); return CG_ERR_INVALID; }
+    int ho, wo;
+    CG_TRY(net_out_hw(net, H, W, &ho, &wo));
+    out[0] = N; out[1] = ho; out[2] = wo; out[3] = net->chan.back();
+    return CG_OK;
+}
+
+// workspace of a single-net call: [activations | gradient arena | dy/dx staging in activation dtype]
+struct SingleLayout { size_t act, arena, dy, dx, total; };
+static int single_layout(const cg_net_s* net, CallCtx* ctx, int N, int H, int W, bool bwd, SingleLayout* lay) {
+    CG_TRY(net_plan(net, N, H, W, bwd, ctx));
+    size_t es = net->elem_size();
+    lay->act = 0;
+    lay->arena = align_up(ctx->act_bytes, 256);
+    lay->dy = lay->arena + align_up(ctx->grad_bytes, 256);
+    lay->dx = lay->dy + (bwd ? align_up((size_t)N * ctx->sample_elems(net->out_tensor()) * es, 256) : 0);
+    lay->total = lay->dx + (bwd ? align_up((size_t)N * ctx->sample_elems(0) * es, 256) : 0);
+    return CG_OK;
+}
+
+extern "C" int cg_net_workspace_bytes(cg_net_t net, int N, int H, int W, int need_backward, size_t* bytes) {
+    if (!net || !bytes) { cg_set_error("null argument"); return CG_ERR_INVALID; }
+    CallCtx ctx; SingleLayout lay;
+    CG_TRY(single_layout(net, &ctx, N, H, W, need_backward != 0, &lay));
+    *bytes = lay.total;
+    return CG_OK;
+}
+
+// the planned context of the last forward is kept per net so that cg_net_backward can follow it
+struct SingleCall { CallCtx ctx; SingleLayout lay; void* ws = nullptr; };
+static void single_forget(cg_net_t net) {
+    std::lock_guard<std::mutex> lk(g_single_mu);
+    for (size_t i = 0; i < g_single.size(); ++i)
+        if (g_single[i].first == net) { delete g_single[i].second; g_single.erase(g_single.begin() + i); return; }
+}
+static SingleCall* single_of(cg_net_t net) {
+    std::lock_guard<std::mutex> lk(g_single_mu);
+    for (auto& p : g_single) if (p.first == net) return p.second;
+    g_single.push_back({net, new SingleCall()});
+    return g_single.back().second;
+}
+
+extern "C" int cg_net_forward(cg_net_t net, const float* params, const float* x, float* y, void* ws, size_t ws_bytes,
+                              int N, int H, int W, int need_backward, void* stream) {
+    if (!net || !params || !x || !y || !ws) { cg_set_error("cg_net_forward: null argument"); return CG_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    SingleCall* sc = single_of(net);
+    CG_TRY(single_layout(net, &sc->ctx, N, H, W, need_backward != 0, &sc->lay));
+    if (sc->lay.total > ws_bytes) { cg_set_error("workspace %zu < required %zu", ws_bytes, sc->lay.total); return CG_ERR_WORKSPACE; }
+    sc->ws = ws;
+    sc->ctx.base = (char*)ws + sc->lay.act;
+    sc->ctx.arena = (char*)ws + sc->lay.arena;
+    sc->ctx.ext_input = nullptr;
+    const int tout = net->out_tensor();
+    size_t nin = (size_t)N * sc->ctx.sample_elems(0), nout = (size_t)N * sc->ctx.sample_elems(tout);
+    if (net->mode == CG_MODE_BF16) {
+        CG_TRY(k_convert_in<bf16>(x, (bf16*)sc->ctx.act(0), nin, st));
+        CG_TRY(net_forward(&sc->ctx, params, st));
+        CG_TRY(k_convert_out<bf16>((const bf16*)sc->ctx.act(tout), y, nout, st));
+    } else {
+        CG_TRY(k_convert_in<float>(x, (float*)sc->ctx.act(0), nin, st));
+        CG_TRY(net_forward(&sc->ctx, params, st));
+        CG_TRY(k_convert_out<float>((const float*)sc->ctx.act(tout), y, nout, st));
+    }
+    return CG_OK;
+}
+
+extern "C" int cg_net_backward(cg_net_t net, const float* params, const float* dy, float* dx, float* grads,
+                               int accumulate, void* ws, size_t ws_bytes, void* stream) {
+    if (!net || !params || !dy || !ws) { cg_set_error("cg_net_backward: null argument"); return CG_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    SingleCall* sc = single_of(net);
+    if (sc->ws != ws || !sc->ctx.forwarded || !sc->ctx.bwd || sc->lay.total > ws_bytes) {
+        cg_set_error("cg_net_backward: no matching cg_net_forward(need_backward=1) on this workspace");
+        return CG_ERR_STATE;
+    }
+    CallCtx& c = sc->ctx;
+    const int tout = net->out_tensor();
+    size_t nin = (size_t)c.N * c.sample_elems(0), nout = (size_t)c.N * c.sample_elems(tout);
+    if (grads && !accumulate) CG_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)net->n_params, st));
+    void* dy_t = (char*)ws + sc->lay.dy;
+    void* dx_t = dx ? (void*)((char*)ws + sc->lay.dx) : nullptr;
+    if (net->mode == CG_MODE_BF16) {
+        CG_TRY(k_convert_in<bf16>(dy, (bf16*)dy_t, nout, st));
+        CG_TRY(net_backward(&c, params, dy_t, dx_t, grads, 0, c.N, st));
+        if (dx) CG_TRY(k_convert_out<bf16>((const bf16*)dx_t, dx, nin, st));
+    } else {
+        CG_TRY(k_convert_in<float>(dy, (float*)dy_t, nout, st));
+        CG_TRY(net_backward(&c, params, dy_t, dx_t, grads, 0, c.N, st));
+        if (dx) CG_TRY(k_convert_out<float>((const float*)dx_t, dx, nin, st));
+    }
+    return CG_OK;
+}

@@ -1,0 +1,118 @@
+// Shared host/device helpers for libcyclegan_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include <string>
+
+#include "../../include/cyclegan_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing (never throw across the C ABI) ---------------------------------
+void cg_set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;      // kernels launched by this library
+
+#define CG_CUDA(call)                                                                     \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            cg_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return CG_ERR_CUDA;                                                           \
+        }                                                                                 \
+    } while (0)
+
+#define CG_TRY(call)                       \
+    do {                                   \
+        int rc__ = (call);                 \
+        if (rc__ != CG_OK) return rc__;    \
+    } while (0)
+
+#define CG_LAUNCH_CHECK()                                                                 \
+    do {                                                                                  \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                               \
+        cudaError_t e__ = cudaGetLastError();                                             \
+        if (e__ != cudaSuccess) {                                                         \
+            cg_set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return CG_ERR_CUDA;                                                           \
+        }                                                                                 \
+    } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- geometry of one convolution (forward orientation) --------------------------------
+// y[n,oh,ow,co] = sum_{kh,kw,ci} x[n, oh*s+kh-pt, ow*s+kw-pl, ci] * w[kh,kw,ci,co]   (w is HWIO)
+struct ConvGeom {
+    int N, Hi, Wi, Cin, Ho, Wo, Cout, k, s, pt, pl;
+};
+
+#ifdef __CUDACC__
+// ---- scalar / vector access helpers ---------------------------------------------------
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ float ldf(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(bf16* p, float v) { *p = __float2bfloat16(v); }
+
+template <typename T, int VEC>
+struct Pack;   // VEC elements of T moved with one (<=16 byte) access
+template <>
+struct Pack<float, 1> { float v[1]; };
+template <>
+struct Pack<bf16, 1> { bf16 v[1]; };
+template <>
+struct __align__(16) Pack<float, 4> { float v[4]; };
+template <>
+struct __align__(16) Pack<bf16, 8> { bf16 v[8]; };
+template <>
+struct __align__(8) Pack<bf16, 4> { bf16 v[4]; };
+
+template <typename T, int VEC>
+__device__ __forceinline__ void load_vec(const T* p, float (&out)[VEC]) {
+    Pack<T, VEC> pk = *reinterpret_cast<const Pack<T, VEC>*>(p);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) out[i] = ldf(&pk.v[i]);
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void store_vec(T* p, const float (&in)[VEC]) {
+    Pack<T, VEC> pk;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) stf(&pk.v[i], in[i]);
+    *reinterpret_cast<Pack<T, VEC>*>(p) = pk;
+}
+
+template <typename T>
+struct VecWidth;     // elements per 16-byte access
+template <>
+struct VecWidth<float> { static constexpr int value = 4; };
+template <>
+struct VecWidth<bf16> { static constexpr int value = 8; };
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float act_fwd(float x, int act, float slope) {
+    switch (act) {
+        case CG_ACT_RELU: return x > 0.f ? x : 0.f;
+        case CG_ACT_LEAKY: return x > 0.f ? x : slope * x;
+        case CG_ACT_TANH: return tanhf(x);
+        case CG_ACT_SIGMOID: return 1.f / (1.f + expf(-x));
+        default: return x;
+    }
+}
+// derivative expressed through the activation OUTPUT y (all four are invertible enough for that)
+__device__ __forceinline__ float act_grad_from_out(float y, int act, float slope) {
+    switch (act) {
+        case CG_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+        case CG_ACT_LEAKY: return y > 0.f ? 1.f : slope;
+        case CG_ACT_TANH: return 1.f - y * y;
+        case CG_ACT_SIGMOID: return y * (1.f - y);
+        default: return 1.f;
+    }
+}
+#endif

@@ -1,0 +1,50 @@
+// Host launchers of the hand-written kernels.  T is the activation type: float (fp32 check
+// mode) or bf16.  Parameters, parameter gradients and all statistics are always float32.
+#pragma once
+#include "common.h"
+
+template <typename T> int k_convert_in(const float* src, T* dst, size_t n, cudaStream_t st);
+template <typename T> int k_convert_out(const T* src, float* dst, size_t n, cudaStream_t st);
+
+// ---- CUDA-core implicit-GEMM convolutions (any geometry) ----
+template <typename T> int k_conv_fwd(const T* x, const float* w, const float* bias, T* y, ConvGeom g, int accumulate,
+                                     cudaStream_t st);
+template <typename T> int k_conv_dgrad(const T* dy, const float* w, const float* bias, T* dx, ConvGeom g,
+                                       int accumulate, cudaStream_t st);
+template <typename T> int k_conv_wgrad(const T* x, const T* dy, float* dw, ConvGeom g, cudaStream_t st);
+template <typename T> int k_colsum(const T* dy, float* db, size_t rows, int C, cudaStream_t st);
+
+// ---- instance norm ----
+template <typename T> int k_in_stats(const T* x, float* stats, int N, int P, int C, float eps, cudaStream_t st);
+int k_in_finalize(float* stats, int NC, int P, float eps, cudaStream_t st);
+template <typename T> int k_in_apply(const T* x, T* y, const float* stats, const float* gamma, const float* beta,
+                                     int act, float slope, int N, int P, int C, cudaStream_t st);
+template <typename T> int k_in_bwd(const T* x, const T* dy, T* dx, const float* stats, const float* gamma,
+                                   const float* beta, float* dgamma, float* dbeta, float* scratch, int act,
+                                   float slope, int N, int P, int C, int accumulate, cudaStream_t st);
+
+// ---- elementwise / data movement ----
+template <typename T> int k_act_fwd(const T* x, T* y, size_t n, int act, float slope, cudaStream_t st);
+template <typename T> int k_act_bwd(const T* y, const T* dy, T* dx, size_t n, int act, float slope, int accumulate,
+                                    cudaStream_t st);
+template <typename T> int k_rpad_fwd(const T* x, T* y, int N, int H, int W, int C, int p, cudaStream_t st);
+template <typename T> int k_rpad_bwd(const T* dy, T* dx, int N, int H, int W, int C, int p, int accumulate,
+                                     cudaStream_t st);
+template <typename T> int k_add(const T* a, const T* b, T* y, size_t n, cudaStream_t st);
+template <typename T> int k_copy_acc(const T* src, T* dst, size_t n, int accumulate, cudaStream_t st);
+template <typename T> int k_slice_copy(const T* src, int Cs, int so, T* dst, int Cd, int doff, int Cc, size_t npix,
+                                       int accumulate, cudaStream_t st);
+template <typename T> int k_avgpool_fwd(const T* x, T* y, int N, int H, int W, int C, cudaStream_t st);
+template <typename T> int k_avgpool_bwd(const T* dy, T* dx, int N, int H, int W, int C, int accumulate, cudaStream_t st);
+template <typename T> int k_upsample_fwd(const T* x, T* y, int N, int H, int W, int C, cudaStream_t st);
+template <typename T> int k_upsample_bwd(const T* dy, T* dx, int N, int H, int W, int C, int accumulate, cudaStream_t st);
+
+// ---- losses (value + gradient seed in one pass), Adam ----
+// sum_out += sum_i L(d_i, target); correct_out += #{(d_i > 0.5) == target}; grad_i = grad_scale * dL/dd_i
+template <typename T> int k_adv_loss(const T* d, size_t n, float target, int kind, float grad_scale, T* grad,
+                                     float* sum_out, float* correct_out, cudaStream_t st);
+// sum_out += sum |real - gen|; grad (+)= grad_scale * sign(gen - real)
+template <typename T> int k_l1_loss(const T* real, const T* gen, size_t n, float grad_scale, T* grad, int accumulate,
+                                    float* sum_out, cudaStream_t st);
+int k_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float b1, float b2, float eps,
+           float grad_scale, cudaStream_t st);

@@ -1,0 +1,394 @@
+// CUDA-core implicit-GEMM convolutions: forward, data-gradient (= transposed-conv forward) and
+// weight-gradient, for ANY geometry the four reference builders produce (k in 1..7, stride 1/2,
+// TF 'same' asymmetric padding or 'valid', Cin/Cout from 1 to 1024+).  They are
+//   * the whole conv path of the fp32 check mode (exact fp32 FMA accumulation), and
+//   * the path of bf16-mode layers whose shape the tcgen05 kernel does not take
+//     (Cin = 3 stems, Cout = 1/3 heads, ...).
+// Tile 64x64x16, 256 threads, 4x4 register micro-tile, fp32 accumulation.  Weights are the
+// float32 master copies in TensorFlow layout (HWIO).
+#include "kernels.h"
+
+#define BM 64
+#define BN 64
+#define BK 16
+
+template <typename T>
+__device__ __forceinline__ void load4_or_zero(const T* p, bool ok, float (&v)[4]) {
+    if (ok) load_vec<T, 4>(p, v);
+    else { v[0] = v[1] = v[2] = v[3] = 0.f; }
+}
+
+#define MICRO_FMA()                                                                   \
+    _Pragma("unroll") for (int kk = 0; kk < BK; ++kk) {                               \
+        float a[4], b[4];                                                             \
+        *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(&As[kk][ty * 4]); \
+        *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]); \
+        _Pragma("unroll") for (int i = 0; i < 4; ++i)                                 \
+            _Pragma("unroll") for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]); \
+    }
+
+// ------------------------------------------------------------------------------------------
+// forward:  M = N*Ho*Wo pixels, Ncol = Cout, K = k*k*Cin
+// ------------------------------------------------------------------------------------------
+template <typename T, bool CIN4>
+__global__ void __launch_bounds__(256) conv_fwd_simt(const T* __restrict__ x, const float* __restrict__ w,
+                                                     const float* __restrict__ bias, T* __restrict__ y, ConvGeom g,
+                                                     int accumulate) {
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int M = g.N * g.Ho * g.Wo, K = g.k * g.k * g.Cin;
+
+    const int a_r = tid >> 2, a_k = (tid & 3) << 2;
+    const int m = m0 + a_r;
+    const bool mvalid = m < M;
+    int n_img = 0, ih0 = 0, iw0 = 0;
+    if (mvalid) {
+        n_img = m / (g.Ho * g.Wo);
+        int r = m - n_img * g.Ho * g.Wo;
+        int oh = r / g.Wo, ow = r - oh * g.Wo;
+        ih0 = oh * g.s - g.pt;
+        iw0 = ow * g.s - g.pl;
+    }
+    const T* xn = x + (size_t)n_img * g.Hi * g.Wi * g.Cin;
+    const int b_k = tid >> 4, b_n = (tid & 15) << 2;
+    const bool cout4 = (g.Cout & 3) == 0;
+
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        {   // A tile: gathered input patch elements
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            int kk = k0 + a_k;
+            if (CIN4) {
+                if (mvalid && kk < K) {
+                    int tap = kk / g.Cin, ci = kk - tap * g.Cin;
+                    int kh = tap / g.k, kw = tap - kh * g.k;
+                    int ih = ih0 + kh, iw = iw0 + kw;
+                    bool ok = ih >= 0 && ih < g.Hi && iw >= 0 && iw < g.Wi;
+                    load4_or_zero<T>(xn + ((size_t)ih * g.Wi + iw) * g.Cin + ci, ok, v);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int kj = kk + j;
+                    if (mvalid && kj < K) {
+                        int tap = kj / g.Cin, ci = kj - tap * g.Cin;
+                        int kh = tap / g.k, kw = tap - kh * g.k;
+                        int ih = ih0 + kh, iw = iw0 + kw;
+                        if (ih >= 0 && ih < g.Hi && iw >= 0 && iw < g.Wi)
+                            v[j] = ldf(xn + ((size_t)ih * g.Wi + iw) * g.Cin + ci);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) As[a_k + j][a_r] = v[j];
+        }
+        {   // B tile: w[kk][co], co contiguous
+            int kk = k0 + b_k, co = n0 + b_n;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (kk < K) {
+                if (cout4 && co + 3 < g.Cout) *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(w + (size_t)kk * g.Cout + co);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (co + j < g.Cout) v[j] = w[(size_t)kk * g.Cout + co + j];
+                }
+            }
+            *reinterpret_cast<float4*>(&Bs[b_k][b_n]) = *reinterpret_cast<float4*>(v);
+        }
+        __syncthreads();
+        MICRO_FMA();
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int mm = m0 + ty * 4 + i;
+        if (mm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int co = n0 + tx * 4 + j;
+            if (co < g.Cout) {
+                T* o = y + (size_t)mm * g.Cout + co;
+                float v = acc[i][j] + (bias ? bias[co] : 0.f);
+                stf(o, accumulate ? ldf(o) + v : v);
+            }
+        }
+    }
+}
+
+template <typename T> int k_conv_fwd(const T* x, const float* w, const float* bias, T* y, ConvGeom g, int accumulate,
+                                     cudaStream_t st) {
+    long long M = (long long)g.N * g.Ho * g.Wo;
+    dim3 grid(cdiv(M, BM), cdiv(g.Cout, BN));
+    if (g.Cin % 4 == 0) conv_fwd_simt<T, true><<<grid, 256, 0, st>>>(x, w, bias, y, g, accumulate);
+    else conv_fwd_simt<T, false><<<grid, 256, 0, st>>>(x, w, bias, y, g, accumulate);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// data gradient / transposed-conv forward (gather form, one grid.z slice per stride-parity class
+// so that only the taps that really hit a pixel are multiplied):
+//   dx[n,ih,iw,ci] = sum_{kh,kw,co} dy[n,oh,ow,co] * w[kh,kw,ci,co],  oh*s + kh - pt = ih
+//   M = pixels of the class, Ncol = Cin, K = (taps of the class) * Cout
+// ------------------------------------------------------------------------------------------
+template <typename T, bool COUT4>
+__global__ void __launch_bounds__(256) conv_dgrad_simt(const T* __restrict__ dy, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, T* __restrict__ dx,
+                                                       ConvGeom g, int accumulate) {
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int ph = blockIdx.z / g.s, pw = blockIdx.z % g.s;
+    const int Hc = (g.Hi - ph + g.s - 1) / g.s, Wc = (g.Wi - pw + g.s - 1) / g.s;
+    const int M = g.N * Hc * Wc;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    if (m0 >= M) return;
+    const int kh_first = (ph + g.pt) % g.s, kw_first = (pw + g.pl) % g.s;
+    const int nkh = kh_first < g.k ? (g.k - kh_first + g.s - 1) / g.s : 0;
+    const int nkw = kw_first < g.k ? (g.k - kw_first + g.s - 1) / g.s : 0;
+    const int qh = (ph + g.pt - kh_first) / g.s, qw = (pw + g.pl - kw_first) / g.s;
+    const int K = nkh * nkw * g.Cout;
+
+    const int a_r = tid >> 2, a_k = (tid & 3) << 2;
+    const int m = m0 + a_r;
+    const bool mvalid = m < M;
+    int n_img = 0, hc = 0, wc = 0;
+    if (mvalid) {
+        n_img = m / (Hc * Wc);
+        int r = m - n_img * Hc * Wc;
+        hc = r / Wc;
+        wc = r - hc * Wc;
+    }
+    const T* dyn = dy + (size_t)n_img * g.Ho * g.Wo * g.Cout;
+    const int b_c = tid >> 2, b_k = (tid & 3) << 2;     // B: column ci = n0 + b_c, 4 consecutive k
+
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        {
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            int kk = k0 + a_k;
+            if (COUT4) {
+                if (mvalid && kk < K) {
+                    int ta = kk / g.Cout, co = kk - ta * g.Cout;
+                    int a = ta / nkw, b = ta - a * nkw;
+                    int oh = hc + qh - a, ow = wc + qw - b;
+                    bool ok = oh >= 0 && oh < g.Ho && ow >= 0 && ow < g.Wo;
+                    load4_or_zero<T>(dyn + ((size_t)oh * g.Wo + ow) * g.Cout + co, ok, v);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int kj = kk + j;
+                    if (mvalid && kj < K) {
+                        int ta = kj / g.Cout, co = kj - ta * g.Cout;
+                        int a = ta / nkw, b = ta - a * nkw;
+                        int oh = hc + qh - a, ow = wc + qw - b;
+                        if (oh >= 0 && oh < g.Ho && ow >= 0 && ow < g.Wo)
+                            v[j] = ldf(dyn + ((size_t)oh * g.Wo + ow) * g.Cout + co);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) As[a_k + j][a_r] = v[j];
+        }
+        {
+            int ci = n0 + b_c;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (ci < g.Cin) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int kj = k0 + b_k + j;
+                    if (kj < K) {
+                        int ta = kj / g.Cout, co = kj - ta * g.Cout;
+                        int a = ta / nkw, b = ta - a * nkw;
+                        int kh = kh_first + a * g.s, kw = kw_first + b * g.s;
+                        v[j] = w[(((size_t)kh * g.k + kw) * g.Cin + ci) * g.Cout + co];
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Bs[b_k + j][b_c] = v[j];
+        }
+        __syncthreads();
+        MICRO_FMA();
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int mm = m0 + ty * 4 + i;
+        if (mm >= M) continue;
+        int ni = mm / (Hc * Wc);
+        int r = mm - ni * Hc * Wc;
+        int h2 = r / Wc, w2 = r - h2 * Wc;
+        size_t pix = ((size_t)ni * g.Hi + (h2 * g.s + ph)) * g.Wi + (w2 * g.s + pw);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int ci = n0 + tx * 4 + j;
+            if (ci < g.Cin) {
+                T* o = dx + pix * g.Cin + ci;
+                float v = acc[i][j] + (bias ? bias[ci] : 0.f);
+                stf(o, accumulate ? ldf(o) + v : v);
+            }
+        }
+    }
+}
+
+template <typename T> int k_conv_dgrad(const T* dy, const float* w, const float* bias, T* dx, ConvGeom g,
+                                       int accumulate, cudaStream_t st) {
+    int Hc = cdiv(g.Hi, g.s), Wc = cdiv(g.Wi, g.s);
+    long long M = (long long)g.N * Hc * Wc;
+    dim3 grid(cdiv(M, BM), cdiv(g.Cin, BN), g.s * g.s);
+    if (g.Cout % 4 == 0) conv_dgrad_simt<T, true><<<grid, 256, 0, st>>>(dy, w, bias, dx, g, accumulate);
+    else conv_dgrad_simt<T, false><<<grid, 256, 0, st>>>(dy, w, bias, dx, g, accumulate);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// weight gradient: dw[(kh,kw,ci), co] += sum_pixels x[n, oh*s+kh-pt, ow*s+kw-pl, ci] * dy[n,oh,ow,co]
+//   M = k*k*Cin, Ncol = Cout, K = N*Ho*Wo pixels, split over grid.z, fp32 atomics into dw
+// ------------------------------------------------------------------------------------------
+template <typename T, bool CIN4>
+__global__ void __launch_bounds__(256) conv_wgrad_simt(const T* __restrict__ x, const T* __restrict__ dy,
+                                                       float* __restrict__ dw, ConvGeom g, int pix_per_split) {
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int Mrows = g.k * g.k * g.Cin;
+    const int P = g.N * g.Ho * g.Wo;
+    const int p_begin = blockIdx.z * pix_per_split;
+    const int p_end = min(P, p_begin + pix_per_split);
+
+    // A: 4 consecutive rows (ci) for one pixel;  rows a_m..a_m+3, pixel slot a_p
+    const int a_m = (tid & 15) << 2, a_p = tid >> 4;
+    int a_tap[4], a_ci[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int r = m0 + a_m + j;
+        if (r < Mrows) { a_tap[j] = r / g.Cin; a_ci[j] = r - a_tap[j] * g.Cin; }
+        else { a_tap[j] = -1; a_ci[j] = 0; }
+    }
+    const int b_n = (tid & 15) << 2, b_p = tid >> 4;
+    const bool cout4 = (g.Cout & 3) == 0;
+
+    float acc[4][4] = {};
+    for (int p0 = p_begin; p0 < p_end; p0 += BK) {
+        {
+            int p = p0 + a_p;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (p < p_end) {
+                int n_img = p / (g.Ho * g.Wo);
+                int r = p - n_img * g.Ho * g.Wo;
+                int oh = r / g.Wo, ow = r - oh * g.Wo;
+                const T* xn = x + (size_t)n_img * g.Hi * g.Wi * g.Cin;
+                if (CIN4) {
+                    if (a_tap[0] >= 0) {
+                        int kh = a_tap[0] / g.k, kw = a_tap[0] - kh * g.k;
+                        int ih = oh * g.s + kh - g.pt, iw = ow * g.s + kw - g.pl;
+                        bool ok = ih >= 0 && ih < g.Hi && iw >= 0 && iw < g.Wi;
+                        load4_or_zero<T>(xn + ((size_t)ih * g.Wi + iw) * g.Cin + a_ci[0], ok, v);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (a_tap[j] >= 0) {
+                            int kh = a_tap[j] / g.k, kw = a_tap[j] - kh * g.k;
+                            int ih = oh * g.s + kh - g.pt, iw = ow * g.s + kw - g.pl;
+                            if (ih >= 0 && ih < g.Hi && iw >= 0 && iw < g.Wi)
+                                v[j] = ldf(xn + ((size_t)ih * g.Wi + iw) * g.Cin + a_ci[j]);
+                        }
+                    }
+                }
+            }
+            *reinterpret_cast<float4*>(&As[a_p][a_m]) = *reinterpret_cast<float4*>(v);
+        }
+        {
+            int p = p0 + b_p, co = n0 + b_n;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (p < p_end) {
+                if (cout4 && co + 3 < g.Cout) load_vec<T, 4>(dy + (size_t)p * g.Cout + co, v);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (co + j < g.Cout) v[j] = ldf(dy + (size_t)p * g.Cout + co + j);
+                }
+            }
+            *reinterpret_cast<float4*>(&Bs[b_p][b_n]) = *reinterpret_cast<float4*>(v);
+        }
+        __syncthreads();
+        MICRO_FMA();
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int r = m0 + ty * 4 + i;
+        if (r >= Mrows) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int co = n0 + tx * 4 + j;
+            if (co < g.Cout) atomicAdd(dw + (size_t)r * g.Cout + co, acc[i][j]);
+        }
+    }
+}
+
+template <typename T> int k_conv_wgrad(const T* x, const T* dy, float* dw, ConvGeom g, cudaStream_t st) {
+    int Mrows = g.k * g.k * g.Cin;
+    long long P = (long long)g.N * g.Ho * g.Wo;
+    int tiles = cdiv(Mrows, BM) * cdiv(g.Cout, BN);
+    int splits = cdiv(148 * 4, tiles);
+    int maxsplits = cdiv(P, 256);
+    if (splits > maxsplits) splits = maxsplits;
+    if (splits < 1) splits = 1;
+    int pps = cdiv(cdiv(P, splits), BK) * BK;
+    splits = cdiv(P, pps);
+    dim3 grid(cdiv(Mrows, BM), cdiv(g.Cout, BN), splits);
+    if (g.Cin % 4 == 0) conv_wgrad_simt<T, true><<<grid, 256, 0, st>>>(x, dy, dw, g, pps);
+    else conv_wgrad_simt<T, false><<<grid, 256, 0, st>>>(x, dy, dw, g, pps);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// bias gradient: db[c] += sum over rows of dy[rows][C]
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ dy, float* __restrict__ db, size_t rows,
+                                                     int C, size_t rchunk) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    const size_t r0 = blockIdx.y * rchunk;
+    const size_t r1 = r0 + rchunk < rows ? r0 + rchunk : rows;
+    float s = 0.f;
+    if (c < C)
+        for (size_t r = r0 + warp; r < r1; r += 8) s += ldf(dy + r * C + c);
+    __shared__ float sh[8][33];
+    sh[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && c < C) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a += sh[w][lane];
+        atomicAdd(db + c, a);
+    }
+}
+template <typename T> int k_colsum(const T* dy, float* db, size_t rows, int C, cudaStream_t st) {
+    int cb = cdiv(C, 32);
+    int splits = cdiv(148 * 4, cb);
+    size_t maxs = (rows + 63) / 64;
+    if ((size_t)splits > maxs) splits = (int)maxs;
+    if (splits < 1) splits = 1;
+    size_t rchunk = (rows + splits - 1) / splits;
+    dim3 grid(cb, (unsigned)((rows + rchunk - 1) / rchunk));
+    colsum_kernel<T><<<grid, 256, 0, st>>>(dy, db, rows, C, rchunk);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+#define INSTANTIATE(T)                                                                                   \
+    template int k_conv_fwd<T>(const T*, const float*, const float*, T*, ConvGeom, int, cudaStream_t);        \
+    template int k_conv_dgrad<T>(const T*, const float*, const float*, T*, ConvGeom, int, cudaStream_t); \
+    template int k_conv_wgrad<T>(const T*, const T*, float*, ConvGeom, cudaStream_t);                    \
+    template int k_colsum<T>(const T*, float*, size_t, int, cudaStream_t);
+INSTANTIATE(float)
+INSTANTIATE(bf16)

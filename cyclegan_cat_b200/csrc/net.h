@@ -1,0 +1,62 @@
+// Layer-graph executor: plans buffers for one (N,H,W) call of a net and launches the kernels
+// for forward and for the hand-scheduled backward.  No allocation: every buffer is a slice of
+// caller-owned workspace.
+#pragma once
+#include <vector>
+
+#include "common.h"
+
+struct TcPlan;   // tensor-core conv plans (conv_tc.cu), opaque here
+
+struct LayerInfo {
+    cg_layer_desc d;
+    long long w_off = -1, b_off = -1, g_off = -1, be_off = -1;   // offsets (floats) into the flat parameter buffer
+    int out_t = 0;          // tensor id this layer writes (i+1, or i+2 when the following ACT is fused in)
+    bool skipped = false;   // ACT folded into the preceding INORM
+    int fused_act = CG_ACT_NONE;
+    float fused_slope = 0.f;
+};
+
+struct cg_net_s {
+    int mode = CG_MODE_BF16;
+    std::vector<LayerInfo> layers;
+    std::vector<int> chan;              // channels per tensor id
+    std::vector<int> n_consumers;       // per tensor id
+    std::vector<char> has_buffer;       // per tensor id
+    std::vector<char> dep_params;       // tensor depends on some trainable variable
+    std::vector<cg_var_info> vars;
+    long long n_params = 0;
+    int out_tensor() const { return (int)layers.size(); }
+    size_t elem_size() const { return mode == CG_MODE_BF16 ? 2 : 4; }
+};
+
+// One planned call: shapes and workspace offsets for a given (N,H,W)
+struct CallCtx {
+    const cg_net_s* net = nullptr;
+    int N = 0, H = 0, W = 0;
+    bool bwd = false;
+    std::vector<int> th, tw;            // spatial size per tensor
+    std::vector<size_t> act_off;        // byte offsets into `base` (activations)
+    std::vector<size_t> stat_off;       // per layer: INORM statistics [N][C][2] float
+    size_t act_bytes = 0;
+    std::vector<size_t> grad_off;       // byte offsets into the shared gradient arena
+    size_t grad_bytes = 0;              // includes the IN-backward scratch at scratch_off
+    size_t scratch_off = 0;
+    char* base = nullptr;               // activations workspace
+    char* arena = nullptr;              // gradient arena (may be shared between calls)
+    void* ext_input = nullptr;          // if set, tensor 0 lives here instead of at act_off[0]
+    bool forwarded = false;
+
+    size_t sample_elems(int t) const { return (size_t)th[t] * tw[t] * net->chan[t]; }
+    void* act(int t) const { return (t == 0 && ext_input) ? ext_input : (void*)(base + act_off[t]); }
+};
+
+int net_plan(const cg_net_s* net, int N, int H, int W, bool bwd, CallCtx* ctx);
+int net_out_hw(const cg_net_s* net, int H, int W, int* ho, int* wo);
+
+// forward over the whole planned batch; output is ctx->act(out_tensor())
+int net_forward(CallCtx* ctx, const float* params, cudaStream_t st);
+// backward over samples [n0, n0+nb): dy is dLoss/d(output) for those samples (activation dtype);
+// dx (nullable) receives dLoss/d(input); parameter gradients are ACCUMULATED into grads when non-null.
+int net_backward(CallCtx* ctx, const float* params, const void* dy, void* dx, float* grads, int n0, int nb,
+                 cudaStream_t st);

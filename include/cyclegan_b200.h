@@ -1,0 +1,172 @@
+/*
+ * cyclegan_b200.h -- C ABI of libcyclegan_b200.so (hand-written sm_100a CUDA).
+ *
+ * Drop-in boundary for ONE hot path of dogeplusplus/cyclegan-cat: the CycleGAN
+ * training step and the generator forward.  The reference has no FFI layer of
+ * its own (it is pure Python on TensorFlow/Keras); each entry point below names
+ * the reference interface it replaces (paths relative to /root/reference).
+ * The Python host package (cyclegan_cat_b200/) binds these with ctypes; the
+ * reference-side stub a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns CG_OK (0) or a negative cg_status; it never throws
+ *    or aborts across the ABI; cg_last_error() returns a thread-local message.
+ *  - all pointers marked "dev" are CUDA device pointers owned by the CALLER
+ *    (torch allocates them); the library owns only plan objects.
+ *  - image tensors cross the boundary as float32 NHWC, exactly what the
+ *    reference feeds Keras (model.py:93-106, predict.py:32).
+ *  - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it.
+ *  - there is no CPU fallback and no cuDNN/cuBLAS/Triton inside.
+ */
+#ifndef CYCLEGAN_B200_H
+#define CYCLEGAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum cg_status {
+    CG_OK = 0,
+    CG_ERR_INVALID = -1,    /* bad argument / unsupported layer graph          */
+    CG_ERR_CUDA = -2,       /* a CUDA runtime / driver call failed             */
+    CG_ERR_WORKSPACE = -3,  /* caller workspace too small                      */
+    CG_ERR_STATE = -4,      /* call order (e.g. backward before forward)       */
+    CG_ERR_COMM = -5        /* NCCL failure                                    */
+} cg_status;
+
+/* arithmetic mode of a net (BASELINE.json north_star: bf16 mode and fp32 check mode) */
+typedef enum cg_mode {
+    CG_MODE_BF16 = 0,        /* NHWC bf16 activations, fp32 accumulate, tcgen05 convs  */
+    CG_MODE_FP32_CHECK = 1   /* everything fp32 on CUDA cores (slow, exact twin)       */
+} cg_mode;
+
+/* Layer kinds = the Keras layers the four reference builders instantiate. */
+typedef enum cg_op {
+    CG_OP_CONV = 1,      /* Conv2D            unet.py:25,54,63,121  resnet.py:28,33,40,50,96,103 */
+    CG_OP_CONVT = 2,     /* Conv2DTranspose   unet.py:66,76         resnet.py:57                 */
+    CG_OP_INORM = 3,     /* tfa InstanceNormalization unet.py:30,56,70  resnet.py:29,34,44,51,58,98 */
+    CG_OP_ACT = 4,       /* ReLU / LeakyReLU / Activation  unet.py:32,60,74,122  resnet.py:30,42,45,101 */
+    CG_OP_RPAD = 5,      /* ReflectionPadding2D resnet.py:11-23                                  */
+    CG_OP_ADD = 6,       /* Add               resnet.py:35                                       */
+    CG_OP_CONCAT = 7,    /* Concatenate [in0, in1] on channels  unet.py:68,118                   */
+    CG_OP_AVGPOOL = 8,   /* AveragePooling2D() 2x2/2   unet.py:101                               */
+    CG_OP_UPSAMPLE = 9   /* UpSampling2D() nearest x2  unet.py:109                               */
+} cg_op;
+
+typedef enum cg_act {
+    CG_ACT_NONE = 0, CG_ACT_RELU = 1, CG_ACT_LEAKY = 2, CG_ACT_TANH = 3, CG_ACT_SIGMOID = 4
+} cg_act;
+
+typedef enum cg_loss {          /* get_loss_obj, losses.py:67-81 */
+    CG_LOSS_MSE = 0, CG_LOSS_MAE = 1, CG_LOSS_BCE = 2
+} cg_loss;
+
+/*
+ * One node of the forward graph.  Tensor 0 is the network input (C = 3,
+ * unet.py:48,92 / resnet.py:65,91); layer i produces tensor i+1; in0/in1 are
+ * tensor ids.  Trainable variables are laid out in ONE flat float32 buffer in
+ * Keras `trainable_variables` order: per layer [kernel, bias] or [gamma, beta].
+ * Kernel layouts are TensorFlow's: Conv2D (kh,kw,Cin,Cout), Conv2DTranspose
+ * (kh,kw,Cout,Cin).
+ */
+typedef struct cg_layer_desc {
+    int32_t op;        /* cg_op                                                      */
+    int32_t in0;       /* input tensor id                                            */
+    int32_t in1;       /* second input (ADD, CONCAT) or -1                           */
+    int32_t cin;       /* input channels (CONV/CONVT); channels otherwise            */
+    int32_t cout;      /* output channels                                            */
+    int32_t k;         /* square kernel size                                         */
+    int32_t stride;    /* 1 or 2                                                     */
+    int32_t same;      /* 1 = padding='same' (TF asymmetric rule), 0 = 'valid'       */
+    int32_t has_bias;  /* use_bias                                                   */
+    int32_t act;       /* cg_act (ACT layers)                                        */
+    int32_t affine;    /* INORM: center=scale=True -> [gamma, beta] variables        */
+    int32_t pad;       /* RPAD amount (same on H and W)                              */
+    float eps;         /* INORM epsilon (TFA default 1e-3)                           */
+    float slope;       /* LeakyReLU alpha                                            */
+} cg_layer_desc;
+
+typedef struct cg_var_info {
+    int32_t layer;     /* index into the layer list                */
+    int32_t role;      /* 0 kernel, 1 bias, 2 gamma, 3 beta        */
+    int32_t ndim;
+    int32_t shape[4];
+    int64_t offset;    /* in floats, into the flat parameter buffer */
+} cg_var_info;
+
+typedef struct cg_adam_cfg {    /* Keras Adam, optimizers.py:14-15 (beta_2, epsilon = Keras defaults) */
+    float learning_rate, beta_1, beta_2, epsilon;
+} cg_adam_cfg;
+
+typedef struct cg_train_cfg {   /* configs/cycle.yaml:36-41 + training_config.yaml:4-11 */
+    int32_t loss;               /* cg_loss                                      */
+    float w_cycle, w_identity, w_generator, w_discriminator;
+    cg_adam_cfg adam[4];        /* order: g_AB, g_BA, d_A, d_B (model.py:68-71) */
+} cg_train_cfg;
+
+typedef struct cg_net_s* cg_net_t;
+typedef struct cg_trainer_s* cg_trainer_t;
+
+/* ---- library ------------------------------------------------------------ */
+int cg_init(int device);                 /* replaces train.py:36-43 (device selection); checks sm_100 */
+const char* cg_last_error(void);
+int cg_version(void);
+
+/* ---- model builder: replaces keras.Model(inputs, outputs) at unet.py:78,123 / resnet.py:85,105 */
+int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode, cg_net_t* out);
+void cg_net_destroy(cg_net_t net);
+int cg_net_param_floats(cg_net_t net, int64_t* n_floats);
+int cg_net_var_count(cg_net_t net, int* n_vars);                   /* len(model.trainable_variables) */
+int cg_net_var_info(cg_net_t net, int i, cg_var_info* out);
+int cg_net_out_shape(cg_net_t net, int N, int H, int W, int out_nhwc[4]);
+int cg_net_workspace_bytes(cg_net_t net, int N, int H, int W, int need_backward, size_t* bytes);
+
+/* model(x) -- Keras Model.__call__ (predict.py:32,35; model.py:93-106; unittests/test_*.py) */
+int cg_net_forward(cg_net_t net, const float* params_dev, const float* x_dev, float* y_dev,
+                   void* workspace_dev, size_t workspace_bytes, int N, int H, int W,
+                   int need_backward, void* stream);
+/* tape.gradient(loss, model.trainable_variables) for one model call (model.py:143-147):
+ * dy is dLoss/dy of the preceding cg_net_forward on the same workspace. */
+int cg_net_backward(cg_net_t net, const float* params_dev, const float* dy_dev, float* dx_dev_or_null,
+                    float* grads_dev, int accumulate, void* workspace_dev, size_t workspace_bytes,
+                    void* stream);
+
+/* ---- trainer: replaces CycleGan.train_step / validate_step (model.py:91-154) */
+int cg_trainer_create(cg_net_t g_AB, cg_net_t g_BA, cg_net_t d_A, cg_net_t d_B,
+                      const cg_train_cfg* cfg, cg_trainer_t* out);
+void cg_trainer_destroy(cg_trainer_t tr);
+int cg_trainer_workspace_bytes(cg_trainer_t tr, int B, int H, int W, size_t* bytes);
+/* params/grads/adam_m/adam_v: four flat float32 device buffers each (g_AB, g_BA, d_A, d_B). */
+int cg_trainer_bind(cg_trainer_t tr, float* const params_dev[4], float* const grads_dev[4],
+                    float* const adam_m_dev[4], float* const adam_v_dev[4],
+                    void* workspace_dev, size_t workspace_bytes);
+/* metrics6_dev: gAB_loss, gBA_loss, dA_loss, dB_loss, dA_acc, dB_acc (model.py:126-133), device floats */
+int cg_validate_step(cg_trainer_t tr, const float* real_a_dev, const float* real_b_dev,
+                     int B, int H, int W, float* metrics6_dev, void* stream);
+int cg_train_step(cg_trainer_t tr, const float* real_a_dev, const float* real_b_dev,
+                  int B, int H, int W, float* metrics6_dev, void* stream);
+/* the two halves of train_step, exposed for tests (per-layer gradient parity) */
+int cg_trainer_compute_gradients(cg_trainer_t tr, const float* real_a_dev, const float* real_b_dev,
+                                 int B, int H, int W, float* metrics6_dev, void* stream);
+int cg_trainer_apply_gradients(cg_trainer_t tr, void* stream);      /* 4x optimizer.apply_gradients, model.py:149-153 */
+int cg_trainer_get_iterations(cg_trainer_t tr, int64_t iters[4]);   /* optimizer.iterations (model.py:314-315)  */
+int cg_trainer_set_iterations(cg_trainer_t tr, const int64_t iters[4]);
+/* pointer to an image the last step produced, for tests: 0 fake_b 1 same_b 2 fake_a 3 same_a 4 cycled_a 5 cycled_b */
+int cg_trainer_fetch_image(cg_trainer_t tr, int which, float* out_dev, void* stream);
+
+/* ---- data parallel (new functionality; the reference is single-device, train.py:36-43) */
+int cg_comm_unique_id(char id_out[128]);
+int cg_trainer_comm_init(cg_trainer_t tr, const char id[128], int rank, int world);
+
+/* ---- instrumentation for bench.py: CUDA-event timing of one kernel family */
+int cg_prof_enable(int enable);                 /* brackets every tensor-core conv launch with events */
+int cg_prof_read(double* total_ms, int64_t* launches, double* total_flops);  /* syncs, resets */
+int cg_launch_count(int64_t* launches, int reset);  /* kernels launched by this library */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CYCLEGAN_B200_H */

@@ -1,0 +1,154 @@
+"""CPU tests of the host side: reference-compatible builders (KeyError behaviour), IR vs oracle
+variable lists, and that the C-ABI library loads and exports every symbol the header declares."""
+import ctypes
+import os
+import re
+from copy import deepcopy
+
+import numpy as np
+import pytest
+
+from cyclegan_cat_b200 import _lib, ir
+from cyclegan_cat_b200.cyclegan.model import accuracy, create_model
+from cyclegan_cat_b200.cyclegan.optimizers import get_optimizer
+from cyclegan_cat_b200.cyclegan.losses import get_loss_obj
+from cyclegan_cat_b200.cyclegan.resnet import resnet_generator, simple_discriminator
+from cyclegan_cat_b200.cyclegan.unet import strided_unet, unet_generator
+from cyclegan_cat_b200.transform.data_load import normalize
+from oracle import models as om
+from tests import common as C
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_incomplete_unet_model_config():
+    """unittests/test_unet.py:41-56."""
+    for field in ['filters', 'kernels', 'expansion', 'normalization', 'dropout', 'output_channels',
+                  'final_activation']:
+        cfg = deepcopy(C.FIX_UNET)
+        del cfg[field]
+        with pytest.raises(KeyError):
+            unet_generator(cfg)
+
+
+def test_incomplete_strided_model_config():
+    """unittests/test_unet.py:59-72 (strided_unet must NOT require expansion / dropout)."""
+    for field in ['filters', 'kernels', 'normalization', 'output_channels', 'final_activation']:
+        cfg = deepcopy(C.FIX_UNET)
+        del cfg[field]
+        with pytest.raises(KeyError):
+            strided_unet(cfg)
+    cfg = deepcopy(C.FIX_UNET)
+    del cfg['expansion'], cfg['dropout']
+    strided_unet(cfg)
+
+
+def test_create_model_dispatch_and_unknown_type():
+    """model.py:22-32."""
+    assert create_model(C.FIX_SIMPLE).name == "simple_discriminator"
+    assert create_model(C.UNET_G).name == "unet_generator"
+    with pytest.raises(KeyError):
+        create_model(dict(type="nope"))
+    with pytest.raises(KeyError):
+        resnet_generator({})
+    with pytest.raises(KeyError):
+        simple_discriminator(dict(filters=[8], kernels=[4]))
+
+
+@pytest.mark.parametrize("cfg", [C.UNET_G, C.UNET_D, C.SIMPLE_D4, C.RESNET64, C.FIX_UNET, C.SMALL_STRIDED])
+def test_variable_lists_match_oracle(cfg):
+    """Keras trainable_variables order/shape/initializer agree between the IR builders and the oracle."""
+    m = create_model(cfg)
+    o = om.create_model(cfg)
+    assert m.graph.var_specs() == o.var_specs
+    assert [v.shape for v in m.trainable_variables] == [tuple(v.shape) for v in o.variables]
+    assert m.n_params == sum(v.numel() for v in o.variables)
+
+
+def test_flops_match_survey_tables():
+    g = create_model(C.RESNET64).graph
+    assert abs(g.flops(256, 256) / 1e9 - 99.103) < 1e-2
+    assert abs(create_model(C.SIMPLE_D4).graph.flops(256, 256) / 1e9 - 3.322) < 1e-2
+    assert abs(create_model(C.UNET_G).graph.flops(256, 256) / 1e9 - 23.467) < 1e-2
+    assert abs(create_model(C.UNET_D).graph.flops(256, 256) / 1e9 - 18.432) < 1e-2
+
+
+def test_optimizer_and_loss_factories():
+    """optimizers.py:5-24, losses.py:67-81."""
+    o = get_optimizer(dict(name="adam", learning_rate=2e-4, beta_1=0.5))
+    assert (o.learning_rate, o.beta_1, o.beta_2, o.epsilon) == (2e-4, 0.5, 0.999, 1e-7)
+    with pytest.raises(ValueError):
+        get_optimizer(dict(name="nadam", learning_rate=1e-3))
+    with pytest.raises(KeyError):
+        get_optimizer(dict(name="adam", learning_rate=1e-3))          # beta_1 is mandatory for adam
+    assert get_loss_obj("mse").kind == 0 and get_loss_obj("bce").kind == 2
+    with pytest.raises(KeyError):
+        get_loss_obj("hinge")
+
+
+def test_normalize_and_accuracy():
+    """data_load.py:31-34, model.py:35-54."""
+    x = np.array([0, 127.5, 255], np.uint8)
+    assert np.allclose(normalize(x), [-1.0, 127 / 127.5 - 1, 1.0])
+    assert normalize(x).dtype == np.float32
+    assert accuracy(np.array([0.9, 0.2]), np.array([0.1, 0.7])) == np.float32(0.5)
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    header = open(os.path.join(ROOT, "include", "cyclegan_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|void|const char\*)\s+(cg_[a-z0-9_]+)\s*\(", header, re.M))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(built_lib, name), name
+    assert built_lib.cg_version() >= 100
+
+
+def test_struct_layouts_match_header(built_lib):
+    assert ctypes.sizeof(ir.LayerDesc) == 14 * 4
+    assert ctypes.sizeof(ir.VarInfo) == 40
+    assert ctypes.sizeof(ir.TrainCfg) == 5 * 4 + 4 * 16
+
+
+def test_native_planner_agrees_with_host(built_lib):
+    """cg_net_create / var_info / out_shape are pure host planning: they run without a GPU."""
+    for cfg, out in ((C.RESNET64, (2, 64, 96, 3)), (C.SIMPLE_D4, (2, 4, 6, 1)), (C.UNET_G, (2, 64, 96, 3)),
+                     (C.SMALL_STRIDED, (2, 64, 96, 3))):
+        m = create_model(cfg)
+        h = m.handle()
+        n = ctypes.c_int()
+        assert built_lib.cg_net_var_count(h, ctypes.byref(n)) == 0 and n.value == len(m.trainable_variables)
+        for i, v in enumerate(m.trainable_variables):
+            info = ir.VarInfo()
+            assert built_lib.cg_net_var_info(h, i, ctypes.byref(info)) == 0
+            assert tuple(info.shape[:info.ndim]) == v.shape and info.offset == v.offset and info.role == v.role
+        assert m.out_shape(2, 64, 96) == out
+        nbytes = ctypes.c_size_t()
+        assert built_lib.cg_net_workspace_bytes(h, 2, 64, 96, 1, ctypes.byref(nbytes)) == 0 and nbytes.value > 0
+
+
+def test_native_rejects_bad_graphs_and_shapes(built_lib):
+    h = ctypes.c_void_p()
+    bad = (ir.LayerDesc * 1)(ir.LayerDesc(ir.OP_CONV, 0, -1, 3, 8, 3, 3, 1, 1, 0, 0, 0, 1e-3, 0.2))   # stride 3
+    assert built_lib.cg_net_create(bad, 1, 0, ctypes.byref(h)) == -1
+    assert b"geometry" in built_lib.cg_last_error()
+    m = create_model(C.UNET_G)
+    out = (ctypes.c_int * 4)()
+    assert built_lib.cg_net_out_shape(m.handle(), 1, 100, 100, ctypes.byref(out)) == -1    # 100 % 8 != 0
+    assert built_lib.cg_net_create(None, 0, 0, ctypes.byref(h)) == -1
+
+
+def test_no_gpu_means_loud_failure(built_lib):
+    """The product path has no CPU fallback: without a device, calling a model raises."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = create_model(C.FIX_SIMPLE)
+    with pytest.raises(_lib.NativeError):
+        m(np.ones((1, 32, 32, 3)))
+
+
+def test_product_package_does_not_import_oracle():
+    import subprocess, sys
+    code = "import sys; import cyclegan_cat_b200.cyclegan.model, cyclegan_cat_b200.runtime; " \
+           "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'"
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
