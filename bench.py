@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""Benchmark of the CycleGAN train step (BASELINE.json metric: train images/sec at 256x256).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C3|C2|C2s|C1] [--mode bf16|fp32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...       # the CPU restatement of the reference (torch-CPU oracle), host cores
+
+One "step" = one full CycleGan.train_step (6 generator forwards, 4 discriminator forwards, the combined backward,
+4 Adam updates) on one synthetic batch.  `value` = (A,B) pairs per second over all ranks with the inputs already in
+HBM; `e2e` = the same through the public API with pinned HOST inputs (H2D inside the timed region) and a D2H read
+of the 6 metrics every step.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+RESNET64 = dict(type="resnet_generator", filters=64)
+SIMPLE_D4 = dict(type="simple_discriminator", filters=[64, 128, 256, 512], kernels=[4, 4, 4, 4],
+                 normalization="instancenorm")
+SIMPLE_D3 = dict(type="simple_discriminator", filters=[64, 128, 256], kernels=[4, 4, 4], normalization="instancenorm")
+UNET_G = dict(type="unet_generator", filters=[16, 32, 64, 128], kernels=[4, 4, 4, 4], output_channels=3,
+              expansion="upsample", normalization="instancenorm", dropout=False, final_activation="tanh")
+UNET_D = dict(type="unet_generator", filters=[16, 32, 64], kernels=[7, 5, 3], output_channels=1,
+              expansion="upsample", normalization="instancenorm", dropout=False, final_activation="sigmoid")
+STRIDED7 = dict(type="strided_unet", filters=[64, 128, 256, 512, 512, 512, 512], kernels=[4] * 7, output_channels=3,
+                normalization="instancenorm", final_activation="tanh")
+WORKLOADS = {
+    "C1": dict(gen=UNET_G, disc=SIMPLE_D3, size=128, batch=1, name="C1: unet_generator(cycle.yaml) + simple_discriminator[64,128,256], 128x128"),
+    "C2": dict(gen=UNET_G, disc=UNET_D, size=256, batch=4, name="C2: cycle.yaml verbatim (U-Net G + U-Net PatchGAN D), 256x256"),
+    "C2s": dict(gen=STRIDED7, disc=UNET_D, size=256, batch=4, name="C2s: strided_unet-7 G + U-Net PatchGAN D, 256x256"),
+    "C3": dict(gen=RESNET64, disc=SIMPLE_D4, size=256, batch=16, name="C3: resnet_generator{filters:64} (9 blocks) + simple_discriminator[64,128,256,512] k4, 256x256"),
+}
+LOSS_WEIGHTS = dict(cycle=2.0, identity=0.5, generator=1.0, discriminator=0.5)
+ADAM = dict(name="adam", learning_rate=2e-4, beta_1=0.5)
+METRIC = "cyclegan_train_pairs_per_sec_256x256"
+UNIT = "images/s"
+
+
+def synthetic_batch(batch, size, rank=0):
+    a = np.random.RandomState(1234 + 2 * rank).uniform(-1.0, 1.0, size=(batch, size, size, 3)).astype(np.float32)
+    b = np.random.RandomState(1235 + 2 * rank).uniform(-1.0, 1.0, size=(batch, size, size, 3)).astype(np.float32)
+    return a, b
+
+
+def step_flops(gen_graph, disc_graph, size):
+    """Algorithmic FLOPs per (a,b) pair: 18 F_G + 14 F_D - 4 f_G0 - 4 f_D0."""
+    return 18 * gen_graph.flops(size, size) + 14 * disc_graph.flops(size, size) \
+        - 4 * gen_graph.first_layer_flops(size, size) - 4 * disc_graph.first_layer_flops(size, size)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), hbm=float(d["hbm_gbs"]),
+                    source="measured (MEASURED_PEAKS.json, bf16_tflops_sustained: kernel timed inside a long step)")
+    return dict(tflops=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop = index, [], set(), None, threading.Event()
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                     "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80}
+            while not self._stop.is_set():
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+                time.sleep(0.1)
+        except Exception as e:       # NVML missing: record that instead of failing the bench
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons))
+
+
+def bunch(**kw):
+    from cyclegan_cat_b200.model_processing.load_model import Bunch
+    return Bunch(**kw)
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the restated reference (oracle) on the host cores
+# ---------------------------------------------------------------------------------------------
+def time_oracle(wl, steps, warmup, sample_batch=1, budget_s=150.0):
+    import torch
+    from oracle.train import OracleCycleGan
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    o = OracleCycleGan(wl["gen"], wl["disc"], loss="mse", loss_weights=LOSS_WEIGHTS, g_opt=ADAM, d_opt=ADAM)
+    a, b = synthetic_batch(sample_batch, wl["size"])
+    t0 = time.perf_counter()
+    o.train_step(a, b)                      # first step also pays one-time oneDNN primitive creation
+    first = time.perf_counter() - t0
+    warm_done = 1
+    while warm_done < warmup and (time.perf_counter() - t0) < budget_s * 0.3:
+        o.train_step(a, b)
+        warm_done += 1
+    times = []
+    t_start = time.perf_counter()
+    for _ in range(steps):
+        t1 = time.perf_counter()
+        o.train_step(a, b)
+        times.append(time.perf_counter() - t1)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    med = float(np.median(times))
+    return dict(value=sample_batch / med, ms_per_step=med * 1e3, cores=cores, steps_done=len(times),
+                warmup_done=warm_done, first_step_s=first,
+                sample=f"{wl['name']}, batch {sample_batch}, {len(times)} timed steps (median), fp32 torch-CPU "
+                       f"restatement of the reference (oneDNN), not TensorFlow")
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = time_oracle(wl, args.steps, args.warmup)
+    line = dict(metric=METRIC, value=r["value"], unit=UNIT, n_gpus=args.gpus, steps=r["steps_done"],
+                warmup=r["warmup_done"], ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload=wl["name"], image_size=wl["size"], batch_per_step=1,
+                            note="reference = torch-CPU restatement of cyclegan/model.py:136-154 (TensorFlow is not "
+                                 "installable here); one step = one train_step on a batch-1 sample of the workload"),
+                cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"]),
+                e2e=dict(value=r["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_gpu(args, wl):
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from cyclegan_cat_b200 import _lib
+    from cyclegan_cat_b200.cyclegan.model import CycleGan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B, S = args.batch or wl["batch"], wl["size"]
+
+    mc = bunch(name="bench", new=True, location="/tmp/cg_b200_bench", generator=dict(wl["gen"]),
+               discriminator=dict(wl["disc"]), loss="mse", loss_weights=dict(LOSS_WEIGHTS))
+    tc = bunch(epochs=1, batch_size=B, image_size=S, g_opt=dict(ADAM), d_opt=dict(ADAM),
+               summary=dict(samples=1, images=5, model=20))
+    gan = CycleGan(mc, tc, mode=args.mode)
+    for i, n in enumerate((gan.g_AB, gan.g_BA, gan.d_A, gan.d_B)):
+        n.initialize(42 + i)                                  # SURVEY 8d seeds
+    gan.prepare(B, S, S)
+    if world > 1:
+        gan.enable_data_parallel()
+
+    lib = _lib.load()
+    a_np, b_np = synthetic_batch(B, S, rank)
+    a_dev, b_dev = torch.from_numpy(a_np).cuda(), torch.from_numpy(b_np).cuda()
+    a_pin, b_pin = torch.from_numpy(a_np).pin_memory(), torch.from_numpy(b_np).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput -----------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        gan.train_step(a_dev, b_dev)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib.cg_launch_count(None, 1)
+    lib.cg_prof_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        m = gan.train_step(a_dev, b_dev)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    launches = ctypes.c_int64()
+    lib.cg_launch_count(ctypes.byref(launches), 0)
+    pms, pl, pfl = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
+    lib.cg_prof_read(ctypes.byref(pms), ctypes.byref(pl), ctypes.byref(pfl))
+    lib.cg_prof_enable(0)
+    last_metrics = {k: float(v) for k, v in m.items()}
+
+    # ---- end to end through the public API: pinned host inputs, metrics read back every step ---------
+    for _ in range(2):
+        gan.train_step(a_pin, b_pin)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        mm = gan.train_step(a_pin, b_pin)
+        _ = [float(v) for v in mm.values()]                  # D2H of the 6 metrics (what model.py:301 does)
+    e3.record()
+    barrier()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    fl_pair = step_flops(gan.g_AB.graph, gan.d_A.graph, S)
+    ms_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    step_tflops = fl_pair * B / (ms_step * 1e-3) / 1e12
+    roof = dict(bound="tensor", kernel="conv_tc_kernel + wgrad_tc_kernel (tcgen05 3x3 convs of the residual trunk: fwd, dgrad, wgrad)",
+                achieved=(pfl.value / (pms.value * 1e-3) / 1e12) if pms.value > 0 else None, peak=pk["tflops"],
+                unit="TFLOP/s", frac=None, traffic=None, launches=int(pl.value),
+                avg_launch_ms=(pms.value / pl.value) if pl.value else None,
+                share_of_step=(pms.value / ms_total) if ms_total > 0 else None, peak_source=pk["source"],
+                whole_step_tflops=step_tflops, whole_step_frac=step_tflops / pk["tflops"])
+    if roof["achieved"] is not None:
+        roof["frac"] = roof["achieved"] / pk["tflops"]
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.mode,
+                data="synthetic",
+                config=dict(workload=wl["name"], image_size=S, batch_per_gpu=B, global_batch=B * world,
+                            parallelism=f"dp{world}", pairs_per_step=B * world,
+                            individual_images_per_sec=2 * value, flops_per_pair=fl_pair,
+                            l2="no flush needed: one step streams tens of GB of activations (>> 126 MB L2)",
+                            weights="random init N(0,0.02), seeds 42-45", last_metrics=last_metrics),
+                roofline=roof, clocks=clocks, gpu_launches=int(launches.value),
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(2 * a_np.nbytes),
+                         d2h_bytes_per_step=24, ms_per_step=ms_e2e / args.steps))
+    if not args.no_cpu_baseline:
+        c1 = WORKLOADS[args.workload]
+        r = time_oracle(c1, steps=2, warmup=1, budget_s=60.0)
+        line["cpu_baseline"] = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"],
+                                    ms_per_step=r["ms_per_step"])
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_gpu(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,5 +1,6 @@
 // C ABI of libcyclegan_b200.so: library init, model builder, single-net forward/backward.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -140,6 +141,26 @@ extern "C" int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode
             net->has_buffer[i + 1] = 0;
         }
     }
+    // tensor-core layers (bf16 mode): 3x3 stride-1 'valid' convs with Cin % 128 == 0 and Cout % 64 == 0 whose output
+    // feeds exactly one instance norm (its backward writes the zero-bordered dY the TMA loads expect)
+    size_t pk = 0;
+    const char* no_tc = getenv("CG_DISABLE_TC");     // test hook: force the CUDA-core convs in bf16 mode
+    if (mode == CG_MODE_BF16 && !(no_tc && no_tc[0] == '1')) {
+        for (int i = 0; i + 1 < n_layers; ++i) {
+            LayerInfo& L = net->layers[i];
+            const cg_layer_desc& d = L.d;
+            const int bn = d.cout < 256 ? d.cout : 256;
+            if (d.op == CG_OP_CONV && d.k == 3 && d.stride == 1 && !d.same && d.cin % 128 == 0 && d.cout % 64 == 0 &&
+                d.cout % bn == 0 && (d.cin <= 256 || d.cin % 256 == 0) && net->n_consumers[i + 1] == 1 &&
+                net->layers[i + 1].d.op == CG_OP_INORM && net->layers[i + 1].d.in0 == i + 1) {
+                L.tc = true;
+                const size_t bytes = align_up((size_t)d.k * d.k * d.cin * d.cout * 2, 1024);
+                L.pk_f = (long long)pk; pk += bytes;
+                L.pk_d = (long long)pk; pk += bytes;
+            }
+        }
+    }
+    net->packed_bytes = pk;
     *out = net;
     return CG_OK;
 }
@@ -178,7 +199,7 @@ extern "C" int cg_net_out_shape(cg_net_t net, int N, int H, int W, int out[4]) {
 }
 
 // workspace of a single-net call: [activations | gradient arena | dy/dx staging in activation dtype]
-struct SingleLayout { size_t act, arena, dy, dx, total; };
+struct SingleLayout { size_t act, arena, dy, dx, packed, total; };
 static int single_layout(const cg_net_s* net, CallCtx* ctx, int N, int H, int W, bool bwd, SingleLayout* lay) {
     CG_TRY(net_plan(net, N, H, W, bwd, ctx));
     size_t es = net->elem_size();
@@ -186,7 +207,8 @@ static int single_layout(const cg_net_s* net, CallCtx* ctx, int N, int H, int W,
     lay->arena = align_up(ctx->act_bytes, 256);
     lay->dy = lay->arena + align_up(ctx->grad_bytes, 256);
     lay->dx = lay->dy + (bwd ? align_up((size_t)N * ctx->sample_elems(net->out_tensor()) * es, 256) : 0);
-    lay->total = lay->dx + (bwd ? align_up((size_t)N * ctx->sample_elems(0) * es, 256) : 0);
+    lay->packed = align_up(lay->dx + (bwd ? align_up((size_t)N * ctx->sample_elems(0) * es, 256) : 0), 1024);
+    lay->total = lay->packed + net->packed_bytes;
     return CG_OK;
 }
 
@@ -223,6 +245,9 @@ extern "C" int cg_net_forward(cg_net_t net, const float* params, const float* x,
     sc->ctx.base = (char*)ws + sc->lay.act;
     sc->ctx.arena = (char*)ws + sc->lay.arena;
     sc->ctx.ext_input = nullptr;
+    sc->ctx.packed = (char*)ws + sc->lay.packed;
+    CG_TRY(net_bind(&sc->ctx));
+    CG_TRY(net_pack(net, params, sc->ctx.packed, st));
     const int tout = net->out_tensor();
     size_t nin = (size_t)N * sc->ctx.sample_elems(0), nout = (size_t)N * sc->ctx.sample_elems(tout);
     if (net->mode == CG_MODE_BF16) {

@@ -1,0 +1,508 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution kernels for sm_100a (bf16 in, fp32 accumulate).
+//
+//   conv_tc_kernel   forward conv and data-gradient (a conv with the transposed weights):
+//                    D[128 pixels x BN channels] += sum over (tap, 64-channel chunk) A_tap[128x64] * B_tap[BNx64]^T
+//                    A tiles are plain TMA box loads of the NHWC activation (one box per filter tap, shifted
+//                    coordinates; zero padding comes from TMA out-of-bounds fill), B tiles are TMA loads of the
+//                    packed bf16 weights.  Both operands K-major, SWIZZLE_128B.  Persistent CTAs, 4-5 stage
+//                    smem ring, double-buffered TMEM accumulator, warp-specialised:
+//                    warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 2-5 = epilogue.
+//   wgrad_tc_kernel  weight gradient dW[tap][ci][co] = sum_pixels X[pixel+tap][ci] * dY[pixel][co]:
+//                    the SAME activation tiles, now used as MN-major operands (K = pixels), split-K over the
+//                    pixel range, fp32 vector reductions (red.global.add.v4.f32) into the float32 gradient.
+#include <cuda.h>
+
+#include "conv_tc.h"
+#include "prof.h"
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Spin on a phase parity.  A bounded spin + trap turns a protocol bug into an error instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; !ok; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by ONE thread for the whole CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier when all MMAs issued so far by this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = lane, register = column)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): SWIZZLE_128B, version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);              // start address, bits [0,14)
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;     // leading byte offset, bits [16,30)
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;     // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                               // layout type: SWIZZLE_128B
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): BF16 x BF16 -> F32, dense
+static inline uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    uint32_t d = 0;
+    d |= 1u << 4;                       // c_format = F32
+    d |= 1u << 7;                       // a_format = BF16
+    d |= 1u << 10;                      // b_format = BF16
+    d |= (uint32_t)a_mn_major << 15;
+    d |= (uint32_t)b_mn_major << 16;
+    d |= (uint32_t)(N >> 3) << 17;
+    d |= (uint32_t)(M >> 4) << 24;
+    return d;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
+static constexpr int TC_THREADS = 192;        // 6 warps: TMA, MMA, 4 x epilogue
+static constexpr int A_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
+static constexpr int TMEM_COLS = 512;
+
+// ------------------------------------------------------------------------------------------
+// forward / data-gradient kernel
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               bf16* __restrict__ out, const float* __restrict__ bias, const TcConvArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t stage_bytes = A_TILE_BYTES + (uint32_t)a.bn * 128u;
+    const int S = a.stages;
+    const uint32_t bar0 = smem0 + S * stage_bytes;          // full[S], empty[S], tfull[2], tempty[2], tmem ptr
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (S + s); };
+    auto tfull = [&](int i) { return bar0 + 8u * (2 * S + i); };
+    auto tempty = [&](int i) { return bar0 + 8u * (2 * S + 2 + i); };
+    const uint32_t tmem_slot = bar0 + 8u * (2 * S + 4);
+    volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+        for (int s = 0; s < S; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int total_tiles = a.nb * a.tiles_per_img * a.n_blocks_n;
+    const int ksteps = a.n_taps * a.cchunks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int nblk = t % a.n_blocks_n, mt = t / a.n_blocks_n;
+                const int img = a.n0 + mt / a.tiles_per_img, ti = mt % a.tiles_per_img;
+                const int w0 = (ti % a.tiles_w) * a.Wb, h0 = (ti / a.tiles_w) * a.Hb;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const int tap = ks / a.cchunks, cc = ks - tap * a.cchunks;
+                    mbar_wait(empty(s), ph ^ 1u);
+                    mbar_expect_tx(full(s), stage_bytes);
+                    const uint32_t sa = smem0 + s * stage_bytes;
+                    tma_load_4d(sa, &mapA, full(s), cc * 64, w0 + a.dw[tap], h0 + a.dh[tap], img);
+                    tma_load_2d(sa + A_TILE_BYTES, &mapB, full(s), cc * 64, tap * a.b_rows_per_tap + nblk * a.bn);
+                    if (++s == S) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(tempty(acc), acc_ph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(full(s), ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem0 + s * stage_bytes;
+                    const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+                    const uint64_t bdesc = make_smem_desc(sa + A_TILE_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)     // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle row
+                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), a.idesc,
+                                  (uint32_t)((ks | k) != 0));
+                    umma_commit(empty(s));
+                    if (++s == S) { s = 0; ph ^= 1u; }
+                }
+                umma_commit(tfull(acc));
+            }
+        }
+    } else {
+        const int q = warp & 3;                   // TMEM lane quarter this warp may read
+        int it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+            const int nblk = t % a.n_blocks_n, mt = t / a.n_blocks_n;
+            const int img = mt / a.tiles_per_img, ti = mt % a.tiles_per_img;      // img relative to the output base
+            const int w0 = (ti % a.tiles_w) * a.Wb, h0 = (ti / a.tiles_w) * a.Hb;
+            const int lin = h0 * a.out_P + w0 + q * 32 + lane;
+            const int oh = lin / a.out_P, ow = lin - oh * a.out_P;
+            const bool valid = ow < a.out_wvalid && oh < a.out_hvalid;
+            bf16* dst = out + (((size_t)img * a.out_H + oh) * a.out_W + ow) * a.Cout + (size_t)nblk * a.bn;
+            mbar_wait(tfull(acc), acc_ph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < a.bn; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)c0, v);
+                if (valid) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
+                        if (bias) { x0 += __ldg(bias + nblk * a.bn + c0 + 2 * j); x1 += __ldg(bias + nblk * a.bn + c0 + 2 * j + 1); }
+                        pk[j] = pack_bf16x2(x0, x1);
+                    }
+                    uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) d4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty(acc));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight-gradient kernel.  One CTA = one (tap, 128 input channels, BN output channels, K split).
+// smem stage: [2 boxes X (64ch x 64px)] [BN/64 boxes dY (64ch x 64px)], each box 8 KB, MN-major.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDY,
+                float* __restrict__ dw, const TcWgradArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nb_boxes = a.bn / 64;
+    const uint32_t stage_bytes = (uint32_t)(2 + nb_boxes) * 8192u;
+    const int S = a.stages;
+    const uint32_t bar0 = smem0 + S * stage_bytes;
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (S + s); };
+    const uint32_t tfull = bar0 + 8u * (2 * S);
+    const uint32_t tmem_slot = bar0 + 8u * (2 * S + 1);
+    volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapX);
+        tma_prefetch_desc(&mapDY);
+        for (int s = 0; s < S; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    // decode the work unit
+    int u = blockIdx.x;
+    const int split = u % a.splits; u /= a.splits;
+    const int coblk = u % a.co_blocks; u /= a.co_blocks;
+    const int ciblk = u % a.ci_blocks; u /= a.ci_blocks;
+    const int tap = u;
+    const int total_chunks = a.nb * a.chunks_per_img;
+    const int per = (total_chunks + a.splits - 1) / a.splits;
+    const int q_begin = split * per;
+    const int q_end = min(total_chunks, q_begin + per);
+    const int nq = q_end - q_begin;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int q = q_begin; q < q_end; ++q) {
+                const int img = a.n0 + q / a.chunks_per_img, r = q % a.chunks_per_img;
+                const int w0 = (r % a.chunks_w) * a.Wk, h0 = (r / a.chunks_w) * a.Hk;
+                mbar_wait(empty(s), ph ^ 1u);
+                mbar_expect_tx(full(s), stage_bytes);
+                const uint32_t sa = smem0 + s * stage_bytes;
+                for (int b = 0; b < 2; ++b)
+                    tma_load_4d(sa + b * 8192u, &mapX, full(s), ciblk * 128 + b * 64, w0 + a.dw[tap], h0 + a.dh[tap], img);
+                for (int b = 0; b < nb_boxes; ++b)
+                    tma_load_4d(sa + (2 + b) * 8192u, &mapDY, full(s), coblk * a.bn + b * 64, w0 + a.dy_off, h0 + a.dy_off,
+                                img - a.n0);
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && nq > 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int i = 0; i < nq; ++i) {
+                mbar_wait(full(s), ph);
+                tc_fence_after();
+                const uint32_t sa = smem0 + s * stage_bytes;
+                // MN-major canonical layout: 64 channels contiguous (128 B), pixels (K) at 128 B, 8-pixel groups at
+                // SBO = 1024 B, next 64-channel group at LBO = 8192 B.  One MMA consumes K = 16 pixels = 2048 B.
+                const uint64_t adesc = make_smem_desc(sa, 8192, 1024);
+                const uint64_t bdesc = make_smem_desc(sa + 2 * 8192u, 8192, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), a.idesc,
+                              (uint32_t)((i | k) != 0));
+                umma_commit(empty(s));
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
+            umma_commit(tfull);
+        }
+    } else if (nq > 0) {
+        const int q = warp & 3;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        const int ci = ciblk * 128 + q * 32 + lane;
+        float* dst = dw + ((size_t)tap * a.Cin + ci) * a.Cout + (size_t)coblk * a.bn;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int c0 = 0; c0 < a.bn; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + 4 * j),
+                             "f"(__uint_as_float(v[4 * j])), "f"(__uint_as_float(v[4 * j + 1])),
+                             "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3]))
+                             : "memory");
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight packing: float32 HWIO -> bf16 [tap][Cout][Cin] (forward B operand) and bf16 [tap][Cin][Cout]
+// (data-gradient B operand; same order as HWIO)
+// ------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restrict__ wf, bf16* __restrict__ wd, int taps,
+                                    int Cin, int Cout) {
+    const size_t n = (size_t)taps * Cin * Cout;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int co = (int)(i % Cout);
+        const size_t r = i / Cout;
+        const int ci = (int)(r % Cin);
+        const int tap = (int)(r / Cin);
+        const bf16 v = __float2bfloat16(w[i]);
+        wd[i] = v;
+        wf[((size_t)tap * Cout + co) * Cin + ci] = v;
+    }
+}
+
+int tc_pack_weights(const float* w, bf16* wf, bf16* wd, int taps, int Cin, int Cout, cudaStream_t st) {
+    size_t n = (size_t)taps * Cin * Cout;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    pack_weights_kernel<<<blocks, 256, 0, st>>>(w, wf, wd, taps, Cin, Cout);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: tensor maps and launches
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+int tc_make_map_4d(CUtensorMap* map, const void* base, int C, int W, int H, int N, int box_w, int box_h) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { cg_set_error("cuTensorMapEncodeTiled is not available from the driver"); return CG_ERR_CUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        cg_set_error("cuTensorMapEncodeTiled(4d C=%d W=%d H=%d N=%d box %dx%d) failed: %d", C, W, H, N, box_w, box_h, (int)r);
+        return CG_ERR_CUDA;
+    }
+    return CG_OK;
+}
+
+int tc_make_map_2d(CUtensorMap* map, const void* base, int cols, int rows, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { cg_set_error("cuTensorMapEncodeTiled is not available from the driver"); return CG_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        cg_set_error("cuTensorMapEncodeTiled(2d cols=%d rows=%d box %d) failed: %d", cols, rows, box_rows, (int)r);
+        return CG_ERR_CUDA;
+    }
+    return CG_OK;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+    if (!g_num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+int tc_conv_stages(int bn) {
+    int stage = A_TILE_BYTES + bn * 128;
+    int s = (227 * 1024 - 2048) / stage;
+    return s > 6 ? 6 : s;
+}
+
+int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, bf16* out, const float* bias, TcConvArgs a,
+                   double flops, cudaStream_t st) {
+    a.stages = tc_conv_stages(a.bn);
+    a.idesc = make_idesc(128, a.bn, 0, 0);
+    const size_t smem = (size_t)a.stages * (A_TILE_BYTES + a.bn * 128) + 1024 + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int total = a.nb * a.tiles_per_img * a.n_blocks_n;
+    int grid = total < num_sms() ? total : num_sms();
+    int pi = prof_begin(st);
+    conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(*mapA, *mapB, out, bias, a);
+    prof_end(pi, st, flops);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+int tc_wgrad_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* dw, TcWgradArgs a, double flops,
+                    cudaStream_t st) {
+    const int stage = (2 + a.bn / 64) * 8192;
+    int s = (227 * 1024 - 2048) / stage;
+    a.stages = s > 6 ? 6 : s;
+    a.idesc = make_idesc(128, a.bn, 1, 1);
+    const int units = a.n_taps * a.ci_blocks * a.co_blocks;
+    const int total_chunks = a.nb * a.chunks_per_img;
+    int splits = num_sms() / units;
+    if (splits < 1) splits = 1;
+    if (splits > total_chunks) splits = total_chunks;
+    a.splits = splits;
+    const size_t smem = (size_t)a.stages * stage + 1024 + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    int pi = prof_begin(st);
+    wgrad_tc_kernel<<<units * splits, TC_THREADS, smem, st>>>(*mapX, *mapDY, dw, a);
+    prof_end(pi, st, flops);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}

@@ -21,7 +21,8 @@ template <typename T> int k_in_apply(const T* x, T* y, const float* stats, const
                                      int act, float slope, int N, int P, int C, cudaStream_t st);
 template <typename T> int k_in_bwd(const T* x, const T* dy, T* dx, const float* stats, const float* gamma,
                                    const float* beta, float* dgamma, float* dbeta, float* scratch, int act,
-                                   float slope, int N, int P, int C, int accumulate, cudaStream_t st);
+                                   float slope, int N, int P, int C, int accumulate, cudaStream_t st,
+                                   int halo = 0, int W = 0);
 
 // ---- elementwise / data movement ----
 template <typename T> int k_act_fwd(const T* x, T* y, size_t n, int act, float slope, cudaStream_t st);

@@ -186,6 +186,45 @@ __global__ void in_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
     }
 }
 
+// same, but dx is a zero-bordered buffer [N][H+2*halo][W+2*halo][C] (the layout the tensor-core data-gradient and
+// weight-gradient kernels read with TMA); this kernel writes the zero border too.
+template <typename T, int VEC>
+__global__ void in_bwd_apply_halo_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
+                                         const float* __restrict__ stats, const float* __restrict__ sums,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                         float slope, int H, int W, int C, int halo, float invP) {
+    const int n = blockIdx.y;
+    const int Cv = C / VEC, Hp = H + 2 * halo, Wp = W + 2 * halo;
+    const float* st = stats + (size_t)n * C * 2;
+    const float* sm = sums + (size_t)n * C * 2;
+    const size_t total = (size_t)Hp * Wp * Cv;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % Cv);
+        size_t r = i / Cv;
+        const int wp = (int)(r % Wp), hp = (int)(r / Wp);
+        const int h = hp - halo, w = wp - halo, c = cv * VEC;
+        float o[VEC];
+        if (h >= 0 && h < H && w >= 0 && w < W) {
+            const size_t e = (((size_t)n * H + h) * W + w) * C + c;
+            float v[VEC], g[VEC];
+            load_vec<T, VEC>(x + e, v);
+            load_vec<T, VEC>(dy + e, g);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                float mean = st[(c + j) * 2], rstd = st[(c + j) * 2 + 1];
+                float ga = gamma ? gamma[c + j] : 1.f, be = beta ? beta[c + j] : 0.f;
+                float xh = (v[j] - mean) * rstd;
+                float gg = g[j] * act_grad_from_out(xh * ga + be, act, slope);
+                o[j] = rstd * ga * (gg - sm[(c + j) * 2] * invP - xh * sm[(c + j) * 2 + 1] * invP);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) o[j] = 0.f;
+        }
+        store_vec<T, VEC>(dx + (((size_t)n * Hp + hp) * Wp + wp) * C + c, o);
+    }
+}
+
 __global__ void in_param_grad_kernel(const float* __restrict__ sums, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta, int N, int C) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -198,7 +237,7 @@ __global__ void in_param_grad_kernel(const float* __restrict__ sums, float* __re
 
 template <typename T> int k_in_bwd(const T* x, const T* dy, T* dx, const float* stats, const float* gamma,
                                    const float* beta, float* dgamma, float* dbeta, float* scratch, int act,
-                                   float slope, int N, int P, int C, int accumulate, cudaStream_t st) {
+                                   float slope, int N, int P, int C, int accumulate, cudaStream_t st, int halo, int W) {
     CG_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * 2 * (size_t)N * C, st));
     dim3 grid; int pchunk;
     in_reduce_grid(N, P, C, grid, pchunk);
@@ -208,7 +247,18 @@ template <typename T> int k_in_bwd(const T* x, const T* dy, T* dx, const float* 
         in_param_grad_kernel<<<cdiv(C, 128), 128, 0, st>>>(scratch, dgamma, dbeta, N, C);
         CG_LAUNCH_CHECK();
     }
-    if (dx) {
+    if (dx && halo > 0) {
+        constexpr int VW = VecWidth<T>::value;
+        if (accumulate || C % VW != 0 || W <= 0 || P % W != 0) {
+            cg_set_error("halo IN backward: unsupported configuration");
+            return CG_ERR_INVALID;
+        }
+        const int H = P / W;
+        dim3 g2(ew_blocks((size_t)(H + 2 * halo) * (W + 2 * halo) * C / VW), N);
+        in_bwd_apply_halo_kernel<T, VW><<<g2, EW_THREADS, 0, st>>>(x, dy, dx, stats, scratch, gamma, beta, act, slope, H,
+                                                                   W, C, halo, 1.f / (float)P);
+        CG_LAUNCH_CHECK();
+    } else if (dx) {
         constexpr int VW = VecWidth<T>::value;
         size_t PC = (size_t)P * C;
         if (C % VW == 0) {
@@ -583,7 +633,7 @@ int k_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, f
     template int k_in_apply<T>(const T*, T*, const float*, const float*, const float*, int, float, int, int, int, \
                                cudaStream_t);                                                                   \
     template int k_in_bwd<T>(const T*, const T*, T*, const float*, const float*, const float*, float*, float*,  \
-                             float*, int, float, int, int, int, int, cudaStream_t);                             \
+                             float*, int, float, int, int, int, int, cudaStream_t, int, int);                   \
     template int k_act_fwd<T>(const T*, T*, size_t, int, float, cudaStream_t);                                  \
     template int k_act_bwd<T>(const T*, const T*, T*, size_t, int, float, int, cudaStream_t);                   \
     template int k_rpad_fwd<T>(const T*, T*, int, int, int, int, int, cudaStream_t);                            \

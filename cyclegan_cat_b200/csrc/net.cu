@@ -102,18 +102,118 @@ int net_plan(const cg_net_s* net, int N, int H, int W, bool bwd, CallCtx* ctx) {
         }
     }
     ctx->act_bytes = off;
+    // tensor-core eligibility for THIS shape: the 128-pixel M tile must be a Wb x Hb box of the output, and the
+    // 64-pixel K chunk of the weight gradient a Wk x Hk box
+    ctx->tc.assign(nl, TcLayer());
+    ctx->grad_halo.assign(nl + 1, 0);
+    for (size_t i = 0; i < nl; ++i) {
+        if (!net->layers[i].tc) continue;
+        const int wo = ctx->tw[i + 1], ho = ctx->th[i + 1];
+        const bool box128 = (wo % 128 == 0) || (128 % wo == 0 && ho % (128 / wo) == 0);
+        const bool box64 = (wo % 64 == 0) || (64 % wo == 0 && ho % (64 / wo) == 0);
+        if (box128 && box64 && (size_t)(ho + 4) * (wo + 4) < (1u << 30)) {
+            ctx->tc[i].on = true;
+            ctx->grad_halo[i + 1] = 2;
+        }
+    }
     ctx->grad_off.assign(nl + 1, 0);
     size_t goff = 0;
     if (bwd) {
         for (size_t t = 1; t < nl; ++t) {      // tensor 0 -> caller's dx, last tensor -> caller's dy
             if (!net->has_buffer[t]) continue;
             ctx->grad_off[t] = goff;
-            goff += align_up((size_t)N * ctx->sample_elems((int)t) * es, 256);
+            const int hl = ctx->grad_halo[t];
+            goff += align_up((size_t)N * (ctx->th[t] + 2 * hl) * (ctx->tw[t] + 2 * hl) * net->chan[t] * es, 256);
         }
         ctx->scratch_off = goff;
         goff += align_up(max_nc * 2 * sizeof(float), 256);
     }
     ctx->grad_bytes = goff;
+    return CG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// tensor-core layers: packed weights and TMA descriptors
+// ------------------------------------------------------------------------------------------
+int net_pack(const cg_net_s* net, const float* params, void* packed, cudaStream_t st) {
+    if (!net->packed_bytes) return CG_OK;
+    if (!packed) { cg_set_error("net_pack: no packed-weight buffer"); return CG_ERR_STATE; }
+    for (const LayerInfo& L : net->layers) {
+        if (!L.tc) continue;
+        CG_TRY(tc_pack_weights(params + L.w_off, (bf16*)((char*)packed + L.pk_f), (bf16*)((char*)packed + L.pk_d),
+                               L.d.k * L.d.k, L.d.cin, L.d.cout, st));
+    }
+    return CG_OK;
+}
+
+int net_bind(CallCtx* c) {
+    const cg_net_s* net = c->net;
+    for (size_t i = 0; i < net->layers.size(); ++i) {
+        TcLayer& t = c->tc[i];
+        if (!t.on) continue;
+        if (!c->packed) { cg_set_error("net_bind: tensor-core layer without packed weights"); return CG_ERR_STATE; }
+        const LayerInfo& L = net->layers[i];
+        const cg_layer_desc& d = L.d;
+        const int tin = d.in0, tout = L.out_t;
+        const int hi = c->th[tin], wi = c->tw[tin], ho = c->th[tout], wo = c->tw[tout];
+        const int taps = d.k * d.k;
+        const bf16* wf = (const bf16*)(c->packed + L.pk_f);
+        const bf16* wd = (const bf16*)(c->packed + L.pk_d);
+        // ---- forward: box mode on the (already reflect-padded) input
+        {
+            TcConvArgs& a = t.fa;
+            memset(&a, 0, sizeof(a));
+            a.Wb = wo % 128 == 0 ? 128 : wo;
+            a.Hb = 128 / a.Wb;
+            a.n_taps = taps; a.cchunks = d.cin / 64;
+            a.bn = d.cout < 256 ? d.cout : 256; a.n_blocks_n = d.cout / a.bn;
+            a.tiles_w = wo / a.Wb; a.tiles_per_img = a.tiles_w * (ho / a.Hb);
+            a.n0 = 0; a.nb = c->N;
+            a.out_P = wo; a.out_wvalid = wo; a.out_hvalid = ho; a.out_H = ho; a.out_W = wo; a.Cout = d.cout;
+            a.b_rows_per_tap = d.cout;
+            for (int kh = 0; kh < d.k; ++kh)
+                for (int kw = 0; kw < d.k; ++kw) { a.dw[kh * d.k + kw] = (short)kw; a.dh[kh * d.k + kw] = (short)kh; }
+            CG_TRY(tc_make_map_4d(&t.mapX, c->act(tin), d.cin, wi, hi, c->N, a.Wb, a.Hb));
+            CG_TRY(tc_make_map_2d(&t.mapWf, wf, d.cin, taps * d.cout, a.bn));
+        }
+        if (!c->bwd) continue;
+        const int hl = c->grad_halo[tout], P = wo + 2 * hl, HP = ho + 2 * hl;
+        const bf16* dy = (const bf16*)(c->arena + c->grad_off[tout]);
+        // ---- data gradient: flat mode over the zero-bordered dY, output = gradient of the padded input
+        {
+            TcConvArgs& a = t.da;
+            memset(&a, 0, sizeof(a));
+            a.Wb = 128; a.Hb = 1;
+            a.n_taps = taps; a.cchunks = d.cout / 64;
+            a.bn = d.cin < 256 ? d.cin : 256; a.n_blocks_n = d.cin / a.bn;
+            a.tiles_per_img = (hi * P + 127) / 128; a.tiles_w = a.tiles_per_img;
+            a.n0 = 0; a.nb = c->N;
+            a.out_P = P; a.out_wvalid = wi; a.out_hvalid = hi; a.out_H = hi; a.out_W = wi; a.Cout = d.cin;
+            a.b_rows_per_tap = d.cin;
+            for (int kh = 0; kh < d.k; ++kh)
+                for (int kw = 0; kw < d.k; ++kw) {
+                    a.dw[kh * d.k + kw] = (short)((hl - kh) * P + (hl - kw));
+                    a.dh[kh * d.k + kw] = 0;
+                }
+            CG_TRY(tc_make_map_4d(&t.mapDYflat, dy, d.cout, HP * P, 1, c->N, 128, 1));
+            CG_TRY(tc_make_map_2d(&t.mapWd, wd, d.cout, taps * d.cin, a.bn));
+        }
+        // ---- weight gradient: 64-pixel K chunks of the input and of dY
+        {
+            TcWgradArgs& a = t.wa;
+            memset(&a, 0, sizeof(a));
+            a.Wk = wo % 64 == 0 ? 64 : wo;
+            a.Hk = 64 / a.Wk;
+            a.n_taps = taps; a.ci_blocks = d.cin / 128;
+            a.bn = d.cout < 256 ? d.cout : 256; a.co_blocks = d.cout / a.bn;
+            a.chunks_w = wo / a.Wk; a.chunks_per_img = a.chunks_w * (ho / a.Hk);
+            a.dy_off = hl; a.Cin = d.cin; a.Cout = d.cout;
+            for (int kh = 0; kh < d.k; ++kh)
+                for (int kw = 0; kw < d.k; ++kw) { a.dw[kh * d.k + kw] = (short)kw; a.dh[kh * d.k + kw] = (short)kh; }
+            CG_TRY(tc_make_map_4d(&t.mapXw, c->act(tin), d.cin, wi, hi, c->N, a.Wk, a.Hk));
+            CG_TRY(tc_make_map_4d(&t.mapDYw, dy, d.cout, P, HP, c->N, a.Wk, a.Hk));
+        }
+    }
     return CG_OK;
 }
 
@@ -133,7 +233,15 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
         switch (d.op) {
             case CG_OP_CONV: {
                 ConvGeom g = conv_geom(d, N, h, w, oh, ow);
-                CG_TRY(k_conv_fwd<T>(x, params + L.w_off, L.b_off >= 0 ? params + L.b_off : nullptr, y, g, 0, st));
+                if (c->tc[i].on) {
+                    TcConvArgs a = c->tc[i].fa;
+                    a.nb = N;
+                    CG_TRY(tc_conv_launch(&c->tc[i].mapX, &c->tc[i].mapWf, (bf16*)y,
+                                          L.b_off >= 0 ? params + L.b_off : nullptr, a,
+                                          2.0 * N * oh * ow * (double)d.cout * d.k * d.k * d.cin, st));
+                } else {
+                    CG_TRY(k_conv_fwd<T>(x, params + L.w_off, L.b_off >= 0 ? params + L.b_off : nullptr, y, g, 0, st));
+                }
                 break;
             }
             case CG_OP_CONVT: {
@@ -212,6 +320,24 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
         switch (d.op) {
             case CG_OP_CONV: {
                 ConvGeom g = conv_geom(d, nb, h, w, oh, ow);
+                if (c->tc[i].on) {      // dy lives in a zero-bordered buffer (halo 2) written by the IN backward
+                    const int hl = c->grad_halo[tout];
+                    const double fl = 2.0 * nb * oh * ow * (double)d.cout * d.k * d.k * d.cin;
+                    if (acc) { cg_set_error("tensor-core dgrad cannot accumulate"); return CG_ERR_STATE; }
+                    if (grads) {
+                        TcWgradArgs a = c->tc[i].wa;
+                        a.n0 = n0; a.nb = nb;
+                        CG_TRY(tc_wgrad_launch(&c->tc[i].mapXw, &c->tc[i].mapDYw, grads + L.w_off, a, fl, st));
+                        if (L.b_off >= 0)
+                            CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * (oh + 2 * hl) * (ow + 2 * hl), d.cout, st));
+                    }
+                    if (want_dx) {
+                        TcConvArgs a = c->tc[i].da;
+                        a.nb = nb;
+                        CG_TRY(tc_conv_launch(&c->tc[i].mapDYflat, &c->tc[i].mapWd, (bf16*)dx, nullptr, a, fl, st));
+                    }
+                    break;
+                }
                 if (grads) {
                     CG_TRY(k_conv_wgrad<T>(A(tin), dy, grads + L.w_off, g, st));
                     if (L.b_off >= 0) CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
@@ -234,7 +360,7 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                 CG_TRY(k_in_bwd<T>(A(tin), dy, dx, stats, L.g_off >= 0 ? params + L.g_off : nullptr,
                                    L.be_off >= 0 ? params + L.be_off : nullptr, pg ? grads + L.g_off : nullptr,
                                    pg ? grads + L.be_off : nullptr, scratch, L.fused_act, L.fused_slope, nb, h * w,
-                                   d.cin, acc, st));
+                                   d.cin, acc, st, c->grad_halo[tin], w));
                 break;
             }
             case CG_OP_ACT:

@@ -6,7 +6,15 @@
 
 #include "common.h"
 
-struct TcPlan;   // tensor-core conv plans (conv_tc.cu), opaque here
+#include "conv_tc.h"
+
+// tensor-core plan of one eligible conv layer for one planned call
+struct TcLayer {
+    bool on = false;
+    CUtensorMap mapX, mapWf, mapDYflat, mapWd, mapXw, mapDYw;
+    TcConvArgs fa, da;
+    TcWgradArgs wa;
+};
 
 struct LayerInfo {
     cg_layer_desc d;
@@ -15,6 +23,8 @@ struct LayerInfo {
     bool skipped = false;   // ACT folded into the preceding INORM
     int fused_act = CG_ACT_NONE;
     float fused_slope = 0.f;
+    bool tc = false;        // 3x3 stride-1 'valid' conv with 64/128-multiple channels -> tcgen05 kernels (bf16 mode)
+    long long pk_f = 0, pk_d = 0;   // byte offsets of the packed bf16 weights ([tap][Cout][Cin] / [tap][Cin][Cout])
 };
 
 struct cg_net_s {
@@ -26,6 +36,7 @@ struct cg_net_s {
     std::vector<char> dep_params;       // tensor depends on some trainable variable
     std::vector<cg_var_info> vars;
     long long n_params = 0;
+    size_t packed_bytes = 0;            // bf16 weight copies for the tensor-core layers
     int out_tensor() const { return (int)layers.size(); }
     size_t elem_size() const { return mode == CG_MODE_BF16 ? 2 : 4; }
 };
@@ -46,12 +57,17 @@ struct CallCtx {
     char* arena = nullptr;              // gradient arena (may be shared between calls)
     void* ext_input = nullptr;          // if set, tensor 0 lives here instead of at act_off[0]
     bool forwarded = false;
+    char* packed = nullptr;             // packed bf16 weights of this net (net_pack)
+    std::vector<TcLayer> tc;            // per layer
+    std::vector<int> grad_halo;         // per tensor: zero border of the gradient buffer (tensor-core layers)
 
     size_t sample_elems(int t) const { return (size_t)th[t] * tw[t] * net->chan[t]; }
     void* act(int t) const { return (t == 0 && ext_input) ? ext_input : (void*)(base + act_off[t]); }
 };
 
 int net_plan(const cg_net_s* net, int N, int H, int W, bool bwd, CallCtx* ctx);
+int net_bind(CallCtx* ctx);           // after base/arena/packed are set: build the TMA descriptors
+int net_pack(const cg_net_s* net, const float* params, void* packed, cudaStream_t st);
 int net_out_hw(const cg_net_s* net, int H, int W, int* ho, int* wo);
 
 // forward over the whole planned batch; output is ctx->act(out_tensor())

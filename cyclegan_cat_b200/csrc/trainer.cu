@@ -70,7 +70,7 @@ struct cg_trainer_s {
     CallCtx F1, F2, C1, C2, DA, DB;
     // misc buffers (activation dtype unless noted)
     size_t o_seedF1 = 0, o_seedF2 = 0, o_seedC1 = 0, o_seedC2 = 0, o_dxC1 = 0, o_dxC2 = 0, o_seedDA = 0, o_seedDB = 0,
-           o_advDA = 0, o_advDB = 0, o_sums = 0, o_arena = 0, total = 0;
+           o_advDA = 0, o_advDB = 0, o_sums = 0, o_arena = 0, o_packed[4] = {0, 0, 0, 0}, total = 0;
     int d_h = 0, d_w = 0, d_c = 0;
     // data parallel
     nccl_comm comm = nullptr; int world = 1, rank = 0;
@@ -118,6 +118,8 @@ static int trainer_layout(cg_trainer_t tr, int B, int H, int W, bool assign) {
     tr->o_seedDA = take(2 * B * dout); tr->o_seedDB = take(2 * B * dout);
     tr->o_advDA = take(B * dout); tr->o_advDB = take(B * dout);
     tr->o_sums = take(S_COUNT * sizeof(float));
+    off = align_up(off, 1024);
+    for (int i = 0; i < 4; ++i) tr->o_packed[i] = take(align_up(tr->net[i]->packed_bytes, 1024));
     tr->total = off;
     if (assign) {
         if (off > tr->ws_bytes) { cg_set_error("trainer workspace %zu < required %zu", tr->ws_bytes, off); return CG_ERR_WORKSPACE; }
@@ -127,6 +129,11 @@ static int trainer_layout(cg_trainer_t tr, int B, int H, int W, bool assign) {
         // cycle calls read the first half (the fakes) of F1 / F2's output in place
         tr->C1.ext_input = tr->F1.act(tr->net[0]->out_tensor());
         tr->C2.ext_input = tr->F2.act(tr->net[1]->out_tensor());
+        const int owner[6] = {0, 1, 1, 0, 2, 3};
+        for (int i = 0; i < 6; ++i) {
+            cs[i]->packed = tr->ws + tr->o_packed[owner[i]];
+            CG_TRY(net_bind(cs[i]));
+        }
         tr->B = B; tr->H = H; tr->W = W; tr->planned = true;
     }
     return CG_OK;
@@ -202,6 +209,7 @@ static int step_T(cg_trainer_t tr, const float* real_a, const float* real_b, int
     float* sums = (float*)(ws + tr->o_sums);
     CG_CUDA(cudaMemsetAsync(sums, 0, S_COUNT * sizeof(float), st));
 
+    for (int i = 0; i < 4; ++i) CG_TRY(net_pack(tr->net[i], tr->params[i], ws + tr->o_packed[i], st));
     // ---- inputs: Xab = [a; b], Xba = [b; a] -------------------------------------------------
     T* Xab = (T*)tr->F1.act(0);
     T* Xba = (T*)tr->F2.act(0);

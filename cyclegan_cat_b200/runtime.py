@@ -203,8 +203,9 @@ class Model:
         torch = _require_cuda()
         lib = _lib.load()
         xd = to_device_f32(x, torch)
-        if xd.dim() != 4 or xd.shape[3] != 3:
-            raise ValueError(f"expected NHWC input with 3 channels, got {tuple(xd.shape)}")
+        cin = self.graph.channels[0]
+        if xd.dim() != 4 or xd.shape[3] != cin:
+            raise ValueError(f"expected NHWC input with {cin} channels, got {tuple(xd.shape)}")
         N, H, W, _ = xd.shape
         f = self.graph.down_factor()
         if H % f or W % f:
