@@ -146,14 +146,24 @@ extern "C" int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode
     size_t pk = 0;
     const char* no_tc = getenv("CG_DISABLE_TC");     // test hook: force the CUDA-core convs in bf16 mode
     if (mode == CG_MODE_BF16 && !(no_tc && no_tc[0] == '1')) {
-        for (int i = 0; i + 1 < n_layers; ++i) {
+        auto chan_ok = [](int cin_f, int cout_f) {      // K chunks of 64, N tiles of <= 256, an M = 128 side for wgrad
+            return cin_f % 64 == 0 && cout_f % 64 == 0 && (cin_f <= 256 || cin_f % 256 == 0) &&
+                   (cout_f <= 256 || cout_f % 256 == 0) && (cin_f % 128 == 0 || cout_f % 128 == 0);
+        };
+        for (int i = 0; i < n_layers; ++i) {
             LayerInfo& L = net->layers[i];
             const cg_layer_desc& d = L.d;
-            const int bn = d.cout < 256 ? d.cout : 256;
-            if (d.op == CG_OP_CONV && d.k == 3 && d.stride == 1 && !d.same && d.cin % 128 == 0 && d.cout % 64 == 0 &&
-                d.cout % bn == 0 && (d.cin <= 256 || d.cin % 256 == 0) && net->n_consumers[i + 1] == 1 &&
-                net->layers[i + 1].d.op == CG_OP_INORM && net->layers[i + 1].d.in0 == i + 1) {
-                L.tc = true;
+            int kind = TC_NONE;
+            if (d.op == CG_OP_CONV && d.k == 3 && d.stride == 1 && !d.same && d.cin % 128 == 0 && chan_ok(d.cin, d.cout) &&
+                i + 1 < n_layers && net->n_consumers[i + 1] == 1 && net->layers[i + 1].d.op == CG_OP_INORM &&
+                net->layers[i + 1].d.in0 == i + 1)
+                kind = TC_S1_VALID;
+            else if (d.op == CG_OP_CONV && d.stride == 2 && d.same && (d.k == 3 || d.k == 4) && chan_ok(d.cin, d.cout))
+                kind = TC_CONV_S2;
+            else if (d.op == CG_OP_CONVT && d.stride == 2 && (d.k == 3 || d.k == 4) && chan_ok(d.cout, d.cin))
+                kind = TC_CONVT_S2;
+            if (kind) {
+                L.tc = kind;
                 const size_t bytes = align_up((size_t)d.k * d.k * d.cin * d.cout * 2, 1024);
                 L.pk_f = (long long)pk; pk += bytes;
                 L.pk_d = (long long)pk; pk += bytes;

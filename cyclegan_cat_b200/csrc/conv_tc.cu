@@ -53,6 +53,13 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -181,8 +188,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     mbar_wait(empty(s), ph ^ 1u);
                     mbar_expect_tx(full(s), stage_bytes);
                     const uint32_t sa = smem0 + s * stage_bytes;
-                    tma_load_4d(sa, &mapA, full(s), cc * 64, w0 + a.dw[tap], h0 + a.dh[tap], img);
-                    tma_load_2d(sa + A_TILE_BYTES, &mapB, full(s), cc * 64, tap * a.b_rows_per_tap + nblk * a.bn);
+                    tma_load_5d(sa, &mapA, full(s), cc * 64 + a.dc[tap], w0 + a.dw[tap], a.dp[tap], h0 + a.dh[tap], img);
+                    tma_load_2d(sa + A_TILE_BYTES, &mapB, full(s), cc * 64, a.tb[tap] * a.b_rows_per_tap + nblk * a.bn);
                     if (++s == S) { s = 0; ph ^= 1u; }
                 }
             }
@@ -225,7 +232,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int lin = h0 * a.out_P + w0 + q * 32 + lane;
             const int oh = lin / a.out_P, ow = lin - oh * a.out_P;
             const bool valid = ow < a.out_wvalid && oh < a.out_hvalid;
-            bf16* dst = out + (((size_t)img * a.out_H + oh) * a.out_W + ow) * a.Cout + (size_t)nblk * a.bn;
+            bf16* dst = out + (((size_t)img * a.out_H + (oh * a.out_sy + a.out_oy)) * a.out_W + (ow * a.out_sx + a.out_ox)) * a.Cout +
+                        (size_t)nblk * a.bn;
             mbar_wait(tfull(acc), acc_ph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
@@ -259,8 +267,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------
-// weight-gradient kernel.  One CTA = one (tap, 128 input channels, BN output channels, K split).
-// smem stage: [2 boxes X (64ch x 64px)] [BN/64 boxes dY (64ch x 64px)], each box 8 KB, MN-major.
+// weight-gradient kernel.  One CTA = one (tap, 128-row block of operand A, BN-column block of operand B, K split).
+//   normal     : A = X  tiles (rows = input channels),  B = dY tiles (cols = output channels)
+//   transposed : A = dY tiles (rows = output channels), B = X  tiles (cols = input channels)   [Cin = 64 layers]
+// smem stage: [2 boxes of A (64ch x 64px)] [BN/64 boxes of B (64ch x 64px)], each box 8 KB, MN-major.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDY,
@@ -294,29 +304,34 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     // decode the work unit
     int u = blockIdx.x;
     const int split = u % a.splits; u /= a.splits;
-    const int coblk = u % a.co_blocks; u /= a.co_blocks;
-    const int ciblk = u % a.ci_blocks; u /= a.ci_blocks;
+    const int bblk = u % a.b_blocks; u /= a.b_blocks;
+    const int ablk = u % a.a_blocks; u /= a.a_blocks;
     const int tap = u;
     const int total_chunks = a.nb * a.chunks_per_img;
     const int per = (total_chunks + a.splits - 1) / a.splits;
     const int q_begin = split * per;
     const int q_end = min(total_chunks, q_begin + per);
     const int nq = q_end - q_begin;
+    // channel bases of the X boxes and of the dY boxes in this unit
+    const int x_c0 = a.transposed ? bblk * a.bn : ablk * 128;
+    const int y_c0 = a.transposed ? ablk * 128 : bblk * a.bn;
+    const int x_boxes = a.transposed ? nb_boxes : 2, y_boxes = a.transposed ? 2 : nb_boxes;
+    const uint32_t x_off = a.transposed ? 2 * 8192u : 0u, y_off = a.transposed ? 0u : 2 * 8192u;
 
     if (warp == 0) {
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
             for (int q = q_begin; q < q_end; ++q) {
-                const int img = a.n0 + q / a.chunks_per_img, r = q % a.chunks_per_img;
+                const int img = q / a.chunks_per_img, r = q % a.chunks_per_img;
                 const int w0 = (r % a.chunks_w) * a.Wk, h0 = (r / a.chunks_w) * a.Hk;
                 mbar_wait(empty(s), ph ^ 1u);
                 mbar_expect_tx(full(s), stage_bytes);
                 const uint32_t sa = smem0 + s * stage_bytes;
-                for (int b = 0; b < 2; ++b)
-                    tma_load_4d(sa + b * 8192u, &mapX, full(s), ciblk * 128 + b * 64, w0 + a.dw[tap], h0 + a.dh[tap], img);
-                for (int b = 0; b < nb_boxes; ++b)
-                    tma_load_4d(sa + (2 + b) * 8192u, &mapDY, full(s), coblk * a.bn + b * 64, w0 + a.dy_off, h0 + a.dy_off,
-                                img - a.n0);
+                for (int b = 0; b < x_boxes; ++b)
+                    tma_load_5d(sa + x_off + b * 8192u, &mapX, full(s), x_c0 + b * 64 + a.dc[tap], w0 + a.dw[tap], a.dp[tap],
+                                h0 + a.dh[tap], a.n0 + img);
+                for (int b = 0; b < y_boxes; ++b)
+                    tma_load_5d(sa + y_off + b * 8192u, &mapDY, full(s), y_c0 + b * 64, w0 + a.dy_off, 0, h0 + a.dy_off, a.y_n0 + img);
                 if (++s == S) { s = 0; ph ^= 1u; }
             }
         }
@@ -344,18 +359,28 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         const int q = warp & 3;
         mbar_wait(tfull, 0);
         tc_fence_after();
-        const int ci = ciblk * 128 + q * 32 + lane;
-        float* dst = dw + ((size_t)tap * a.Cin + ci) * a.Cout + (size_t)coblk * a.bn;
+        const int row = ablk * 128 + q * 32 + lane;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        for (int c0 = 0; c0 < a.bn; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(taddr + (uint32_t)c0, v);
+        if (!a.transposed) {        // row = ci, columns = co (contiguous in dW): 16-byte vector reductions
+            float* dst = dw + ((size_t)tap * a.Cin + row) * a.Cout + (size_t)bblk * a.bn;
+            for (int c0 = 0; c0 < a.bn; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)c0, v);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + 4 * j),
-                             "f"(__uint_as_float(v[4 * j])), "f"(__uint_as_float(v[4 * j + 1])),
-                             "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3]))
-                             : "memory");
+                for (int j = 0; j < 8; ++j) {
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + 4 * j),
+                                 "f"(__uint_as_float(v[4 * j])), "f"(__uint_as_float(v[4 * j + 1])),
+                                 "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3]))
+                                 : "memory");
+                }
+            }
+        } else {                    // row = co (lanes -> consecutive addresses), columns = ci
+            float* dst = dw + ((size_t)tap * a.Cin + (size_t)bblk * a.bn) * a.Cout + row;
+            for (int c0 = 0; c0 < a.bn; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)c0, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) atomicAdd(dst + (size_t)(c0 + j) * a.Cout, __uint_as_float(v[j]));
             }
         }
     }
@@ -412,18 +437,28 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-int tc_make_map_4d(CUtensorMap* map, const void* base, int C, int W, int H, int N, int box_w, int box_h) {
+int tc_make_map_act(CUtensorMap* map, const void* base, int C, int W, int H, int N, int parity, int box_w, int box_h) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { cg_set_error("cuTensorMapEncodeTiled is not available from the driver"); return CG_ERR_CUDA; }
-    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+    cuuint64_t dims[5], strides[4];
+    if (!parity) {
+        dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = N;
+        strides[0] = (cuuint64_t)C * 2; strides[1] = (cuuint64_t)W * C * 2; strides[2] = (cuuint64_t)W * C * 2;
+        strides[3] = (cuuint64_t)H * W * C * 2;
+    } else {
+        if ((W | H) & 1) { cg_set_error("parity view needs even H, W (got %dx%d)", H, W); return CG_ERR_INVALID; }
+        dims[0] = 2 * (cuuint64_t)C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = N;
+        strides[0] = (cuuint64_t)2 * C * 2; strides[1] = (cuuint64_t)W * C * 2; strides[2] = (cuuint64_t)2 * W * C * 2;
+        strides[3] = (cuuint64_t)H * W * C * 2;
+    }
+    cuuint32_t box[5] = {64, (cuuint32_t)box_w, 1, (cuuint32_t)box_h, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        cg_set_error("cuTensorMapEncodeTiled(4d C=%d W=%d H=%d N=%d box %dx%d) failed: %d", C, W, H, N, box_w, box_h, (int)r);
+        cg_set_error("cuTensorMapEncodeTiled(act C=%d W=%d H=%d N=%d parity=%d box %dx%d) failed: %d", C, W, H, N, parity,
+                     box_w, box_h, (int)r);
         return CG_ERR_CUDA;
     }
     return CG_OK;
@@ -488,7 +523,7 @@ int tc_wgrad_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* dw
     int s = (227 * 1024 - 2048) / stage;
     a.stages = s > 6 ? 6 : s;
     a.idesc = make_idesc(128, a.bn, 1, 1);
-    const int units = a.n_taps * a.ci_blocks * a.co_blocks;
+    const int units = a.n_taps * a.a_blocks * a.b_blocks;
     const int total_chunks = a.nb * a.chunks_per_img;
     int splits = num_sms() / units;
     if (splits < 1) splits = 1;

@@ -9,23 +9,28 @@ struct TcConvArgs {
     int tiles_per_img, tiles_w, Wb, Hb;         // M tiling: 128 output pixels = Wb x Hb box
     int n0, nb;                                 // images [n0, n0+nb)
     int out_P, out_wvalid, out_hvalid, out_H, out_W, Cout;   // epilogue: linear index -> (oh, ow), masks, dense output
+    int out_sy, out_oy, out_sx, out_ox;         // output pixel = (oh*sy + oy, ow*sx + ox): stride-2 scatter of a parity class
     int b_rows_per_tap;                         // rows of the packed weight matrix per tap
     int stages;
     uint32_t idesc;
-    short dw[49], dh[49];                       // TMA coordinate offsets per tap
+    // per K-loop tap: TMA coordinate offsets into the 5-D activation view (c, w, p, h, n) and the weight row block
+    short dc[49], dw[49], dp[49], dh[49], tb[49];
 };
 
 struct TcWgradArgs {
-    int n_taps, ci_blocks, co_blocks, bn, splits, stages;
-    int n0, nb;
-    int chunks_per_img, chunks_w, Wk, Hk;       // K chunk = 64 pixels = Wk x Hk box
+    int n_taps, a_blocks, b_blocks, bn, splits, stages;   // M = 128-row blocks of operand A, N = bn-column blocks of B
+    int transposed;                             // 0: A = X (rows = ci), B = dY (cols = co);  1: A = dY (rows = co), B = X
+    int n0, nb, y_n0;                           // image offsets: X operand starts at n0, dY operand at y_n0
+    int chunks_per_img, chunks_w, Wk, Hk;       // K chunk = 64 pixels = Wk x Hk box of the dY grid
     int dy_off;                                 // halo of the dY buffer
     int Cin, Cout;
     uint32_t idesc;
-    short dw[49], dh[49];
+    short dc[49], dw[49], dp[49], dh[49];       // X coordinate offsets per tap (5-D view)
 };
 
-int tc_make_map_4d(CUtensorMap* map, const void* base, int C, int W, int H, int N, int box_w, int box_h);
+// 5-D activation view (c, w, p, h, n).  parity = 0: dense NHWC tensor, p is a dummy dim of size 1.
+// parity = 1: stride-2 view of an NHWC tensor with even H, W: c' = pw*C + c (size 2C), w' = w/2, p = h%2, h' = h/2.
+int tc_make_map_act(CUtensorMap* map, const void* base, int C, int W, int H, int N, int parity, int box_w, int box_h);
 int tc_make_map_2d(CUtensorMap* map, const void* base, int cols, int rows, int box_rows);
 int tc_pack_weights(const float* w, bf16* wf, bf16* wd, int taps, int Cin, int Cout, cudaStream_t st);
 int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, bf16* out, const float* bias, TcConvArgs a,

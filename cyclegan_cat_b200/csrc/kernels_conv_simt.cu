@@ -116,9 +116,140 @@ __global__ void __launch_bounds__(256) conv_fwd_simt(const T* __restrict__ x, co
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// skinny convolutions (Cout <= 4: the tanh head c7s1-3 of resnet.py:82, 1x1 heads): a 64-wide GEMM tile would
+// waste 95 % of its columns.  forward: one thread = two horizontally adjacent output pixels x all Cout channels,
+// weights broadcast from shared memory as float4 rows; inputs read as 16-byte channel vectors.
+// ------------------------------------------------------------------------------------------
+template <typename T, bool VEC8>
+__global__ void __launch_bounds__(128) conv_fwd_skinny(const T* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, T* __restrict__ y, ConvGeom g,
+                                                       int accumulate) {
+    extern __shared__ float4 wsm[];      // [K] rows of (w0, w1, w2, w3), zero padded
+    const int K = g.k * g.k * g.Cin;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* pv = &v.x;
+        for (int c = 0; c < g.Cout; ++c) pv[c] = w[(size_t)i * g.Cout + c];
+        wsm[i] = v;
+    }
+    __syncthreads();
+    const int wpairs = (g.Wo + 1) / 2;
+    const long long total = (long long)g.N * g.Ho * wpairs;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int wp = (int)(idx % wpairs);
+        long long r = idx / wpairs;
+        const int oh = (int)(r % g.Ho), n = (int)(r / g.Ho);
+        const int ow0 = wp * 2;
+        const bool second = ow0 + 1 < g.Wo;
+        float acc[2][4] = {};
+        const T* xn = x + (size_t)n * g.Hi * g.Wi * g.Cin;
+        for (int kh = 0; kh < g.k; ++kh) {
+            const int ih = oh * g.s + kh - g.pt;
+            if (ih < 0 || ih >= g.Hi) continue;
+            for (int kw = 0; kw < g.k; ++kw) {
+                const int iw0 = ow0 * g.s + kw - g.pl, iw1 = iw0 + g.s;
+                const bool ok0 = iw0 >= 0 && iw0 < g.Wi, ok1 = second && iw1 >= 0 && iw1 < g.Wi;
+                if (!ok0 && !ok1) continue;
+                const T* p0 = xn + ((size_t)ih * g.Wi + iw0) * g.Cin;
+                const T* p1 = xn + ((size_t)ih * g.Wi + iw1) * g.Cin;
+                const float4* wr = wsm + (kh * g.k + kw) * g.Cin;
+                if (VEC8) {
+                    for (int ci = 0; ci < g.Cin; ci += 8) {
+                        float a0[8], a1[8];
+                        if (ok0) load_vec<T, VecWidth<T>::value == 8 ? 8 : 4>(p0 + ci, *reinterpret_cast<float(*)[VecWidth<T>::value == 8 ? 8 : 4]>(a0));
+                        if (ok1) load_vec<T, VecWidth<T>::value == 8 ? 8 : 4>(p1 + ci, *reinterpret_cast<float(*)[VecWidth<T>::value == 8 ? 8 : 4]>(a1));
+                        if (VecWidth<T>::value == 4) {
+                            if (ok0) load_vec<T, 4>(p0 + ci + 4, *reinterpret_cast<float(*)[4]>(a0 + 4));
+                            if (ok1) load_vec<T, 4>(p1 + ci + 4, *reinterpret_cast<float(*)[4]>(a1 + 4));
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 wv = wr[ci + j];
+                            if (ok0) { acc[0][0] = fmaf(a0[j], wv.x, acc[0][0]); acc[0][1] = fmaf(a0[j], wv.y, acc[0][1]);
+                                       acc[0][2] = fmaf(a0[j], wv.z, acc[0][2]); acc[0][3] = fmaf(a0[j], wv.w, acc[0][3]); }
+                            if (ok1) { acc[1][0] = fmaf(a1[j], wv.x, acc[1][0]); acc[1][1] = fmaf(a1[j], wv.y, acc[1][1]);
+                                       acc[1][2] = fmaf(a1[j], wv.z, acc[1][2]); acc[1][3] = fmaf(a1[j], wv.w, acc[1][3]); }
+                        }
+                    }
+                } else {
+                    for (int ci = 0; ci < g.Cin; ++ci) {
+                        const float4 wv = wr[ci];
+                        if (ok0) { const float a = ldf(p0 + ci);
+                                   acc[0][0] = fmaf(a, wv.x, acc[0][0]); acc[0][1] = fmaf(a, wv.y, acc[0][1]);
+                                   acc[0][2] = fmaf(a, wv.z, acc[0][2]); acc[0][3] = fmaf(a, wv.w, acc[0][3]); }
+                        if (ok1) { const float a = ldf(p1 + ci);
+                                   acc[1][0] = fmaf(a, wv.x, acc[1][0]); acc[1][1] = fmaf(a, wv.y, acc[1][1]);
+                                   acc[1][2] = fmaf(a, wv.z, acc[1][2]); acc[1][3] = fmaf(a, wv.w, acc[1][3]); }
+                    }
+                }
+            }
+        }
+        for (int px = 0; px < (second ? 2 : 1); ++px) {
+            T* o = y + (((size_t)n * g.Ho + oh) * g.Wo + ow0 + px) * g.Cout;
+            for (int c = 0; c < g.Cout; ++c) {
+                float v = acc[px][c] + (bias ? bias[c] : 0.f);
+                stf(o + c, accumulate ? ldf(o + c) + v : v);
+            }
+        }
+    }
+}
+
+// weight gradient for Cout <= 4: thread = (kw, pair of input channels), blockIdx.y = kh, blockIdx.x = strip of output
+// pixels; every thread walks the strip accumulating 2 x Cout sums, then one atomicAdd each.
+template <typename T>
+__global__ void __launch_bounds__(1024) conv_wgrad_skinny(const T* __restrict__ x, const T* __restrict__ dy,
+                                                          float* __restrict__ dw, ConvGeom g, int strip) {
+    const int half = g.Cin / 2;
+    const int kw = threadIdx.x / half, ci = (threadIdx.x % half) * 2, kh = blockIdx.y;
+    if (kw >= g.k) return;
+    const long long P = (long long)g.N * g.Ho * g.Wo;
+    const long long p0 = (long long)blockIdx.x * strip;
+    const long long p1 = p0 + strip < P ? p0 + strip : P;
+    float acc[2][4] = {};
+    for (long long p = p0; p < p1; ++p) {
+        const int ow = (int)(p % g.Wo);
+        long long r = p / g.Wo;
+        const int oh = (int)(r % g.Ho), n = (int)(r / g.Ho);
+        const int ih = oh * g.s + kh - g.pt, iw = ow * g.s + kw - g.pl;
+        if (ih < 0 || ih >= g.Hi || iw < 0 || iw >= g.Wi) continue;
+        const T* xp = x + (((size_t)n * g.Hi + ih) * g.Wi + iw) * g.Cin + ci;
+        const float a0 = ldf(xp), a1 = ldf(xp + 1);
+        const T* dp = dy + (size_t)p * g.Cout;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c < g.Cout) {
+                const float d = ldf(dp + c);
+                acc[0][c] = fmaf(a0, d, acc[0][c]);
+                acc[1][c] = fmaf(a1, d, acc[1][c]);
+            }
+    }
+    float* o = dw + ((size_t)(kh * g.k + kw) * g.Cin + ci) * g.Cout;
+    for (int c = 0; c < g.Cout; ++c) {
+        atomicAdd(o + c, acc[0][c]);
+        atomicAdd(o + g.Cout + c, acc[1][c]);
+    }
+}
+
 template <typename T> int k_conv_fwd(const T* x, const float* w, const float* bias, T* y, ConvGeom g, int accumulate,
                                      cudaStream_t st) {
     long long M = (long long)g.N * g.Ho * g.Wo;
+    const size_t wbytes = (size_t)g.k * g.k * g.Cin * sizeof(float4);
+    if (g.Cout <= 4 && wbytes <= 96 * 1024) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            CG_CUDA(cudaFuncSetAttribute(conv_fwd_skinny<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            CG_CUDA(cudaFuncSetAttribute(conv_fwd_skinny<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr_done = true;
+        }
+        long long work = (long long)g.N * g.Ho * ((g.Wo + 1) / 2);
+        int blocks = (int)((work + 127) / 128 < 148 * 16 ? (work + 127) / 128 : 148 * 16);
+        if (g.Cin % 8 == 0) conv_fwd_skinny<T, true><<<blocks, 128, wbytes, st>>>(x, w, bias, y, g, accumulate);
+        else conv_fwd_skinny<T, false><<<blocks, 128, wbytes, st>>>(x, w, bias, y, g, accumulate);
+        CG_LAUNCH_CHECK();
+        return CG_OK;
+    }
     dim3 grid(cdiv(M, BM), cdiv(g.Cout, BN));
     if (g.Cin % 4 == 0) conv_fwd_simt<T, true><<<grid, 256, 0, st>>>(x, w, bias, y, g, accumulate);
     else conv_fwd_simt<T, false><<<grid, 256, 0, st>>>(x, w, bias, y, g, accumulate);
@@ -335,6 +466,16 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt(const T* __restrict__ x, 
 template <typename T> int k_conv_wgrad(const T* x, const T* dy, float* dw, ConvGeom g, cudaStream_t st) {
     int Mrows = g.k * g.k * g.Cin;
     long long P = (long long)g.N * g.Ho * g.Wo;
+    if (g.Cout <= 4 && g.Cin % 2 == 0 && g.k * (g.Cin / 2) <= 1024) {
+        const int threads = ((g.k * (g.Cin / 2) + 31) / 32) * 32;
+        long long want = 148LL * 8 / g.k + 1;                   // strips so that the grid fills the GPU a few times
+        int strip = (int)((P + want - 1) / want);
+        if (strip < 64) strip = 64;
+        dim3 grid((unsigned)((P + strip - 1) / strip), g.k);
+        conv_wgrad_skinny<T><<<grid, threads, 0, st>>>(x, dy, dw, g, strip);
+        CG_LAUNCH_CHECK();
+        return CG_OK;
+    }
     int tiles = cdiv(Mrows, BM) * cdiv(g.Cout, BN);
     int splits = cdiv(148 * 4, tiles);
     int maxsplits = cdiv(P, 256);

@@ -102,19 +102,26 @@ int net_plan(const cg_net_s* net, int N, int H, int W, bool bwd, CallCtx* ctx) {
         }
     }
     ctx->act_bytes = off;
-    // tensor-core eligibility for THIS shape: the 128-pixel M tile must be a Wb x Hb box of the output, and the
-    // 64-pixel K chunk of the weight gradient a Wk x Hk box
+    // tensor-core eligibility for THIS shape: every 128-pixel M tile must be a Wb x Hb box of the (class) output grid
+    // and every 64-pixel K chunk of the weight gradient a Wk x Hk box
     ctx->tc.assign(nl, TcLayer());
     ctx->grad_halo.assign(nl + 1, 0);
+    auto boxable = [](int w, int h, int px) { return (w % px == 0) || (px % w == 0 && h % (px / w) == 0); };
     for (size_t i = 0; i < nl; ++i) {
-        if (!net->layers[i].tc) continue;
-        const int wo = ctx->tw[i + 1], ho = ctx->th[i + 1];
-        const bool box128 = (wo % 128 == 0) || (128 % wo == 0 && ho % (128 / wo) == 0);
-        const bool box64 = (wo % 64 == 0) || (64 % wo == 0 && ho % (64 / wo) == 0);
-        if (box128 && box64 && (size_t)(ho + 4) * (wo + 4) < (1u << 30)) {
-            ctx->tc[i].on = true;
-            ctx->grad_halo[i + 1] = 2;
+        const int kind = net->layers[i].tc;
+        if (!kind) continue;
+        const cg_layer_desc& d = net->layers[i].d;
+        const int hi = ctx->th[d.in0], wi = ctx->tw[d.in0], ho = ctx->th[i + 1], wo = ctx->tw[i + 1];
+        bool ok = false;
+        if (kind == TC_S1_VALID) {
+            ok = boxable(wo, ho, 128) && boxable(wo, ho, 64) && (size_t)(ho + 4) * (wo + 4) < (1u << 30);
+            if (ok) ctx->grad_halo[i + 1] = 2;
+        } else if (kind == TC_CONV_S2) {       // fwd tiles on (ho,wo); dgrad classes on (hi/2, wi/2)
+            ok = !((hi | wi) & 1) && boxable(wo, ho, 128) && boxable(wo, ho, 64) && boxable(wi / 2, hi / 2, 128);
+        } else if (kind == TC_CONVT_S2) {      // fwd classes on (hi,wi) = half the output grid; its dgrad tiles on (hi,wi)
+            ok = boxable(wi, hi, 128) && boxable(wi, hi, 64);
         }
+        ctx->tc[i].on = ok;
     }
     ctx->grad_off.assign(nl + 1, 0);
     size_t goff = 0;
@@ -140,9 +147,113 @@ int net_pack(const cg_net_s* net, const float* params, void* packed, cudaStream_
     if (!packed) { cg_set_error("net_pack: no packed-weight buffer"); return CG_ERR_STATE; }
     for (const LayerInfo& L : net->layers) {
         if (!L.tc) continue;
+        // the TF kernel of a Conv2DTranspose (kh,kw,Cout,Cin) IS the HWIO kernel of the conv F it back-propagates
+        const int cin_f = L.d.op == CG_OP_CONV ? L.d.cin : L.d.cout, cout_f = L.d.op == CG_OP_CONV ? L.d.cout : L.d.cin;
         CG_TRY(tc_pack_weights(params + L.w_off, (bf16*)((char*)packed + L.pk_f), (bf16*)((char*)packed + L.pk_d),
-                               L.d.k * L.d.k, L.d.cin, L.d.cout, st));
+                               L.d.k * L.d.k, cin_f, cout_f, st));
     }
+    return CG_OK;
+}
+
+static inline int floor_div2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
+
+// tiles of 128 output pixels as a Wb x Hb box of a (w x h) grid
+static void set_tiles(TcConvArgs& a, int w, int h) {
+    a.Wb = w % 128 == 0 ? 128 : w;
+    a.Hb = 128 / a.Wb;
+    a.tiles_w = w / a.Wb;
+    a.tiles_per_img = a.tiles_w * (h / a.Hb);
+    a.out_P = w; a.out_wvalid = w; a.out_hvalid = h;
+}
+
+// conv-type launch: out[n,oh,ow,:] = sum_taps in[n, oh*s + kh - pt, ow*s + kw - pl, :] * Wf[tap]  (+ bias)
+//   `in` is [hi x wi x cin_k] (cin_k = GEMM K per tap), `Wf` is the [tap][n_out][cin_k] packing
+static int make_conv_launch(TcConvLaunch& L, const void* in, int hi, int wi, int cin_k, int N, const bf16* wmat, int n_out,
+                            int k, int s, int pt, int pl, int ho, int wo) {
+    TcConvArgs& a = L.a;
+    memset(&a, 0, sizeof(a));
+    set_tiles(a, wo, ho);
+    a.n_taps = k * k; a.cchunks = cin_k / 64;
+    a.bn = n_out < 256 ? n_out : 256; a.n_blocks_n = n_out / a.bn;
+    a.n0 = 0; a.nb = N;
+    a.out_H = ho; a.out_W = wo; a.Cout = n_out;
+    a.out_sy = a.out_sx = 1; a.out_oy = a.out_ox = 0;
+    a.b_rows_per_tap = n_out;
+    for (int kh = 0; kh < k; ++kh)
+        for (int kw = 0; kw < k; ++kw) {
+            const int t = kh * k + kw, oh = kh - pt, ow = kw - pl;
+            a.tb[t] = (short)t;
+            if (s == 1) { a.dc[t] = 0; a.dw[t] = (short)ow; a.dp[t] = 0; a.dh[t] = (short)oh; }
+            else {
+                const int ah = floor_div2(oh), aw = floor_div2(ow);
+                a.dc[t] = (short)((ow - 2 * aw) * cin_k); a.dw[t] = (short)aw; a.dp[t] = (short)(oh - 2 * ah); a.dh[t] = (short)ah;
+            }
+        }
+    CG_TRY(tc_make_map_act(&L.mapA, in, cin_k, wi, hi, N, s == 2, a.Wb, a.Hb));
+    CG_TRY(tc_make_map_2d(&L.mapB, wmat, cin_k, k * k * n_out, a.bn));
+    return CG_OK;
+}
+
+// data-gradient of a stride-2 conv F, one launch per output parity class (ph,pw):
+//   dx[n, 2hc+ph, 2wc+pw, ci] = sum_{taps of the class} dy[n, hc + qh - a, wc + qw - b, :] * Wd[tap][ci][:]  (+ bias)
+//   `dy` is [ho x wo x cout_f] dense (zero padding = TMA out-of-bounds fill), `Wd` the native [tap][cin_f][cout_f] layout
+static int make_class_launches(std::vector<TcConvLaunch>& out, const void* dy, int ho, int wo, int cout_f, int N,
+                               const bf16* wd, int cin_f, int k, int pt, int pl, int hi, int wi) {
+    out.assign(4, TcConvLaunch());
+    int total_taps = 0;
+    for (int cls = 0; cls < 4; ++cls) {
+        const int ph = cls >> 1, pw = cls & 1;
+        TcConvLaunch& L = out[cls];
+        TcConvArgs& a = L.a;
+        memset(&a, 0, sizeof(a));
+        set_tiles(a, wi / 2, hi / 2);
+        const int kh0 = (ph + pt) % 2, kw0 = (pw + pl) % 2;
+        const int nkh = kh0 < k ? (k - kh0 + 1) / 2 : 0, nkw = kw0 < k ? (k - kw0 + 1) / 2 : 0;
+        const int qh = (ph + pt - kh0) / 2, qw = (pw + pl - kw0) / 2;
+        a.n_taps = nkh * nkw; a.cchunks = cout_f / 64;
+        a.bn = cin_f < 256 ? cin_f : 256; a.n_blocks_n = cin_f / a.bn;
+        a.n0 = 0; a.nb = N;
+        a.out_H = hi; a.out_W = wi; a.Cout = cin_f;
+        a.out_sy = a.out_sx = 2; a.out_oy = ph; a.out_ox = pw;
+        a.b_rows_per_tap = cin_f;
+        for (int ia = 0; ia < nkh; ++ia)
+            for (int ib = 0; ib < nkw; ++ib) {
+                const int t = ia * nkw + ib;
+                a.tb[t] = (short)((kh0 + 2 * ia) * k + (kw0 + 2 * ib));
+                a.dc[t] = 0; a.dp[t] = 0; a.dw[t] = (short)(qw - ib); a.dh[t] = (short)(qh - ia);
+            }
+        total_taps += a.n_taps;
+        CG_TRY(tc_make_map_act(&L.mapA, dy, cout_f, wo, ho, N, 0, a.Wb, a.Hb));
+        CG_TRY(tc_make_map_2d(&L.mapB, wd, cout_f, k * k * cin_f, a.bn));
+    }
+    for (auto& L : out) L.flop_share = (double)L.a.n_taps / (double)(total_taps ? total_taps : 1);
+    return CG_OK;
+}
+
+// weight gradient of conv F (stride s): X = F's input [hi x wi x cin_f] (parity view when s == 2), dY = F's output gradient
+static int make_wgrad(TcLayer& t, const void* x, int hi, int wi, int cin_f, const void* dy, int ho, int wo, int cout_f, int N,
+                      int k, int s, int pt, int pl, int dy_halo) {
+    TcWgradArgs& a = t.wa;
+    memset(&a, 0, sizeof(a));
+    a.Wk = wo % 64 == 0 ? 64 : wo;
+    a.Hk = 64 / a.Wk;
+    a.n_taps = k * k;
+    a.transposed = cin_f % 128 == 0 ? 0 : 1;
+    if (!a.transposed) { a.a_blocks = cin_f / 128; a.bn = cout_f < 256 ? cout_f : 256; a.b_blocks = cout_f / a.bn; }
+    else { a.a_blocks = cout_f / 128; a.bn = cin_f < 256 ? cin_f : 256; a.b_blocks = cin_f / a.bn; }
+    a.chunks_w = wo / a.Wk; a.chunks_per_img = a.chunks_w * (ho / a.Hk);
+    a.dy_off = dy_halo; a.Cin = cin_f; a.Cout = cout_f;
+    for (int kh = 0; kh < k; ++kh)
+        for (int kw = 0; kw < k; ++kw) {
+            const int tp = kh * k + kw, oh = kh - pt, ow = kw - pl;
+            if (s == 1) { a.dc[tp] = 0; a.dw[tp] = (short)ow; a.dp[tp] = 0; a.dh[tp] = (short)oh; }
+            else {
+                const int ah = floor_div2(oh), aw = floor_div2(ow);
+                a.dc[tp] = (short)((ow - 2 * aw) * cin_f); a.dw[tp] = (short)aw; a.dp[tp] = (short)(oh - 2 * ah); a.dh[tp] = (short)ah;
+            }
+        }
+    CG_TRY(tc_make_map_act(&t.mapXw, x, cin_f, wi, hi, N, s == 2, a.Wk, a.Hk));
+    CG_TRY(tc_make_map_act(&t.mapDYw, dy, cout_f, wo + 2 * dy_halo, ho + 2 * dy_halo, N, 0, a.Wk, a.Hk));
     return CG_OK;
 }
 
@@ -154,64 +265,59 @@ int net_bind(CallCtx* c) {
         if (!c->packed) { cg_set_error("net_bind: tensor-core layer without packed weights"); return CG_ERR_STATE; }
         const LayerInfo& L = net->layers[i];
         const cg_layer_desc& d = L.d;
-        const int tin = d.in0, tout = L.out_t;
+        const int tin = d.in0, tout = L.out_t, k = d.k;
         const int hi = c->th[tin], wi = c->tw[tin], ho = c->th[tout], wo = c->tw[tout];
-        const int taps = d.k * d.k;
-        const bf16* wf = (const bf16*)(c->packed + L.pk_f);
-        const bf16* wd = (const bf16*)(c->packed + L.pk_d);
-        // ---- forward: box mode on the (already reflect-padded) input
-        {
-            TcConvArgs& a = t.fa;
-            memset(&a, 0, sizeof(a));
-            a.Wb = wo % 128 == 0 ? 128 : wo;
-            a.Hb = 128 / a.Wb;
-            a.n_taps = taps; a.cchunks = d.cin / 64;
-            a.bn = d.cout < 256 ? d.cout : 256; a.n_blocks_n = d.cout / a.bn;
-            a.tiles_w = wo / a.Wb; a.tiles_per_img = a.tiles_w * (ho / a.Hb);
-            a.n0 = 0; a.nb = c->N;
-            a.out_P = wo; a.out_wvalid = wo; a.out_hvalid = ho; a.out_H = ho; a.out_W = wo; a.Cout = d.cout;
-            a.b_rows_per_tap = d.cout;
-            for (int kh = 0; kh < d.k; ++kh)
-                for (int kw = 0; kw < d.k; ++kw) { a.dw[kh * d.k + kw] = (short)kw; a.dh[kh * d.k + kw] = (short)kh; }
-            CG_TRY(tc_make_map_4d(&t.mapX, c->act(tin), d.cin, wi, hi, c->N, a.Wb, a.Hb));
-            CG_TRY(tc_make_map_2d(&t.mapWf, wf, d.cin, taps * d.cout, a.bn));
-        }
-        if (!c->bwd) continue;
-        const int hl = c->grad_halo[tout], P = wo + 2 * hl, HP = ho + 2 * hl;
-        const bf16* dy = (const bf16*)(c->arena + c->grad_off[tout]);
-        // ---- data gradient: flat mode over the zero-bordered dY, output = gradient of the padded input
-        {
-            TcConvArgs& a = t.da;
+        const bf16* wf = (const bf16*)(c->packed + L.pk_f);     // [tap][Cout_F][Cin_F]
+        const bf16* wd = (const bf16*)(c->packed + L.pk_d);     // [tap][Cin_F][Cout_F]  (native TF layout)
+        const void* x = c->act(tin);
+        const void* dy = c->bwd ? (const void*)(c->arena + c->grad_off[tout]) : nullptr;
+        if (L.tc == TC_S1_VALID) {
+            t.fwd.assign(1, TcConvLaunch());
+            CG_TRY(make_conv_launch(t.fwd[0], x, hi, wi, d.cin, c->N, wf, d.cout, k, 1, 0, 0, ho, wo));
+            if (!c->bwd) continue;
+            // data gradient in flat mode over the zero-bordered dY: output = gradient of the (padded) input, computed
+            // in the row pitch P of the dY buffer so that every tap is a constant row shift
+            const int hl = c->grad_halo[tout], P = wo + 2 * hl, HP = ho + 2 * hl;
+            t.dgrad.assign(1, TcConvLaunch());
+            TcConvArgs& a = t.dgrad[0].a;
             memset(&a, 0, sizeof(a));
             a.Wb = 128; a.Hb = 1;
-            a.n_taps = taps; a.cchunks = d.cout / 64;
+            a.n_taps = k * k; a.cchunks = d.cout / 64;
             a.bn = d.cin < 256 ? d.cin : 256; a.n_blocks_n = d.cin / a.bn;
             a.tiles_per_img = (hi * P + 127) / 128; a.tiles_w = a.tiles_per_img;
             a.n0 = 0; a.nb = c->N;
             a.out_P = P; a.out_wvalid = wi; a.out_hvalid = hi; a.out_H = hi; a.out_W = wi; a.Cout = d.cin;
+            a.out_sy = a.out_sx = 1;
             a.b_rows_per_tap = d.cin;
-            for (int kh = 0; kh < d.k; ++kh)
-                for (int kw = 0; kw < d.k; ++kw) {
-                    a.dw[kh * d.k + kw] = (short)((hl - kh) * P + (hl - kw));
-                    a.dh[kh * d.k + kw] = 0;
+            for (int kh = 0; kh < k; ++kh)
+                for (int kw = 0; kw < k; ++kw) {
+                    const int tp = kh * k + kw;
+                    a.tb[tp] = (short)tp;
+                    a.dw[tp] = (short)((hl - kh) * P + (hl - kw));
                 }
-            CG_TRY(tc_make_map_4d(&t.mapDYflat, dy, d.cout, HP * P, 1, c->N, 128, 1));
-            CG_TRY(tc_make_map_2d(&t.mapWd, wd, d.cout, taps * d.cin, a.bn));
-        }
-        // ---- weight gradient: 64-pixel K chunks of the input and of dY
-        {
-            TcWgradArgs& a = t.wa;
-            memset(&a, 0, sizeof(a));
-            a.Wk = wo % 64 == 0 ? 64 : wo;
-            a.Hk = 64 / a.Wk;
-            a.n_taps = taps; a.ci_blocks = d.cin / 128;
-            a.bn = d.cout < 256 ? d.cout : 256; a.co_blocks = d.cout / a.bn;
-            a.chunks_w = wo / a.Wk; a.chunks_per_img = a.chunks_w * (ho / a.Hk);
-            a.dy_off = hl; a.Cin = d.cin; a.Cout = d.cout;
-            for (int kh = 0; kh < d.k; ++kh)
-                for (int kw = 0; kw < d.k; ++kw) { a.dw[kh * d.k + kw] = (short)kw; a.dh[kh * d.k + kw] = (short)kh; }
-            CG_TRY(tc_make_map_4d(&t.mapXw, c->act(tin), d.cin, wi, hi, c->N, a.Wk, a.Hk));
-            CG_TRY(tc_make_map_4d(&t.mapDYw, dy, d.cout, P, HP, c->N, a.Wk, a.Hk));
+            CG_TRY(tc_make_map_act(&t.dgrad[0].mapA, dy, d.cout, HP * P, 1, c->N, 0, 128, 1));
+            CG_TRY(tc_make_map_2d(&t.dgrad[0].mapB, wd, d.cout, k * k * d.cin, a.bn));
+            CG_TRY(make_wgrad(t, x, hi, wi, d.cin, dy, ho, wo, d.cout, c->N, k, 1, 0, 0, hl));
+        } else if (L.tc == TC_CONV_S2) {
+            int pt, pl;
+            same_pad(hi, k, 2, &pt);
+            same_pad(wi, k, 2, &pl);
+            t.fwd.assign(1, TcConvLaunch());
+            CG_TRY(make_conv_launch(t.fwd[0], x, hi, wi, d.cin, c->N, wf, d.cout, k, 2, pt, pl, ho, wo));
+            if (!c->bwd) continue;
+            CG_TRY(make_class_launches(t.dgrad, dy, ho, wo, d.cout, c->N, wd, d.cin, k, pt, pl, hi, wi));
+            CG_TRY(make_wgrad(t, x, hi, wi, d.cin, dy, ho, wo, d.cout, c->N, k, 2, pt, pl, 0));
+        } else if (L.tc == TC_CONVT_S2) {
+            // F: (ho x wo x cout) -> (hi x wi x cin), stride 2, 'same' padding computed on the big grid
+            int pt, pl;
+            same_pad(ho, k, 2, &pt);
+            same_pad(wo, k, 2, &pl);
+            CG_TRY(make_class_launches(t.fwd, x, hi, wi, d.cin, c->N, wd, d.cout, k, pt, pl, ho, wo));
+            if (!c->bwd) continue;
+            t.dgrad.assign(1, TcConvLaunch());
+            CG_TRY(make_conv_launch(t.dgrad[0], dy, ho, wo, d.cout, c->N, wf, d.cin, k, 2, pt, pl, hi, wi));
+            CG_TRY(make_wgrad(t, dy, ho, wo, d.cout, x, hi, wi, d.cin, c->N, k, 2, pt, pl, 0));
+            t.wg_x_is_dy = 1;
         }
     }
     return CG_OK;
@@ -234,11 +340,12 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
             case CG_OP_CONV: {
                 ConvGeom g = conv_geom(d, N, h, w, oh, ow);
                 if (c->tc[i].on) {
-                    TcConvArgs a = c->tc[i].fa;
-                    a.nb = N;
-                    CG_TRY(tc_conv_launch(&c->tc[i].mapX, &c->tc[i].mapWf, (bf16*)y,
-                                          L.b_off >= 0 ? params + L.b_off : nullptr, a,
-                                          2.0 * N * oh * ow * (double)d.cout * d.k * d.k * d.cin, st));
+                    for (const TcConvLaunch& tl : c->tc[i].fwd) {
+                        TcConvArgs a = tl.a;
+                        a.nb = N;
+                        CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, (bf16*)y, L.b_off >= 0 ? params + L.b_off : nullptr, a,
+                                              tl.flop_share * 2.0 * N * oh * ow * (double)d.cout * d.k * d.k * d.cin, st));
+                    }
                 } else {
                     CG_TRY(k_conv_fwd<T>(x, params + L.w_off, L.b_off >= 0 ? params + L.b_off : nullptr, y, g, 0, st));
                 }
@@ -246,7 +353,16 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
             }
             case CG_OP_CONVT: {
                 ConvGeom g = conv_geom(d, N, h, w, oh, ow);
-                CG_TRY(k_conv_dgrad<T>(x, params + L.w_off, L.b_off >= 0 ? params + L.b_off : nullptr, y, g, 0, st));
+                if (c->tc[i].on) {
+                    for (const TcConvLaunch& tl : c->tc[i].fwd) {
+                        TcConvArgs a = tl.a;
+                        a.nb = N;
+                        CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, (bf16*)y, L.b_off >= 0 ? params + L.b_off : nullptr, a,
+                                              tl.flop_share * 2.0 * N * h * w * (double)d.cout * d.k * d.k * d.cin, st));
+                    }
+                } else {
+                    CG_TRY(k_conv_dgrad<T>(x, params + L.w_off, L.b_off >= 0 ? params + L.b_off : nullptr, y, g, 0, st));
+                }
                 break;
             }
             case CG_OP_INORM: {
@@ -320,10 +436,10 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
         switch (d.op) {
             case CG_OP_CONV: {
                 ConvGeom g = conv_geom(d, nb, h, w, oh, ow);
-                if (c->tc[i].on) {      // dy lives in a zero-bordered buffer (halo 2) written by the IN backward
+                if (c->tc[i].on && !acc) {
+                    // stride-1 layers: dy lives in a zero-bordered buffer (halo 2) written by the IN backward
                     const int hl = c->grad_halo[tout];
                     const double fl = 2.0 * nb * oh * ow * (double)d.cout * d.k * d.k * d.cin;
-                    if (acc) { cg_set_error("tensor-core dgrad cannot accumulate"); return CG_ERR_STATE; }
                     if (grads) {
                         TcWgradArgs a = c->tc[i].wa;
                         a.n0 = n0; a.nb = nb;
@@ -331,13 +447,15 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                         if (L.b_off >= 0)
                             CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * (oh + 2 * hl) * (ow + 2 * hl), d.cout, st));
                     }
-                    if (want_dx) {
-                        TcConvArgs a = c->tc[i].da;
-                        a.nb = nb;
-                        CG_TRY(tc_conv_launch(&c->tc[i].mapDYflat, &c->tc[i].mapWd, (bf16*)dx, nullptr, a, fl, st));
-                    }
+                    if (want_dx)
+                        for (const TcConvLaunch& tl : c->tc[i].dgrad) {
+                            TcConvArgs a = tl.a;
+                            a.nb = nb;
+                            CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, (bf16*)dx, nullptr, a, tl.flop_share * fl, st));
+                        }
                     break;
                 }
+                if (c->grad_halo[tout]) { cg_set_error("layer %d: zero-bordered dY needs the tensor-core path", i); return CG_ERR_STATE; }
                 if (grads) {
                     CG_TRY(k_conv_wgrad<T>(A(tin), dy, grads + L.w_off, g, st));
                     if (L.b_off >= 0) CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
@@ -347,6 +465,22 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
             }
             case CG_OP_CONVT: {
                 ConvGeom g = conv_geom(d, nb, h, w, oh, ow);
+                if (c->tc[i].on && !acc) {
+                    const double fl = 2.0 * nb * h * w * (double)d.cout * d.k * d.k * d.cin;
+                    if (grads) {
+                        TcWgradArgs a = c->tc[i].wa;      // X operand = dY (arena, sub-batch relative), dY operand = x (absolute)
+                        a.n0 = 0; a.nb = nb; a.y_n0 = n0;
+                        CG_TRY(tc_wgrad_launch(&c->tc[i].mapXw, &c->tc[i].mapDYw, grads + L.w_off, a, fl, st));
+                        if (L.b_off >= 0) CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
+                    }
+                    if (want_dx)
+                        for (const TcConvLaunch& tl : c->tc[i].dgrad) {
+                            TcConvArgs a = tl.a;
+                            a.nb = nb;
+                            CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, (bf16*)dx, nullptr, a, tl.flop_share * fl, st));
+                        }
+                    break;
+                }
                 if (grads) {
                     CG_TRY(k_conv_wgrad<T>(dy, A(tin), grads + L.w_off, g, st));
                     if (L.b_off >= 0) CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));

@@ -9,12 +9,16 @@
 #include "conv_tc.h"
 
 // tensor-core plan of one eligible conv layer for one planned call
+struct TcConvLaunch { CUtensorMap mapA, mapB; TcConvArgs a; double flop_share = 1.0; };
 struct TcLayer {
     bool on = false;
-    CUtensorMap mapX, mapWf, mapDYflat, mapWd, mapXw, mapDYw;
-    TcConvArgs fa, da;
+    std::vector<TcConvLaunch> fwd;      // 1 launch (Conv2D) or 4 stride-parity classes (Conv2DTranspose)
+    std::vector<TcConvLaunch> dgrad;    // 1 launch (stride 1: flat mode; Conv2DTranspose: a stride-2 conv of dY) or 4 classes
+    CUtensorMap mapXw, mapDYw;
     TcWgradArgs wa;
+    int wg_x_is_dy = 0;                 // Conv2DTranspose: the "X" operand of the weight gradient is dY
 };
+enum { TC_NONE = 0, TC_S1_VALID = 1, TC_CONV_S2 = 2, TC_CONVT_S2 = 3 };
 
 struct LayerInfo {
     cg_layer_desc d;
@@ -23,7 +27,7 @@ struct LayerInfo {
     bool skipped = false;   // ACT folded into the preceding INORM
     int fused_act = CG_ACT_NONE;
     float fused_slope = 0.f;
-    bool tc = false;        // 3x3 stride-1 'valid' conv with 64/128-multiple channels -> tcgen05 kernels (bf16 mode)
+    int tc = 0;             // TC_* kind: which convs run on the tcgen05 kernels in bf16 mode
     long long pk_f = 0, pk_d = 0;   // byte offsets of the packed bf16 weights ([tap][Cout][Cin] / [tap][Cin][Cout])
 };
 

@@ -35,6 +35,18 @@ def _block_net(cin, cout):
     return g
 
 
+def _updown_net(cin, cout, k):
+    """Conv k s2 same -> IN -> ReLU -> ConvT k s2 same -> IN: the down/up-sampling layers of resnet.py:49-60 and the
+    strided U-Net / discriminator stride-2 stacks (unet.py:54,66; resnet.py:96)."""
+    g = ir.Graph(channels=[cin])
+    x = g.conv(g.input, cout, k, stride=2, padding='same')
+    x = g.instance_norm(x, affine=True)
+    x = g.act(x, ir.ACT_RELU)
+    x = g.conv_transpose(x, cin, k, stride=2)
+    x = g.instance_norm(x, affine=False)
+    return g
+
+
 def _make(graph, tc, seed=0):
     os.environ["CG_DISABLE_TC"] = "0" if tc else "1"
     try:
@@ -51,6 +63,27 @@ def test_tc_conv_matches_cuda_core_conv(cin, cout, h, w, n):
     g = _block_net(cin, cout)
     a, b = _make(g, True), _make(g, False)
     rng = np.random.RandomState(1)
+    ws = [_bf16_round(v + (rng.normal(0, 0.05, v.shape) if v.ndim == 1 else 0)) for v in a.get_weights()]
+    a.set_weights(ws)
+    b.set_weights(ws)
+    x = _bf16_round(rng.uniform(-1, 1, (n, h, w, cin)))
+    dy = _bf16_round(rng.normal(0, 1, (n, h, w, cin)))
+    ya, dxa, ga = _net_grads(a, x, dy)
+    yb, dxb, gb = _net_grads(b, x, dy)
+    assert C.rel_l2(ya, yb) <= 4e-3, C.rel_l2(ya, yb)
+    assert C.rel_l2(dxa, dxb) <= 1e-2, C.rel_l2(dxa, dxb)
+    scale = max(np.linalg.norm(v) for v in gb)
+    for i, (u, v) in enumerate(zip(ga, gb)):
+        e = np.linalg.norm(u - v) / max(np.linalg.norm(v), 0.02 * scale)
+        assert e <= 1e-2, (i, u.shape, e)
+
+
+@pytest.mark.parametrize("cin,cout,k,h,w,n", [(64, 128, 3, 32, 32, 2), (128, 256, 4, 32, 64, 1), (256, 512, 4, 16, 16, 2),
+                                              (128, 64, 3, 256, 256, 1), (64, 128, 4, 64, 64, 3)])
+def test_tc_strided_and_transposed_convs_match_cuda_core(cin, cout, k, h, w, n):
+    g = _updown_net(cin, cout, k)
+    a, b = _make(g, True), _make(g, False)
+    rng = np.random.RandomState(3)
     ws = [_bf16_round(v + (rng.normal(0, 0.05, v.shape) if v.ndim == 1 else 0)) for v in a.get_weights()]
     a.set_weights(ws)
     b.set_weights(ws)
