@@ -126,7 +126,7 @@ def _check_grads(got, ref, mode, what="", sens=None):
                        each layer flips ~0.3 % of its units (|pre-activation| < 2^-8 sigma), i.e. adds ~sqrt(0.003) = 5.6 %
                        of gradient error per layer REGARDLESS of layer size, ~sqrt(L * 0.003) over L layers (25-35 %
                        for the two-generator cycle path).  The gate is therefore only a sanity bound (median <= 0.4,
-                       flat <= 0.6, any variable <= 0.9: a schedule / indexing bug gives >= 1); the tight evidence is
+                       flat <= 0.75, any variable <= 0.9: a schedule / indexing bug gives >= 1); the tight evidence is
                        (a) the fp32 check mode running the SAME templated schedule, (b) kernel-level bf16 parity
                        (tests/test_gpu_tc.py), (c) bf16 forward / loss parity at 2e-2.
     Variables whose reference gradient is zero by construction (biases feeding an instance norm) or tiny by
@@ -146,7 +146,7 @@ def _check_grads(got, ref, mode, what="", sens=None):
         flat = np.linalg.norm(np.concatenate([(g - r).ravel() for g, r in zip(got, ref)])) / \
             np.linalg.norm(np.concatenate([r.ravel() for r in ref]))
         assert np.median(errs) <= 0.4, (what, "median", float(np.median(errs)))
-        assert flat <= 0.6, (what, "flat", flat)
+        assert flat <= 0.75, (what, "flat", flat)
 
 
 def _oracle_sensitivity(make_grads, ref):
