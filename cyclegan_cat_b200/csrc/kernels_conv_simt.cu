@@ -196,39 +196,125 @@ __global__ void __launch_bounds__(128) conv_fwd_skinny(const T* __restrict__ x, 
     }
 }
 
-// weight gradient for Cout <= 4: thread = (kw, pair of input channels), blockIdx.y = kh, blockIdx.x = strip of output
-// pixels; every thread walks the strip accumulating 2 x Cout sums, then one atomicAdd each.
+// weight gradient for Cout <= 4: thread = (kw, pair of input channels), blockIdx.y = kh, blockIdx.x = (image, band of
+// output rows); every thread walks its band with 4 independent pixels in flight, accumulating 2 x Cout sums, then one
+// atomicAdd each (few blocks per address: the band is sized so that the grid is ~2 waves).
 template <typename T>
 __global__ void __launch_bounds__(1024) conv_wgrad_skinny(const T* __restrict__ x, const T* __restrict__ dy,
-                                                          float* __restrict__ dw, ConvGeom g, int strip) {
+                                                          float* __restrict__ dw, ConvGeom g, int rows_per_block,
+                                                          int bands) {
     const int half = g.Cin / 2;
     const int kw = threadIdx.x / half, ci = (threadIdx.x % half) * 2, kh = blockIdx.y;
     if (kw >= g.k) return;
-    const long long P = (long long)g.N * g.Ho * g.Wo;
-    const long long p0 = (long long)blockIdx.x * strip;
-    const long long p1 = p0 + strip < P ? p0 + strip : P;
+    const int n = blockIdx.x / bands, band = blockIdx.x % bands;
+    const int oh0 = band * rows_per_block;
+    const int oh1 = min(g.Ho, oh0 + rows_per_block);
     float acc[2][4] = {};
-    for (long long p = p0; p < p1; ++p) {
-        const int ow = (int)(p % g.Wo);
-        long long r = p / g.Wo;
-        const int oh = (int)(r % g.Ho), n = (int)(r / g.Ho);
-        const int ih = oh * g.s + kh - g.pt, iw = ow * g.s + kw - g.pl;
-        if (ih < 0 || ih >= g.Hi || iw < 0 || iw >= g.Wi) continue;
-        const T* xp = x + (((size_t)n * g.Hi + ih) * g.Wi + iw) * g.Cin + ci;
-        const float a0 = ldf(xp), a1 = ldf(xp + 1);
-        const T* dp = dy + (size_t)p * g.Cout;
+    // valid output columns for this kw: 0 <= ow*s + kw - pl < Wi
+    int ow_lo = 0, ow_hi = g.Wo;
+    while (ow_lo < g.Wo && ow_lo * g.s + kw - g.pl < 0) ++ow_lo;
+    while (ow_hi > ow_lo && (ow_hi - 1) * g.s + kw - g.pl >= g.Wi) --ow_hi;
+    for (int oh = oh0; oh < oh1; ++oh) {
+        const int ih = oh * g.s + kh - g.pt;
+        if (ih < 0 || ih >= g.Hi) continue;
+        const T* xrow = x + (((size_t)n * g.Hi + ih) * g.Wi + (kw - g.pl)) * g.Cin + ci;
+        const T* drow = dy + (((size_t)n * g.Ho + oh) * g.Wo) * g.Cout;
+        int ow = ow_lo;
+        for (; ow + 4 <= ow_hi; ow += 4) {
+            float a0[4], a1[4], d[4][4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-            if (c < g.Cout) {
-                const float d = ldf(dp + c);
-                acc[0][c] = fmaf(a0, d, acc[0][c]);
-                acc[1][c] = fmaf(a1, d, acc[1][c]);
+            for (int u = 0; u < 4; ++u) {
+                const T* xp = xrow + (size_t)(ow + u) * g.s * g.Cin;
+                a0[u] = ldf(xp); a1[u] = ldf(xp + 1);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) d[u][c] = c < g.Cout ? ldf(drow + (size_t)(ow + u) * g.Cout + c) : 0.f;
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { acc[0][c] = fmaf(a0[u], d[u][c], acc[0][c]); acc[1][c] = fmaf(a1[u], d[u][c], acc[1][c]); }
+        }
+        for (; ow < ow_hi; ++ow) {
+            const T* xp = xrow + (size_t)ow * g.s * g.Cin;
+            const float a0 = ldf(xp), a1 = ldf(xp + 1);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < g.Cout) {
+                    const float dd = ldf(drow + (size_t)ow * g.Cout + c);
+                    acc[0][c] = fmaf(a0, dd, acc[0][c]);
+                    acc[1][c] = fmaf(a1, dd, acc[1][c]);
+                }
+        }
     }
     float* o = dw + ((size_t)(kh * g.k + kw) * g.Cin + ci) * g.Cout;
     for (int c = 0; c < g.Cout; ++c) {
         atomicAdd(o + c, acc[0][c]);
         atomicAdd(o + g.Cout + c, acc[1][c]);
+    }
+}
+
+// data gradient for Cin <= 4 (image-side layers: the 7x7 stem, the first discriminator conv): one thread = one input
+// pixel x all Cin channels; weights [tap][co] -> float4 over ci in shared memory; dY read as 16-byte channel vectors.
+template <typename T, bool VEC8>
+__global__ void __launch_bounds__(128) conv_dgrad_skinny(const T* __restrict__ dy, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, T* __restrict__ dx, ConvGeom g,
+                                                         int accumulate) {
+    extern __shared__ float4 wsm[];      // [tap][co] -> (w[ci=0], w[1], w[2], w[3])
+    const int KT = g.k * g.k * g.Cout;
+    for (int i = threadIdx.x; i < KT; i += blockDim.x) {
+        const int tap = i / g.Cout, co = i - tap * g.Cout;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* pv = &v.x;
+        for (int c = 0; c < g.Cin; ++c) pv[c] = w[((size_t)tap * g.Cin + c) * g.Cout + co];
+        wsm[i] = v;
+    }
+    __syncthreads();
+    const long long total = (long long)g.N * g.Hi * g.Wi;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int iw = (int)(idx % g.Wi);
+        long long r = idx / g.Wi;
+        const int ih = (int)(r % g.Hi), n = (int)(r / g.Hi);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const T* dyn = dy + (size_t)n * g.Ho * g.Wo * g.Cout;
+        for (int kh = 0; kh < g.k; ++kh) {
+            const int th = ih + g.pt - kh;
+            if (th < 0 || th % g.s) continue;
+            const int oh = th / g.s;
+            if (oh >= g.Ho) continue;
+            for (int kw = 0; kw < g.k; ++kw) {
+                const int tw = iw + g.pl - kw;
+                if (tw < 0 || tw % g.s) continue;
+                const int ow = tw / g.s;
+                if (ow >= g.Wo) continue;
+                const T* p = dyn + ((size_t)oh * g.Wo + ow) * g.Cout;
+                const float4* wr = wsm + (kh * g.k + kw) * g.Cout;
+                if (VEC8) {
+                    for (int co = 0; co < g.Cout; co += 8) {
+                        float a[8];
+                        load_vec<T, VecWidth<T>::value == 8 ? 8 : 4>(p + co, *reinterpret_cast<float(*)[VecWidth<T>::value == 8 ? 8 : 4]>(a));
+                        if (VecWidth<T>::value == 4) load_vec<T, 4>(p + co + 4, *reinterpret_cast<float(*)[4]>(a + 4));
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 wv = wr[co + j];
+                            acc[0] = fmaf(a[j], wv.x, acc[0]); acc[1] = fmaf(a[j], wv.y, acc[1]);
+                            acc[2] = fmaf(a[j], wv.z, acc[2]); acc[3] = fmaf(a[j], wv.w, acc[3]);
+                        }
+                    }
+                } else {
+                    for (int co = 0; co < g.Cout; ++co) {
+                        const float a = ldf(p + co);
+                        const float4 wv = wr[co];
+                        acc[0] = fmaf(a, wv.x, acc[0]); acc[1] = fmaf(a, wv.y, acc[1]);
+                        acc[2] = fmaf(a, wv.z, acc[2]); acc[3] = fmaf(a, wv.w, acc[3]);
+                    }
+                }
+            }
+        }
+        T* o = dx + (size_t)idx * g.Cin;
+        for (int c = 0; c < g.Cin; ++c) {
+            float v = acc[c] + (bias ? bias[c] : 0.f);
+            stf(o + c, accumulate ? ldf(o + c) + v : v);
+        }
     }
 }
 
@@ -367,6 +453,21 @@ __global__ void __launch_bounds__(256) conv_dgrad_simt(const T* __restrict__ dy,
 
 template <typename T> int k_conv_dgrad(const T* dy, const float* w, const float* bias, T* dx, ConvGeom g,
                                        int accumulate, cudaStream_t st) {
+    const size_t wbytes = (size_t)g.k * g.k * g.Cout * sizeof(float4);
+    if (g.Cin <= 4 && wbytes <= 96 * 1024) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            CG_CUDA(cudaFuncSetAttribute(conv_dgrad_skinny<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            CG_CUDA(cudaFuncSetAttribute(conv_dgrad_skinny<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr_done = true;
+        }
+        long long work = (long long)g.N * g.Hi * g.Wi;
+        int blocks = (int)((work + 127) / 128 < 148 * 16 ? (work + 127) / 128 : 148 * 16);
+        if (g.Cout % 8 == 0) conv_dgrad_skinny<T, true><<<blocks, 128, wbytes, st>>>(dy, w, bias, dx, g, accumulate);
+        else conv_dgrad_skinny<T, false><<<blocks, 128, wbytes, st>>>(dy, w, bias, dx, g, accumulate);
+        CG_LAUNCH_CHECK();
+        return CG_OK;
+    }
     int Hc = cdiv(g.Hi, g.s), Wc = cdiv(g.Wi, g.s);
     long long M = (long long)g.N * Hc * Wc;
     dim3 grid(cdiv(M, BM), cdiv(g.Cin, BN), g.s * g.s);
@@ -468,11 +569,16 @@ template <typename T> int k_conv_wgrad(const T* x, const T* dy, float* dw, ConvG
     long long P = (long long)g.N * g.Ho * g.Wo;
     if (g.Cout <= 4 && g.Cin % 2 == 0 && g.k * (g.Cin / 2) <= 1024) {
         const int threads = ((g.k * (g.Cin / 2) + 31) / 32) * 32;
-        long long want = 148LL * 8 / g.k + 1;                   // strips so that the grid fills the GPU a few times
-        int strip = (int)((P + want - 1) / want);
-        if (strip < 64) strip = 64;
-        dim3 grid((unsigned)((P + strip - 1) / strip), g.k);
-        conv_wgrad_skinny<T><<<grid, threads, 0, st>>>(x, dy, dw, g, strip);
+        int per_sm = 2048 / threads;
+        if (per_sm < 1) per_sm = 1;
+        long long want_blocks = 148LL * per_sm * 2 / g.k + 1;          // ~2 waves over (image, row band) x kh
+        int bands = (int)((want_blocks + g.N - 1) / g.N);
+        if (bands < 1) bands = 1;
+        if (bands > g.Ho) bands = g.Ho;
+        const int rows = (g.Ho + bands - 1) / bands;
+        bands = (g.Ho + rows - 1) / rows;
+        dim3 grid((unsigned)(g.N * bands), g.k);
+        conv_wgrad_skinny<T><<<grid, threads, 0, st>>>(x, dy, dw, g, rows, bands);
         CG_LAUNCH_CHECK();
         return CG_OK;
     }

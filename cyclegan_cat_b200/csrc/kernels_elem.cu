@@ -141,11 +141,112 @@ __global__ void in_apply_kernel(const T* __restrict__ x, T* __restrict__ y, cons
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// "fast" instance-norm elementwise kernels: when the number of 16-byte channel vectors per pixel (CV = C/VEC) divides
+// the block size, every thread owns ONE channel vector for its whole life, so the per-channel constants (mean, rstd,
+// gamma, beta, backward sums) sit in registers and the loop body is load -> FMA -> store.  (The generic kernels above
+// re-read 2-6 per-channel scalars per element and are LSU-bound at ~1.3 TB/s.)
+// grid = (pixel blocks, N); block = 256 threads = (256/CV) pixels x CV channel vectors.
+// ------------------------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) in_apply_fast_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                            const float* __restrict__ stats,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, int act, float slope, int P,
+                                                            int C) {
+    const int CV = C / VEC, n = blockIdx.y;
+    const int cv = threadIdx.x % CV, prow = threadIdx.x / CV, ppb = 256 / CV;
+    float sc[VEC], sh[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        const int c = cv * VEC + j;
+        const float mean = stats[((size_t)n * C + c) * 2], rstd = stats[((size_t)n * C + c) * 2 + 1];
+        const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+        sc[j] = rstd * ga;
+        sh[j] = be - mean * sc[j];
+    }
+    const size_t base = (size_t)n * P * C + (size_t)cv * VEC;
+    for (int p = blockIdx.x * ppb + prow; p < P; p += gridDim.x * ppb) {
+        float v[VEC];
+        load_vec<T, VEC>(x + base + (size_t)p * C, v);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) v[j] = act_fwd(fmaf(v[j], sc[j], sh[j]), act, slope);
+        store_vec<T, VEC>(y + base + (size_t)p * C, v);
+    }
+}
+
+// dx = rstd*gamma*(g - S1/P - xhat*S2/P), optionally into a zero-bordered [H+2h][W+2h] buffer (halo > 0)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) in_bwd_apply_fast_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                                T* __restrict__ dx, const float* __restrict__ stats,
+                                                                const float* __restrict__ sums,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, int act, float slope,
+                                                                int H, int W, int C, int halo, float invP,
+                                                                int accumulate) {
+    const int CV = C / VEC, n = blockIdx.y;
+    const int cv = threadIdx.x % CV, prow = threadIdx.x / CV, ppb = 256 / CV;
+    float mean[VEC], rstd[VEC], ga[VEC], be[VEC], s1[VEC], s2[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        const int c = cv * VEC + j;
+        mean[j] = stats[((size_t)n * C + c) * 2];
+        rstd[j] = stats[((size_t)n * C + c) * 2 + 1];
+        ga[j] = gamma ? gamma[c] : 1.f;
+        be[j] = beta ? beta[c] : 0.f;
+        s1[j] = sums[((size_t)n * C + c) * 2] * invP;
+        s2[j] = sums[((size_t)n * C + c) * 2 + 1] * invP;
+    }
+    const int Hp = H + 2 * halo, Wp = W + 2 * halo;
+    const int PP = Hp * Wp;
+    const size_t in_base = (size_t)n * H * W * C + (size_t)cv * VEC;
+    const size_t out_base = (size_t)n * PP * C + (size_t)cv * VEC;
+    for (int pp = blockIdx.x * ppb + prow; pp < PP; pp += gridDim.x * ppb) {
+        const int hp = pp / Wp, wp = pp - hp * Wp;
+        const int h = hp - halo, w = wp - halo;
+        float o[VEC];
+        if (h >= 0 && h < H && w >= 0 && w < W) {
+            const size_t e = in_base + ((size_t)h * W + w) * C;
+            float v[VEC], g[VEC];
+            load_vec<T, VEC>(x + e, v);
+            load_vec<T, VEC>(dy + e, g);
+            if (accumulate) load_vec<T, VEC>(dx + out_base + (size_t)pp * C, o);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const float xh = (v[j] - mean[j]) * rstd[j];
+                const float gg = g[j] * act_grad_from_out(fmaf(xh, ga[j], be[j]), act, slope);
+                const float r = rstd[j] * ga[j] * (gg - s1[j] - xh * s2[j]);
+                o[j] = accumulate ? o[j] + r : r;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) o[j] = 0.f;
+        }
+        store_vec<T, VEC>(dx + out_base + (size_t)pp * C, o);
+    }
+}
+
+static inline bool fast_cv_ok(int C, int VW) {
+    if (C % VW) return false;
+    const int cv = C / VW;
+    return cv <= 256 && (256 % cv) == 0;
+}
+static inline int fast_blocks(int P, int C, int VW, int N) {
+    const int ppb = 256 / (C / VW);
+    long long want = (148LL * 8 + N - 1) / N;           // ~8 blocks per SM over all samples
+    long long maxb = (P + ppb - 1) / ppb;
+    long long b = want < maxb ? want : maxb;
+    return (int)(b < 1 ? 1 : b);
+}
+
 template <typename T> int k_in_apply(const T* x, T* y, const float* stats, const float* gamma, const float* beta,
                                      int act, float slope, int N, int P, int C, cudaStream_t st) {
     constexpr int VW = VecWidth<T>::value;
     size_t PC = (size_t)P * C;
-    if (C % VW == 0) {
+    if (fast_cv_ok(C, VW)) {
+        dim3 grid(fast_blocks(P, C, VW, N), N);
+        in_apply_fast_kernel<T, VW><<<grid, 256, 0, st>>>(x, y, stats, gamma, beta, act, slope, P, C);
+    } else if (C % VW == 0) {
         dim3 grid(ew_blocks(PC / VW), N);
         in_apply_kernel<T, VW><<<grid, EW_THREADS, 0, st>>>(x, y, stats, gamma, beta, act, slope, PC / VW, C);
     } else {
@@ -247,7 +348,14 @@ template <typename T> int k_in_bwd(const T* x, const T* dy, T* dx, const float* 
         in_param_grad_kernel<<<cdiv(C, 128), 128, 0, st>>>(scratch, dgamma, dbeta, N, C);
         CG_LAUNCH_CHECK();
     }
-    if (dx && halo > 0) {
+    if (dx && fast_cv_ok(C, VecWidth<T>::value) && (halo == 0 || (!accumulate && W > 0 && P % W == 0))) {
+        constexpr int VW = VecWidth<T>::value;
+        const int Wd = halo > 0 ? W : P, Hd = halo > 0 ? P / W : 1;     // halo == 0: treat the plane as one row
+        dim3 g2(fast_blocks((Hd + 2 * halo) * (Wd + 2 * halo), C, VW, N), N);
+        in_bwd_apply_fast_kernel<T, VW><<<g2, 256, 0, st>>>(x, dy, dx, stats, scratch, gamma, beta, act, slope, Hd, Wd, C,
+                                                           halo, 1.f / (float)P, accumulate);
+        CG_LAUNCH_CHECK();
+    } else if (dx && halo > 0) {
         constexpr int VW = VecWidth<T>::value;
         if (accumulate || C % VW != 0 || W <= 0 || P % W != 0) {
             cg_set_error("halo IN backward: unsupported configuration");
