@@ -228,12 +228,14 @@ class CycleGan:
         if self._trainer is None:
             raise RuntimeError("call enable_data_parallel() after the first _ensure_trainer/step shape is known; "
                                "use prepare(B, H, W) first")
-        buf = (ctypes.c_char * 128)()
-        if rank == 0:
+        from ..parallel import exchange_unique_id
+
+        def make_id():
+            buf = (ctypes.c_char * 128)()
             _lib.check(_lib.load().cg_comm_unique_id(buf), "cg_comm_unique_id")
-        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device="cuda")
-        dist.broadcast(t, src=0)
-        buf = (ctypes.c_char * 128)(*bytes(t.cpu().tolist()))
+            return bytes(buf)
+        raw = exchange_unique_id(make_id, dist, device="cuda")
+        buf = (ctypes.c_char * 128)(*raw)
         _lib.check(_lib.load().cg_trainer_comm_init(self._trainer, buf, rank, world), "cg_trainer_comm_init")
         self._world = world
 

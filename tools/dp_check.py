@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Multi-GPU check (run under torchrun): data-parallel training over n ranks with B pairs each must equal the
+single-process step on the global batch n*B (fp32 check mode; equality up to summation order), SURVEY.md 8e.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dp_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from cyclegan_cat_b200.cyclegan.model import CycleGan  # noqa: E402
+from cyclegan_cat_b200.parallel import shard_batch  # noqa: E402
+from tests import common as C  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    per = 2
+    rng_a, rng_b = np.random.RandomState(1234), np.random.RandomState(1235)
+    a = rng_a.uniform(-1, 1, (per * world, 64, 64, 3)).astype(np.float32)
+    b = rng_b.uniform(-1, 1, (per * world, 64, 64, 3)).astype(np.float32)
+
+    def make(seed_base=42):
+        g = CycleGan(C.model_config(C.FIX_RESNET, C.FIX_SIMPLE), C.train_config(), mode="fp32")
+        for i, n in enumerate((g.g_AB, g.g_BA, g.d_A, g.d_B)):
+            n.initialize(seed_base + i)
+        return g
+
+    dp = make()
+    dp.prepare(per, 64, 64)
+    dp.enable_data_parallel()
+    sa, sb = shard_batch(a, b, rank, world)
+    for _ in range(3):
+        dp.train_step(sa, sb)
+    torch.cuda.synchronize()
+    ok = True
+    if rank == 0:
+        ref = make()
+        for _ in range(3):
+            ref.train_step(a, b)
+        torch.cuda.synchronize()
+        for name in ("g_AB", "g_BA", "d_A", "d_B"):
+            for v, r in zip(getattr(dp, name).get_weights(), getattr(ref, name).get_weights()):
+                if r.ndim == 4:
+                    e = np.linalg.norm(v - r) / np.linalg.norm(r)
+                    if e > 2e-3:
+                        ok = False
+                        print("MISMATCH", name, r.shape, e)
+        print("dp_check", "OK" if ok else "FAILED", "world", world)
+    # all ranks must hold identical weights
+    flat = dp.g_AB.device_params().clone()
+    ref0 = flat.clone()
+    dist.broadcast(ref0, src=0)
+    same = bool(torch.equal(flat, ref0))
+    t = torch.tensor([int(same)], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("replicas identical:", bool(t.item()))
+    dist.destroy_process_group()
+    sys.exit(0 if ok and t.item() else 1)
+
+
+if __name__ == "__main__":
+    main()
