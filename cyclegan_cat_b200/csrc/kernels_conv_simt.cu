@@ -196,6 +196,83 @@ __global__ void __launch_bounds__(128) conv_fwd_skinny(const T* __restrict__ x, 
     }
 }
 
+// stride-1 skinny forward with the input tile (output tile + halo) staged ONCE in shared memory (the 7x7 head reads
+// each input pixel 49 times): block = 32 x (8*PX) output pixels, thread = PX vertically stacked pixels x Cout
+// channels, 16-byte channel vectors XOR-swizzled by pixel so that a warp reading 32 neighbouring pixels is
+// bank-conflict free, weights broadcast as float4 rows.
+template <typename T, int PX>
+__global__ void __launch_bounds__(256) conv_fwd_skinny_tiled(const T* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, T* __restrict__ y,
+                                                             ConvGeom g, int accumulate, int tiles_w, int tiles_h) {
+    constexpr int VEC = VecWidth<T>::value;
+    constexpr int TW = 32, TH = 8 * PX;
+    extern __shared__ float4 smem4[];
+    const int K = g.k * g.k * g.Cin;
+    float4* wsm = smem4;                                  // [K] weight rows
+    uint4* xs = reinterpret_cast<uint4*>(smem4 + K);      // [IH*IW][nv] 16-byte vectors
+    const int nv = g.Cin / VEC, IW = TW + g.k - 1, IH = TH + g.k - 1;
+    for (int i = threadIdx.x; i < K; i += 256) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* pv = &v.x;
+        for (int c = 0; c < g.Cout; ++c) pv[c] = w[(size_t)i * g.Cout + c];
+        wsm[i] = v;
+    }
+    int t = blockIdx.x;
+    const int tw = t % tiles_w; t /= tiles_w;
+    const int th = t % tiles_h;
+    const int n = t / tiles_h;
+    const int ow0 = tw * TW, oh0 = th * TH;
+    const int iw0 = ow0 - g.pl, ih0 = oh0 - g.pt;
+    const T* xn = x + (size_t)n * g.Hi * g.Wi * g.Cin;
+    for (int i = threadIdx.x; i < IH * IW * nv; i += 256) {
+        const int cv = i % nv, p = i / nv;
+        const int ph = p / IW, pw = p - ph * IW;
+        const int ih = ih0 + ph, iw = iw0 + pw;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (ih >= 0 && ih < g.Hi && iw >= 0 && iw < g.Wi)
+            v = *reinterpret_cast<const uint4*>(xn + ((size_t)ih * g.Wi + iw) * g.Cin + cv * VEC);
+        xs[p * nv + (cv ^ (p & (nv - 1)))] = v;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    float acc[PX][4] = {};
+    for (int kh = 0; kh < g.k; ++kh)
+        for (int kw = 0; kw < g.k; ++kw) {
+            const float4* wr = wsm + (kh * g.k + kw) * g.Cin;
+            int pbase[PX];
+#pragma unroll
+            for (int q = 0; q < PX; ++q) pbase[q] = (ty + 8 * q + kh) * IW + tx + kw;
+            for (int cv = 0; cv < nv; ++cv) {
+                float a[PX][VEC];
+#pragma unroll
+                for (int q = 0; q < PX; ++q) {
+                    const uint4 raw = xs[pbase[q] * nv + (cv ^ (pbase[q] & (nv - 1)))];
+                    load_vec<T, VEC>(reinterpret_cast<const T*>(&raw), a[q]);
+                }
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    const float4 wv = wr[cv * VEC + j];
+#pragma unroll
+                    for (int q = 0; q < PX; ++q) {
+                        acc[q][0] = fmaf(a[q][j], wv.x, acc[q][0]); acc[q][1] = fmaf(a[q][j], wv.y, acc[q][1]);
+                        acc[q][2] = fmaf(a[q][j], wv.z, acc[q][2]); acc[q][3] = fmaf(a[q][j], wv.w, acc[q][3]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+    for (int q = 0; q < PX; ++q) {
+        const int oh = oh0 + ty + 8 * q, ow = ow0 + tx;
+        if (oh < g.Ho && ow < g.Wo) {
+            T* o = y + (((size_t)n * g.Ho + oh) * g.Wo + ow) * g.Cout;
+            for (int c = 0; c < g.Cout; ++c) {
+                float v = acc[q][c] + (bias ? bias[c] : 0.f);
+                stf(o + c, accumulate ? ldf(o + c) + v : v);
+            }
+        }
+    }
+}
+
 // weight gradient for Cout <= 4: thread = (kw, pair of input channels), blockIdx.y = kh, blockIdx.x = (image, band of
 // output rows); every thread walks its band with 4 independent pixels in flight, accumulating 2 x Cout sums, then one
 // atomicAdd each (few blocks per address: the band is sized so that the grid is ~2 waves).
@@ -251,6 +328,61 @@ __global__ void __launch_bounds__(1024) conv_wgrad_skinny(const T* __restrict__ 
         atomicAdd(o + c, acc[0][c]);
         atomicAdd(o + g.Cout + c, acc[1][c]);
     }
+}
+
+// vectorised variant: thread = (kw, 16-byte vector of input channels); 4 pixels in flight per thread
+template <typename T>
+__global__ void __launch_bounds__(1024) conv_wgrad_skinny_vec(const T* __restrict__ x, const T* __restrict__ dy,
+                                                              float* __restrict__ dw, ConvGeom g, int rows_per_block,
+                                                              int bands) {
+    constexpr int VEC = VecWidth<T>::value;
+    const int nv = g.Cin / VEC;
+    const int kw = threadIdx.x / nv, ci = (threadIdx.x % nv) * VEC, kh = blockIdx.y;
+    if (kw >= g.k) return;
+    const int n = blockIdx.x / bands, band = blockIdx.x % bands;
+    const int oh0 = band * rows_per_block;
+    const int oh1 = min(g.Ho, oh0 + rows_per_block);
+    float acc[VEC][4] = {};
+    int ow_lo = 0, ow_hi = g.Wo;
+    while (ow_lo < g.Wo && ow_lo * g.s + kw - g.pl < 0) ++ow_lo;
+    while (ow_hi > ow_lo && (ow_hi - 1) * g.s + kw - g.pl >= g.Wi) --ow_hi;
+    for (int oh = oh0; oh < oh1; ++oh) {
+        const int ih = oh * g.s + kh - g.pt;
+        if (ih < 0 || ih >= g.Hi) continue;
+        const T* xrow = x + (((size_t)n * g.Hi + ih) * g.Wi + (kw - g.pl)) * g.Cin + ci;
+        const T* drow = dy + (((size_t)n * g.Ho + oh) * g.Wo) * g.Cout;
+        int ow = ow_lo;
+        for (; ow + 4 <= ow_hi; ow += 4) {
+            float a[4][VEC], d[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                load_vec<T, VEC>(xrow + (size_t)(ow + u) * g.s * g.Cin, a[u]);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) d[u][c] = c < g.Cout ? ldf(drow + (size_t)(ow + u) * g.Cout + c) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[j][c] = fmaf(a[u][j], d[u][c], acc[j][c]);
+        }
+        for (; ow < ow_hi; ++ow) {
+            float a[VEC];
+            load_vec<T, VEC>(xrow + (size_t)ow * g.s * g.Cin, a);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < g.Cout) {
+                    const float dd = ldf(drow + (size_t)ow * g.Cout + c);
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) acc[j][c] = fmaf(a[j], dd, acc[j][c]);
+                }
+        }
+    }
+    float* o = dw + ((size_t)(kh * g.k + kw) * g.Cin + ci) * g.Cout;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)
+        for (int c = 0; c < g.Cout; ++c) atomicAdd(o + (size_t)j * g.Cout + c, acc[j][c]);
 }
 
 // data gradient for Cin <= 4 (image-side layers: the 7x7 stem, the first discriminator conv): one thread = one input
@@ -322,6 +454,24 @@ template <typename T> int k_conv_fwd(const T* x, const float* w, const float* bi
                                      cudaStream_t st) {
     long long M = (long long)g.N * g.Ho * g.Wo;
     const size_t wbytes = (size_t)g.k * g.k * g.Cin * sizeof(float4);
+    {   // stride-1 skinny conv with enough reuse: stage the input tile in shared memory
+        constexpr int VW = VecWidth<T>::value;
+        constexpr int PX = sizeof(T) == 2 ? 2 : 1;
+        const int nv = g.Cin % VW == 0 ? g.Cin / VW : 0;
+        const size_t tile_bytes = (size_t)(8 * PX + g.k - 1) * (32 + g.k - 1) * g.Cin * sizeof(T);
+        if (g.Cout <= 4 && g.s == 1 && g.k >= 3 && nv >= 1 && (nv & (nv - 1)) == 0 && wbytes + tile_bytes <= 200 * 1024) {
+            static bool attr_t = false;
+            if (!attr_t) {
+                CG_CUDA(cudaFuncSetAttribute(conv_fwd_skinny_tiled<T, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr_t = true;
+            }
+            const int tiles_w = cdiv(g.Wo, 32), tiles_h = cdiv(g.Ho, 8 * PX);
+            conv_fwd_skinny_tiled<T, PX><<<g.N * tiles_w * tiles_h, 256, wbytes + tile_bytes, st>>>(x, w, bias, y, g, accumulate,
+                                                                                                 tiles_w, tiles_h);
+            CG_LAUNCH_CHECK();
+            return CG_OK;
+        }
+    }
     if (g.Cout <= 4 && wbytes <= 96 * 1024) {
         static bool attr_done = false;
         if (!attr_done) {
@@ -451,6 +601,62 @@ __global__ void __launch_bounds__(256) conv_dgrad_simt(const T* __restrict__ dy,
     }
 }
 
+// data gradient of a stride-1 conv with Cout <= 4 (the 7x7 tanh head: 3 -> 64 channels back): K = taps x Cout is tiny
+// and the output is wide, so one thread = one input pixel x one 16-byte vector of input channels; weights
+// [tap][ci] -> float4 over co in shared memory, dY scalars come from L1.
+template <typename T>
+__global__ void __launch_bounds__(256) conv_dgrad_thin(const T* __restrict__ dy, const float* __restrict__ w,
+                                                       T* __restrict__ dx, ConvGeom g, int accumulate) {
+    constexpr int VEC = VecWidth<T>::value;
+    extern __shared__ float4 wsm[];      // [tap*Cin + ci] -> (w[co=0..3])
+    const int K = g.k * g.k * g.Cin;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* pv = &v.x;
+        for (int c = 0; c < g.Cout; ++c) pv[c] = w[(size_t)i * g.Cout + c];
+        wsm[i] = v;
+    }
+    __syncthreads();
+    const int nv = g.Cin / VEC;
+    const long long total = (long long)g.N * g.Hi * g.Wi * nv;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % nv);
+        long long r = idx / nv;
+        const int iw = (int)(r % g.Wi); r /= g.Wi;
+        const int ih = (int)(r % g.Hi), n = (int)(r / g.Hi);
+        float acc[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+        const T* dyn = dy + (size_t)n * g.Ho * g.Wo * g.Cout;
+        for (int kh = 0; kh < g.k; ++kh) {
+            const int oh = ih + g.pt - kh;
+            if (oh < 0 || oh >= g.Ho) continue;
+            for (int kw = 0; kw < g.k; ++kw) {
+                const int ow = iw + g.pl - kw;
+                if (ow < 0 || ow >= g.Wo) continue;
+                const T* p = dyn + ((size_t)oh * g.Wo + ow) * g.Cout;
+                float d[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) d[c] = c < g.Cout ? ldf(p + c) : 0.f;
+                const float4* wr = wsm + (kh * g.k + kw) * g.Cin + cv * VEC;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    const float4 wv = wr[j];
+                    acc[j] = fmaf(d[0], wv.x, fmaf(d[1], wv.y, fmaf(d[2], wv.z, fmaf(d[3], wv.w, acc[j]))));
+                }
+            }
+        }
+        T* o = dx + (((size_t)n * g.Hi + ih) * g.Wi + iw) * g.Cin + cv * VEC;
+        if (accumulate) {
+            float old[VEC];
+            load_vec<T, VEC>(o, old);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[j] += old[j];
+        }
+        store_vec<T, VEC>(o, acc);
+    }
+}
+
 template <typename T> int k_conv_dgrad(const T* dy, const float* w, const float* bias, T* dx, ConvGeom g,
                                        int accumulate, cudaStream_t st) {
     const size_t wbytes = (size_t)g.k * g.k * g.Cout * sizeof(float4);
@@ -465,6 +671,19 @@ template <typename T> int k_conv_dgrad(const T* dy, const float* w, const float*
         int blocks = (int)((work + 127) / 128 < 148 * 16 ? (work + 127) / 128 : 148 * 16);
         if (g.Cout % 8 == 0) conv_dgrad_skinny<T, true><<<blocks, 128, wbytes, st>>>(dy, w, bias, dx, g, accumulate);
         else conv_dgrad_skinny<T, false><<<blocks, 128, wbytes, st>>>(dy, w, bias, dx, g, accumulate);
+        CG_LAUNCH_CHECK();
+        return CG_OK;
+    }
+    if (g.Cout <= 4 && g.s == 1 && !bias && g.Cin % VecWidth<T>::value == 0 &&
+        (size_t)g.k * g.k * g.Cin * sizeof(float4) <= 96 * 1024) {
+        static bool attr_thin = false;
+        if (!attr_thin) {
+            CG_CUDA(cudaFuncSetAttribute(conv_dgrad_thin<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr_thin = true;
+        }
+        long long work = (long long)g.N * g.Hi * g.Wi * (g.Cin / VecWidth<T>::value);
+        int blocks = (int)((work + 255) / 256 < 148 * 16 ? (work + 255) / 256 : 148 * 16);
+        conv_dgrad_thin<T><<<blocks, 256, (size_t)g.k * g.k * g.Cin * sizeof(float4), st>>>(dy, w, dx, g, accumulate);
         CG_LAUNCH_CHECK();
         return CG_OK;
     }
@@ -567,6 +786,21 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt(const T* __restrict__ x, 
 template <typename T> int k_conv_wgrad(const T* x, const T* dy, float* dw, ConvGeom g, cudaStream_t st) {
     int Mrows = g.k * g.k * g.Cin;
     long long P = (long long)g.N * g.Ho * g.Wo;
+    if (g.Cout <= 4 && g.Cin % VecWidth<T>::value == 0 && g.k * (g.Cin / VecWidth<T>::value) <= 1024) {
+        const int threads = ((g.k * (g.Cin / VecWidth<T>::value) + 31) / 32) * 32;
+        int per_sm = 2048 / threads;
+        if (per_sm > 32) per_sm = 32;
+        long long want_blocks = 148LL * per_sm * 2 / g.k + 1;
+        int bands = (int)((want_blocks + g.N - 1) / g.N);
+        if (bands < 1) bands = 1;
+        if (bands > g.Ho) bands = g.Ho;
+        const int rows = (g.Ho + bands - 1) / bands;
+        bands = (g.Ho + rows - 1) / rows;
+        dim3 grid((unsigned)(g.N * bands), g.k);
+        conv_wgrad_skinny_vec<T><<<grid, threads, 0, st>>>(x, dy, dw, g, rows, bands);
+        CG_LAUNCH_CHECK();
+        return CG_OK;
+    }
     if (g.Cout <= 4 && g.Cin % 2 == 0 && g.k * (g.Cin / 2) <= 1024) {
         const int threads = ((g.k * (g.Cin / 2) + 31) / 32) * 32;
         int per_sm = 2048 / threads;

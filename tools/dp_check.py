@@ -37,22 +37,44 @@ def main():
     dp.prepare(per, 64, 64)
     dp.enable_data_parallel()
     sa, sb = shard_batch(a, b, rank, world)
-    for _ in range(3):
-        dp.train_step(sa, sb)
+    # (1) gradients: the all-reduced SUM of the per-rank gradients / world == global-batch gradient
+    _, g_dp = dp.compute_gradients(sa, sb)
     torch.cuda.synchronize()
     ok = True
+    ref = None
     if rank == 0:
         ref = make()
-        for _ in range(3):
+        _, g_ref = ref.compute_gradients(a, b)
+        worst = 0.0
+        for name in ("g_AB", "g_BA", "d_A", "d_B"):
+            scale = max(np.linalg.norm(r) for r in g_ref[name])
+            for v, r in zip(g_dp[name], g_ref[name]):
+                e = np.linalg.norm(v / world - r) / max(np.linalg.norm(r), 0.02 * scale)
+                worst = max(worst, e)
+                # fp32 summation order differs between the 2 x B and the 1 x 2B runs; a single ReLU-mask flip moves
+                # every upstream gradient by 0.1-4 % (DESIGN.md 'gradient tolerance'), so the gate is 2e-2 here;
+                # exact equivalence is proven in fp64 by tests/test_parallel_cpu.py
+                if e > 2e-2:
+                    ok = False
+                    print("GRAD MISMATCH", name, r.shape, e)
+        print("dp_check gradients worst rel err", worst)
+    # (2) three full steps: Adam's first updates are ~lr*sign(g), so entries with |g| ~ 0 may differ; loose bound
+    dp.apply_gradients()
+    for _ in range(2):
+        dp.train_step(sa, sb)
+    torch.cuda.synchronize()
+    if rank == 0:
+        ref.apply_gradients()
+        for _ in range(2):
             ref.train_step(a, b)
         torch.cuda.synchronize()
         for name in ("g_AB", "g_BA", "d_A", "d_B"):
             for v, r in zip(getattr(dp, name).get_weights(), getattr(ref, name).get_weights()):
                 if r.ndim == 4:
                     e = np.linalg.norm(v - r) / np.linalg.norm(r)
-                    if e > 2e-3:
+                    if e > 2e-2:
                         ok = False
-                        print("MISMATCH", name, r.shape, e)
+                        print("WEIGHT MISMATCH", name, r.shape, e)
         print("dp_check", "OK" if ok else "FAILED", "world", world)
     # all ranks must hold identical weights
     flat = dp.g_AB.device_params().clone()
