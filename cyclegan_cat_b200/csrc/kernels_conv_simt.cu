@@ -601,62 +601,6 @@ __global__ void __launch_bounds__(256) conv_dgrad_simt(const T* __restrict__ dy,
     }
 }
 
-// data gradient of a stride-1 conv with Cout <= 4 (the 7x7 tanh head: 3 -> 64 channels back): K = taps x Cout is tiny
-// and the output is wide, so one thread = one input pixel x one 16-byte vector of input channels; weights
-// [tap][ci] -> float4 over co in shared memory, dY scalars come from L1.
-template <typename T>
-__global__ void __launch_bounds__(256) conv_dgrad_thin(const T* __restrict__ dy, const float* __restrict__ w,
-                                                       T* __restrict__ dx, ConvGeom g, int accumulate) {
-    constexpr int VEC = VecWidth<T>::value;
-    extern __shared__ float4 wsm[];      // [tap*Cin + ci] -> (w[co=0..3])
-    const int K = g.k * g.k * g.Cin;
-    for (int i = threadIdx.x; i < K; i += blockDim.x) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        float* pv = &v.x;
-        for (int c = 0; c < g.Cout; ++c) pv[c] = w[(size_t)i * g.Cout + c];
-        wsm[i] = v;
-    }
-    __syncthreads();
-    const int nv = g.Cin / VEC;
-    const long long total = (long long)g.N * g.Hi * g.Wi * nv;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int cv = (int)(idx % nv);
-        long long r = idx / nv;
-        const int iw = (int)(r % g.Wi); r /= g.Wi;
-        const int ih = (int)(r % g.Hi), n = (int)(r / g.Hi);
-        float acc[VEC];
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
-        const T* dyn = dy + (size_t)n * g.Ho * g.Wo * g.Cout;
-        for (int kh = 0; kh < g.k; ++kh) {
-            const int oh = ih + g.pt - kh;
-            if (oh < 0 || oh >= g.Ho) continue;
-            for (int kw = 0; kw < g.k; ++kw) {
-                const int ow = iw + g.pl - kw;
-                if (ow < 0 || ow >= g.Wo) continue;
-                const T* p = dyn + ((size_t)oh * g.Wo + ow) * g.Cout;
-                float d[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) d[c] = c < g.Cout ? ldf(p + c) : 0.f;
-                const float4* wr = wsm + (kh * g.k + kw) * g.Cin + cv * VEC;
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    const float4 wv = wr[j];
-                    acc[j] = fmaf(d[0], wv.x, fmaf(d[1], wv.y, fmaf(d[2], wv.z, fmaf(d[3], wv.w, acc[j]))));
-                }
-            }
-        }
-        T* o = dx + (((size_t)n * g.Hi + ih) * g.Wi + iw) * g.Cin + cv * VEC;
-        if (accumulate) {
-            float old[VEC];
-            load_vec<T, VEC>(o, old);
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) acc[j] += old[j];
-        }
-        store_vec<T, VEC>(o, acc);
-    }
-}
-
 template <typename T> int k_conv_dgrad(const T* dy, const float* w, const float* bias, T* dx, ConvGeom g,
                                        int accumulate, cudaStream_t st) {
     const size_t wbytes = (size_t)g.k * g.k * g.Cout * sizeof(float4);
@@ -671,19 +615,6 @@ template <typename T> int k_conv_dgrad(const T* dy, const float* w, const float*
         int blocks = (int)((work + 127) / 128 < 148 * 16 ? (work + 127) / 128 : 148 * 16);
         if (g.Cout % 8 == 0) conv_dgrad_skinny<T, true><<<blocks, 128, wbytes, st>>>(dy, w, bias, dx, g, accumulate);
         else conv_dgrad_skinny<T, false><<<blocks, 128, wbytes, st>>>(dy, w, bias, dx, g, accumulate);
-        CG_LAUNCH_CHECK();
-        return CG_OK;
-    }
-    if (g.Cout <= 4 && g.s == 1 && !bias && g.Cin % VecWidth<T>::value == 0 &&
-        (size_t)g.k * g.k * g.Cin * sizeof(float4) <= 96 * 1024) {
-        static bool attr_thin = false;
-        if (!attr_thin) {
-            CG_CUDA(cudaFuncSetAttribute(conv_dgrad_thin<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            attr_thin = true;
-        }
-        long long work = (long long)g.N * g.Hi * g.Wi * (g.Cin / VecWidth<T>::value);
-        int blocks = (int)((work + 255) / 256 < 148 * 16 ? (work + 255) / 256 : 148 * 16);
-        conv_dgrad_thin<T><<<blocks, 256, (size_t)g.k * g.k * g.Cin * sizeof(float4), st>>>(dy, w, dx, g, accumulate);
         CG_LAUNCH_CHECK();
         return CG_OK;
     }
