@@ -162,7 +162,20 @@ extern "C" int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode
                 kind = TC_CONV_S2;
             else if (d.op == CG_OP_CONVT && d.stride == 2 && (d.k == 3 || d.k == 4) && chan_ok(d.cout, d.cin))
                 kind = TC_CONVT_S2;
-            if (kind) {
+            else if (d.op == CG_OP_CONV && d.stride == 1 && !d.same && d.k >= 3 && d.cin <= 4 && d.k * d.cin <= 64 &&
+                     d.cout % 64 == 0 && d.cout <= 256)
+                kind = TC_STEM;         // c7s1-f stem (resnet.py:39-40): horizontal taps unfolded into channels
+            else if (d.op == CG_OP_CONV && d.stride == 1 && !d.same && d.k >= 3 && d.cout <= 4 && d.k * d.cout <= 32 &&
+                     d.cin % 64 == 0 && d.cin <= 256)
+                kind = TC_HEAD;         // c7s1-3 tanh head (resnet.py:82)
+            if (kind == TC_STEM) {
+                L.tc = kind;
+                L.pk_f = (long long)pk; pk += align_up((size_t)d.k * d.cout * 64 * 2, 1024);
+            } else if (kind == TC_HEAD) {
+                L.tc = kind;
+                L.pk_f = (long long)pk; pk += align_up((size_t)d.k * 32 * d.cin * 2, 1024);
+                L.pk_d = (long long)pk; pk += align_up((size_t)d.k * d.cin * 64 * 2, 1024);
+            } else if (kind) {
                 L.tc = kind;
                 const size_t bytes = align_up((size_t)d.k * d.k * d.cin * d.cout * 2, 1024);
                 L.pk_f = (long long)pk; pk += bytes;
@@ -209,7 +222,7 @@ extern "C" int cg_net_out_shape(cg_net_t net, int N, int H, int W, int out[4]) {
 }
 
 // workspace of a single-net call: [activations | gradient arena | dy/dx staging in activation dtype]
-struct SingleLayout { size_t act, arena, dy, dx, packed, total; };
+struct SingleLayout { size_t act, arena, dy, dx, packed, tcs, total; };
 static int single_layout(const cg_net_s* net, CallCtx* ctx, int N, int H, int W, bool bwd, SingleLayout* lay) {
     CG_TRY(net_plan(net, N, H, W, bwd, ctx));
     size_t es = net->elem_size();
@@ -218,7 +231,8 @@ static int single_layout(const cg_net_s* net, CallCtx* ctx, int N, int H, int W,
     lay->dy = lay->arena + align_up(ctx->grad_bytes, 256);
     lay->dx = lay->dy + (bwd ? align_up((size_t)N * ctx->sample_elems(net->out_tensor()) * es, 256) : 0);
     lay->packed = align_up(lay->dx + (bwd ? align_up((size_t)N * ctx->sample_elems(0) * es, 256) : 0), 1024);
-    lay->total = lay->packed + net->packed_bytes;
+    lay->tcs = align_up(lay->packed + net->packed_bytes, 1024);
+    lay->total = lay->tcs + ctx->tcs_bytes;
     return CG_OK;
 }
 
@@ -256,6 +270,7 @@ extern "C" int cg_net_forward(cg_net_t net, const float* params, const float* x,
     sc->ctx.arena = (char*)ws + sc->lay.arena;
     sc->ctx.ext_input = nullptr;
     sc->ctx.packed = (char*)ws + sc->lay.packed;
+    sc->ctx.tcs = (char*)ws + sc->lay.tcs;
     CG_TRY(net_bind(&sc->ctx));
     CG_TRY(net_pack(net, params, sc->ctx.packed, st));
     const int tout = net->out_tensor();

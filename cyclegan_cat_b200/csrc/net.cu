@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include "conv_special.h"
 #include "kernels.h"
 
 static inline void same_pad(int in, int k, int s, int* before) {
@@ -106,6 +107,7 @@ int net_plan(const cg_net_s* net, int N, int H, int W, bool bwd, CallCtx* ctx) {
     // and every 64-pixel K chunk of the weight gradient a Wk x Hk box
     ctx->tc.assign(nl, TcLayer());
     ctx->grad_halo.assign(nl + 1, 0);
+    ctx->tcs_bytes = 0;
     auto boxable = [](int w, int h, int px) { return (w % px == 0) || (px % w == 0 && h % (px / w) == 0); };
     for (size_t i = 0; i < nl; ++i) {
         const int kind = net->layers[i].tc;
@@ -121,7 +123,20 @@ int net_plan(const cg_net_s* net, int N, int H, int W, bool bwd, CallCtx* ctx) {
         } else if (kind == TC_CONVT_S2) {      // fwd classes on (hi,wi) = half the output grid; its dgrad tiles on (hi,wi)
             ok = boxable(wi, hi, 128) && boxable(wi, hi, 64);
         }
+        else if (kind == TC_STEM) {
+            ok = boxable(wo, ho, 128) && boxable(wo, ho, 64);
+        } else if (kind == TC_HEAD) {
+            ok = ((size_t)ho * wi) % 64 == 0 && (size_t)hi * wi < (1u << 30);
+        }
         ctx->tc[i].on = ok;
+        if (ok && (kind == TC_STEM || kind == TC_HEAD)) {
+            // scratch: the unfolded tensor (128 channels) [+ S for the head forward, smaller] then the fp32 dW staging
+            const size_t big = kind == TC_STEM ? (size_t)N * hi * wo * 128 * 2 : (size_t)N * ho * wi * 128 * 2;
+            const size_t tmp = kind == TC_STEM ? (size_t)d.k * 128 * d.cout * 4 : (size_t)d.k * d.cin * 128 * 4;
+            ctx->tc[i].sc_tmp = align_up(big, 1024);
+            const size_t need = ctx->tc[i].sc_tmp + align_up(tmp, 1024);
+            if (need > ctx->tcs_bytes) ctx->tcs_bytes = need;
+        }
     }
     ctx->grad_off.assign(nl + 1, 0);
     size_t goff = 0;
@@ -147,6 +162,15 @@ int net_pack(const cg_net_s* net, const float* params, void* packed, cudaStream_
     if (!packed) { cg_set_error("net_pack: no packed-weight buffer"); return CG_ERR_STATE; }
     for (const LayerInfo& L : net->layers) {
         if (!L.tc) continue;
+        if (L.tc == TC_STEM) {
+            CG_TRY(sp_pack_stem(params + L.w_off, (bf16*)((char*)packed + L.pk_f), L.d.k, L.d.cin, L.d.cout, st));
+            continue;
+        }
+        if (L.tc == TC_HEAD) {
+            CG_TRY(sp_pack_head(params + L.w_off, (bf16*)((char*)packed + L.pk_f), (bf16*)((char*)packed + L.pk_d), L.d.k,
+                                L.d.cin, L.d.cout, st));
+            continue;
+        }
         // the TF kernel of a Conv2DTranspose (kh,kw,Cout,Cin) IS the HWIO kernel of the conv F it back-propagates
         const int cin_f = L.d.op == CG_OP_CONV ? L.d.cin : L.d.cout, cout_f = L.d.op == CG_OP_CONV ? L.d.cout : L.d.cin;
         CG_TRY(tc_pack_weights(params + L.w_off, (bf16*)((char*)packed + L.pk_f), (bf16*)((char*)packed + L.pk_d),
@@ -307,6 +331,80 @@ int net_bind(CallCtx* c) {
             if (!c->bwd) continue;
             CG_TRY(make_class_launches(t.dgrad, dy, ho, wo, d.cout, c->N, wd, d.cin, k, pt, pl, hi, wi));
             CG_TRY(make_wgrad(t, x, hi, wi, d.cin, dy, ho, wo, d.cout, c->N, k, 2, pt, pl, 0));
+        } else if (L.tc == TC_STEM) {
+            if (!c->tcs) { cg_set_error("net_bind: no scratch for the unfolded stem input"); return CG_ERR_STATE; }
+            const void* U = c->tcs;                         // [N][hi][wo][128]: U[r][ow][kw*cin+ci] = x[r][ow+kw][ci]
+            t.fwd.assign(1, TcConvLaunch());
+            {
+                TcConvArgs& a = t.fwd[0].a;
+                memset(&a, 0, sizeof(a));
+                set_tiles(a, wo, ho);
+                a.n_taps = k; a.cchunks = 1; a.bn = d.cout; a.n_blocks_n = 1;
+                a.nb = c->N; a.out_H = ho; a.out_W = wo; a.Cout = d.cout; a.out_sy = a.out_sx = 1;
+                a.b_rows_per_tap = d.cout;
+                for (int kh = 0; kh < k; ++kh) { a.tb[kh] = (short)kh; a.dh[kh] = (short)kh; }
+                CG_TRY(tc_make_map_act(&t.fwd[0].mapA, U, 128, wo, hi, c->N, 0, a.Wb, a.Hb));
+                CG_TRY(tc_make_map_2d(&t.fwd[0].mapB, wf, 64, k * d.cout, a.bn));
+            }
+            if (!c->bwd) continue;
+            {
+                TcWgradArgs& a = t.wa;
+                memset(&a, 0, sizeof(a));
+                a.Wk = wo % 64 == 0 ? 64 : wo; a.Hk = 64 / a.Wk;
+                a.n_taps = k; a.transposed = 0; a.a_blocks = 1; a.bn = d.cout; a.b_blocks = 1;
+                a.chunks_w = wo / a.Wk; a.chunks_per_img = a.chunks_w * (ho / a.Hk);
+                a.Cin = 128; a.Cout = d.cout;
+                for (int kh = 0; kh < k; ++kh) a.dh[kh] = (short)kh;
+                CG_TRY(tc_make_map_act(&t.mapXw, U, 128, wo, hi, c->N, 0, a.Wk, a.Hk));
+                CG_TRY(tc_make_map_act(&t.mapDYw, dy, d.cout, wo, ho, c->N, 0, a.Wk, a.Hk));
+            }
+        } else if (L.tc == TC_HEAD) {
+            if (!c->tcs) { cg_set_error("net_bind: no scratch for the unfolded head tensors"); return CG_ERR_STATE; }
+            const void* S = c->tcs;                         // forward:  [N][ho][wi][32]
+            const void* T = c->tcs;                         // backward: [N][ho][wi][128], T[r][q][kw*cout+co] = dy[r][q-kw][co]
+            t.fwd.assign(1, TcConvLaunch());
+            {
+                TcConvArgs& a = t.fwd[0].a;
+                memset(&a, 0, sizeof(a));
+                a.Wb = 128; a.Hb = 1;
+                a.n_taps = k; a.cchunks = d.cin / 64; a.bn = 32; a.n_blocks_n = 1;
+                a.tiles_per_img = (ho * wi + 127) / 128; a.tiles_w = a.tiles_per_img;
+                a.nb = c->N;
+                a.out_P = wi; a.out_wvalid = wi; a.out_hvalid = ho; a.out_H = ho; a.out_W = wi; a.Cout = 32;
+                a.out_sy = a.out_sx = 1;
+                a.b_rows_per_tap = 32;
+                for (int kh = 0; kh < k; ++kh) { a.tb[kh] = (short)kh; a.dw[kh] = (short)(kh * wi); }
+                CG_TRY(tc_make_map_act(&t.fwd[0].mapA, x, d.cin, hi * wi, 1, c->N, 0, 128, 1));
+                CG_TRY(tc_make_map_2d(&t.fwd[0].mapB, wf, d.cin, k * 32, 32));
+                (void)S;
+            }
+            if (!c->bwd) continue;
+            t.dgrad.assign(1, TcConvLaunch());
+            {
+                TcConvArgs& a = t.dgrad[0].a;
+                memset(&a, 0, sizeof(a));
+                a.Wb = 128; a.Hb = 1;
+                a.n_taps = k; a.cchunks = 1; a.bn = d.cin; a.n_blocks_n = 1;
+                a.tiles_per_img = (hi * wi + 127) / 128; a.tiles_w = a.tiles_per_img;
+                a.nb = c->N;
+                a.out_P = wi; a.out_wvalid = wi; a.out_hvalid = hi; a.out_H = hi; a.out_W = wi; a.Cout = d.cin;
+                a.out_sy = a.out_sx = 1;
+                a.b_rows_per_tap = d.cin;
+                for (int kh = 0; kh < k; ++kh) { a.tb[kh] = (short)kh; a.dw[kh] = (short)(-kh * wi); }
+                CG_TRY(tc_make_map_act(&t.dgrad[0].mapA, T, 128, ho * wi, 1, c->N, 0, 128, 1));
+                CG_TRY(tc_make_map_2d(&t.dgrad[0].mapB, wd, 64, k * d.cin, a.bn));
+            }
+            {
+                TcWgradArgs& a = t.wa;
+                memset(&a, 0, sizeof(a));
+                a.Wk = 64; a.Hk = 1;
+                a.n_taps = k; a.transposed = 1; a.a_blocks = 1; a.bn = d.cin; a.b_blocks = 1;
+                a.chunks_per_img = ho * wi / 64; a.chunks_w = a.chunks_per_img;
+                a.Cin = d.cin; a.Cout = 128;
+                for (int kh = 0; kh < k; ++kh) a.dw[kh] = (short)(kh * wi);
+                CG_TRY(tc_make_map_act(&t.mapXw, x, d.cin, hi * wi, 1, c->N, 0, 64, 1));
+                CG_TRY(tc_make_map_act(&t.mapDYw, T, 128, ho * wi, 1, c->N, 0, 64, 1));
+            }
         } else if (L.tc == TC_CONVT_S2) {
             // F: (ho x wo x cout) -> (hi x wi x cin), stride 2, 'same' padding computed on the big grid
             int pt, pl;
@@ -339,15 +437,28 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
         switch (d.op) {
             case CG_OP_CONV: {
                 ConvGeom g = conv_geom(d, N, h, w, oh, ow);
-                if (c->tc[i].on) {
+                const float* bias = L.b_off >= 0 ? params + L.b_off : nullptr;
+                const double fl = 2.0 * N * oh * ow * (double)d.cout * d.k * d.k * d.cin;
+                if (c->tc[i].on && L.tc == TC_STEM) {
+                    const TcConvLaunch& tl = c->tc[i].fwd[0];
+                    CG_TRY(sp_unfold_w((const bf16*)x, (bf16*)c->tcs, N, h, w, d.cin, ow, d.k, +1, st));
+                    TcConvArgs a = tl.a;
+                    a.nb = N;
+                    CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, (bf16*)y, bias, a, fl, st));
+                } else if (c->tc[i].on && L.tc == TC_HEAD) {
+                    const TcConvLaunch& tl = c->tc[i].fwd[0];
+                    TcConvArgs a = tl.a;
+                    a.nb = N;
+                    CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, (bf16*)c->tcs, nullptr, a, fl, st));
+                    CG_TRY(sp_diag_sum((const bf16*)c->tcs, bias, (bf16*)y, N, oh, ow, w, d.k, d.cout, st));
+                } else if (c->tc[i].on) {
                     for (const TcConvLaunch& tl : c->tc[i].fwd) {
                         TcConvArgs a = tl.a;
                         a.nb = N;
-                        CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, (bf16*)y, L.b_off >= 0 ? params + L.b_off : nullptr, a,
-                                              tl.flop_share * 2.0 * N * oh * ow * (double)d.cout * d.k * d.k * d.cin, st));
+                        CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, (bf16*)y, bias, a, tl.flop_share * fl, st));
                     }
                 } else {
-                    CG_TRY(k_conv_fwd<T>(x, params + L.w_off, L.b_off >= 0 ? params + L.b_off : nullptr, y, g, 0, st));
+                    CG_TRY(k_conv_fwd<T>(x, params + L.w_off, bias, y, g, 0, st));
                 }
                 break;
             }
@@ -436,6 +547,40 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
         switch (d.op) {
             case CG_OP_CONV: {
                 ConvGeom g = conv_geom(d, nb, h, w, oh, ow);
+                if (c->tc[i].on && !acc && (L.tc == TC_STEM || L.tc == TC_HEAD)) {
+                    const double fl = 2.0 * nb * oh * ow * (double)d.cout * d.k * d.k * d.cin;
+                    float* tmp = (float*)(c->tcs + c->tc[i].sc_tmp);
+                    bf16* big = (bf16*)c->tcs;
+                    if (L.tc == TC_STEM) {
+                        if (grads) {
+                            CG_TRY(sp_unfold_w((const bf16*)A(tin), big, nb, h, w, d.cin, ow, d.k, +1, st));
+                            CG_CUDA(cudaMemsetAsync(tmp, 0, (size_t)d.k * 128 * d.cout * sizeof(float), st));
+                            TcWgradArgs a = c->tc[i].wa;
+                            a.n0 = 0; a.nb = nb;
+                            CG_TRY(tc_wgrad_launch(&c->tc[i].mapXw, &c->tc[i].mapDYw, tmp, a, fl, st));
+                            CG_TRY(sp_unpack_dw(tmp, grads + L.w_off, d.k, d.cin, d.cout, 0, st));
+                            if (L.b_off >= 0) CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
+                        }
+                        if (want_dx) CG_TRY(k_conv_dgrad<T>(dy, params + L.w_off, nullptr, dx, g, 0, st));
+                    } else {
+                        CG_TRY(sp_unfold_w((const bf16*)dy, big, nb, oh, ow, d.cout, w, d.k, -1, st));
+                        if (grads) {
+                            CG_CUDA(cudaMemsetAsync(tmp, 0, (size_t)d.k * d.cin * 128 * sizeof(float), st));
+                            TcWgradArgs a = c->tc[i].wa;
+                            a.n0 = n0; a.nb = nb;
+                            CG_TRY(tc_wgrad_launch(&c->tc[i].mapXw, &c->tc[i].mapDYw, tmp, a, fl, st));
+                            CG_TRY(sp_unpack_dw(tmp, grads + L.w_off, d.k, d.cin, d.cout, 1, st));
+                            if (L.b_off >= 0) CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
+                        }
+                        if (want_dx) {
+                            const TcConvLaunch& tl = c->tc[i].dgrad[0];
+                            TcConvArgs a = tl.a;
+                            a.nb = nb;
+                            CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, (bf16*)dx, nullptr, a, fl, st));
+                        }
+                    }
+                    break;
+                }
                 if (c->tc[i].on && !acc) {
                     // stride-1 layers: dy lives in a zero-bordered buffer (halo 2) written by the IN backward
                     const int hl = c->grad_halo[tout];

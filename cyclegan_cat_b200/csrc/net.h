@@ -17,8 +17,9 @@ struct TcLayer {
     CUtensorMap mapXw, mapDYw;
     TcWgradArgs wa;
     int wg_x_is_dy = 0;                 // Conv2DTranspose: the "X" operand of the weight gradient is dY
+    size_t sc_tmp = 0;                  // TC_STEM / TC_HEAD: offset of the fp32 weight-gradient staging buffer in the scratch
 };
-enum { TC_NONE = 0, TC_S1_VALID = 1, TC_CONV_S2 = 2, TC_CONVT_S2 = 3 };
+enum { TC_NONE = 0, TC_S1_VALID = 1, TC_CONV_S2 = 2, TC_CONVT_S2 = 3, TC_STEM = 4, TC_HEAD = 5 };
 
 struct LayerInfo {
     cg_layer_desc d;
@@ -62,6 +63,8 @@ struct CallCtx {
     void* ext_input = nullptr;          // if set, tensor 0 lives here instead of at act_off[0]
     bool forwarded = false;
     char* packed = nullptr;             // packed bf16 weights of this net (net_pack)
+    char* tcs = nullptr;                // scratch for the unfolded tensors of the 7x7 stem / head (conv_special.cu)
+    size_t tcs_bytes = 0;
     std::vector<TcLayer> tc;            // per layer
     std::vector<int> grad_halo;         // per tensor: zero border of the gradient buffer (tensor-core layers)
 

@@ -70,7 +70,7 @@ struct cg_trainer_s {
     CallCtx F1, F2, C1, C2, DA, DB;
     // misc buffers (activation dtype unless noted)
     size_t o_seedF1 = 0, o_seedF2 = 0, o_seedC1 = 0, o_seedC2 = 0, o_dxC1 = 0, o_dxC2 = 0, o_seedDA = 0, o_seedDB = 0,
-           o_advDA = 0, o_advDB = 0, o_sums = 0, o_arena = 0, o_packed[4] = {0, 0, 0, 0}, total = 0;
+           o_advDA = 0, o_advDB = 0, o_sums = 0, o_arena = 0, o_packed[4] = {0, 0, 0, 0}, o_tcs = 0, total = 0;
     int d_h = 0, d_w = 0, d_c = 0;
     // data parallel
     nccl_comm comm = nullptr; int world = 1, rank = 0;
@@ -120,6 +120,9 @@ static int trainer_layout(cg_trainer_t tr, int B, int H, int W, bool assign) {
     tr->o_sums = take(S_COUNT * sizeof(float));
     off = align_up(off, 1024);
     for (int i = 0; i < 4; ++i) tr->o_packed[i] = take(align_up(tr->net[i]->packed_bytes, 1024));
+    size_t tcs = 0;
+    for (CallCtx* c : {&tr->F1, &tr->F2, &tr->C1, &tr->C2, &tr->DA, &tr->DB}) if (c->tcs_bytes > tcs) tcs = c->tcs_bytes;
+    tr->o_tcs = take(align_up(tcs, 1024));
     tr->total = off;
     if (assign) {
         if (off > tr->ws_bytes) { cg_set_error("trainer workspace %zu < required %zu", tr->ws_bytes, off); return CG_ERR_WORKSPACE; }
@@ -132,6 +135,7 @@ static int trainer_layout(cg_trainer_t tr, int B, int H, int W, bool assign) {
         const int owner[6] = {0, 1, 1, 0, 2, 3};
         for (int i = 0; i < 6; ++i) {
             cs[i]->packed = tr->ws + tr->o_packed[owner[i]];
+            cs[i]->tcs = tr->ws + tr->o_tcs;
             CG_TRY(net_bind(cs[i]));
         }
         tr->B = B; tr->H = H; tr->W = W; tr->planned = true;

@@ -47,6 +47,20 @@ def _updown_net(cin, cout, k):
     return g
 
 
+def _stem_head_net(f):
+    """RPad3 -> Conv7x7(3->f) -> IN -> ReLU -> RPad3 -> Conv7x7(f->3) -> tanh: the two image-side layers of
+    resnet_generator (resnet.py:38-46, 68, 82)."""
+    g = ir.Graph(channels=[3])
+    x = g.reflect_pad(g.input, 3)
+    x = g.conv(x, f, 7, stride=1, padding='valid')
+    x = g.instance_norm(x, affine=False)
+    x = g.act(x, ir.ACT_RELU)
+    x = g.reflect_pad(x, 3)
+    x = g.conv(x, 3, 7, stride=1, padding='valid')
+    x = g.act(x, ir.ACT_TANH)
+    return g
+
+
 def _make(graph, tc, seed=0):
     os.environ["CG_DISABLE_TC"] = "0" if tc else "1"
     try:
@@ -97,6 +111,27 @@ def test_tc_strided_and_transposed_convs_match_cuda_core(cin, cout, k, h, w, n):
     for i, (u, v) in enumerate(zip(ga, gb)):
         e = np.linalg.norm(u - v) / max(np.linalg.norm(v), 0.02 * scale)
         assert e <= 1e-2, (i, u.shape, e)
+
+
+@pytest.mark.parametrize("f,h,w,n", [(64, 64, 64, 2), (64, 32, 128, 3), (128, 256, 256, 1)])
+def test_tc_stem_and_head_match_cuda_core(f, h, w, n):
+    g = _stem_head_net(f)
+    a, b = _make(g, True), _make(g, False)
+    rng = np.random.RandomState(4)
+    ws = [_bf16_round(v + (rng.normal(0, 0.05, v.shape) if v.ndim == 1 else 0)) for v in a.get_weights()]
+    a.set_weights(ws)
+    b.set_weights(ws)
+    x = _bf16_round(rng.uniform(-1, 1, (n, h, w, 3)))
+    dy = _bf16_round(rng.normal(0, 1, (n, h, w, 3)))
+    ya, dxa, ga = _net_grads(a, x, dy)
+    yb, dxb, gb = _net_grads(b, x, dy)
+    # the head sums 7 bf16-rounded partial rows (S) instead of one fp32 accumulator: 2-3 extra roundings of 2^-9
+    assert C.rel_l2(ya, yb) <= 8e-3, C.rel_l2(ya, yb)
+    assert C.rel_l2(dxa, dxb) <= 2e-2, C.rel_l2(dxa, dxb)
+    scale = max(np.linalg.norm(v) for v in gb)
+    for i, (u, v) in enumerate(zip(ga, gb)):
+        e = np.linalg.norm(u - v) / max(np.linalg.norm(v), 0.02 * scale)
+        assert e <= 2e-2, (i, u.shape, e)
 
 
 def test_tc_single_conv_against_fp64():
