@@ -283,19 +283,17 @@ def test_ragged_last_batch_replans():
     assert abs(float(got["gAB_loss"]) - ref["gAB_loss"]) <= 2e-4 * abs(ref["gAB_loss"])
 
 
-def test_linearity_property_of_backward_bf16():
-    """Size-independent property at a larger size: backward is linear in dy (scale 2 -> grads x2 exactly in
-    structure; checked to bf16 tolerance) for the ResNet generator at 64x64, f=16."""
-    m, _ = _pair(C.FIX_RESNET, "bf16")
+def test_linearity_property_of_backward():
+    """Size-independent property at a larger size: backward is linear in dy (dy -> 2 dy doubles every gradient) for the
+    ResNet generator at 64x64, f=16.  fp32 check mode: two runs of the same forward differ only in fp32 atomic
+    summation order, so the doubling holds to ~1e-6 unless a ReLU mask flips between the runs (then ~1e-2)."""
+    m, _ = _pair(C.FIX_RESNET, "fp32")
     rng = np.random.RandomState(1)
     x = rng.uniform(-1, 1, (1, 64, 64, 3)).astype(np.float32)
     dy = rng.normal(0, 1, (1, 64, 64, 3)).astype(np.float32)
-    _, _, g1 = _net_grads(m, x, dy)
-    _, _, g2 = _net_grads(m, x, 2 * dy)
-    big = [i for i, g in enumerate(g1) if g.ndim == 4]
-    # not bit-equal: the two forwards differ in their fp32 atomic summation order (instance-norm statistics), which
-    # re-rounds some stored bf16 activations and flips a few ReLU masks; the effect accumulates towards the first
-    # layers (same mechanism as _check_grads), so the bound is tight near the output and loose at the stem
-    for rank, i in enumerate(big):
-        lim = 6e-2 if rank >= len(big) // 2 else 0.4
-        assert C.rel_l2(g2[i], 2 * g1[i]) <= lim, (i, C.rel_l2(g2[i], 2 * g1[i]))
+    _, dx1, g1 = _net_grads(m, x, dy)
+    _, dx2, g2 = _net_grads(m, x, 2 * dy)
+    assert C.rel_l2(dx2, 2 * dx1) <= 2e-2
+    for i, g in enumerate(g1):
+        if g.ndim == 4:
+            assert C.rel_l2(g2[i], 2 * g1[i]) <= 2e-2, (i, C.rel_l2(g2[i], 2 * g1[i]))
