@@ -141,6 +141,15 @@ extern "C" int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode
             net->has_buffer[i + 1] = 0;
         }
     }
+    // A conv / transposed-conv bias that feeds ONLY an instance norm has an identically zero gradient: the norm subtracts
+    // the per-(sample, channel) mean, so sum_pixels dL/dy == 0 ('zero-by-construction gradients').  The
+    // reference computes rounding noise there; this library writes the exact value 0 and skips the reduction.
+    for (int i = 0; i + 1 < n_layers; ++i) {
+        LayerInfo& L = net->layers[i];
+        if ((L.d.op == CG_OP_CONV || L.d.op == CG_OP_CONVT) && L.d.has_bias && net->n_consumers[i + 1] == 1 &&
+            net->layers[i + 1].d.op == CG_OP_INORM && net->layers[i + 1].d.in0 == i + 1)
+            L.bias_grad_zero = true;
+    }
     // tensor-core layers (bf16 mode): 3x3 stride-1 'valid' convs with Cin % 128 == 0 and Cout % 64 == 0 whose output
     // feeds exactly one instance norm (its backward writes the zero-bordered dY the TMA loads expect)
     size_t pk = 0;

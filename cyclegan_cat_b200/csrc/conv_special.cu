@@ -14,32 +14,40 @@ static inline int blocks_for(size_t n) {
     return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
 }
 
-// dst[n][h][q][kw*Cs + c] = src[n][h][q + sign*kw][c]  (0 outside [0,Ws)), channels >= k*Cs are zero; dst has 128 channels
+// dst[n][h][q][kw*Cs + c] = src[n][h][q + sign*kw][c]  (0 outside [0,Ws)), channels >= k*Cs are zero; dst has 128 channels.
+// One thread = one destination pixel: it gathers the k*Cs (<= 32) live values once and writes 16 x 16-byte vectors.
 __global__ void unfold_w_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int N, int H, int Ws, int Cs, int Wd,
                                 int k, int sign) {
-    const size_t total = (size_t)N * H * Wd * 16;          // 16 vectors of 8 channels
+    const size_t total = (size_t)N * H * Wd;
+    const int live = k * Cs;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int v = (int)(i % 16);
-        size_t r = i / 16;
-        const int q = (int)(r % Wd); r /= Wd;
-        const int h = (int)(r % H), n = (int)(r / H);
-        Pack<bf16, 8> pk;
+        const int q = (int)(i % Wd);
+        const size_t row = i / Wd;                          // n*H + h
+        const bf16* srow = src + row * Ws * Cs;
+        uint4* d = reinterpret_cast<uint4*>(dst + i * 128);
+        const bf16 zero = __float2bfloat16(0.f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int ch = v * 8 + j;
-            float val = 0.f;
-            if (ch < k * Cs) {
-                const int kw = ch / Cs, c = ch - kw * Cs;
-                const int ws = q + sign * kw;
-                if (ws >= 0 && ws < Ws) val = __bfloat162float(src[(((size_t)n * H + h) * Ws + ws) * Cs + c]);
+        for (int v = 0; v < 4; ++v) {
+            Pack<bf16, 8> pk;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int ch = v * 8 + j;
+                bf16 val = zero;
+                if (ch < live) {
+                    const int kw = ch / Cs, c = ch - kw * Cs;
+                    const int ws = q + sign * kw;
+                    if (ws >= 0 && ws < Ws) val = srow[(size_t)ws * Cs + c];
+                }
+                pk.v[j] = val;
             }
-            pk.v[j] = __float2bfloat16(val);
+            d[v] = *reinterpret_cast<uint4*>(&pk);
         }
-        *reinterpret_cast<Pack<bf16, 8>*>(dst + i * 8) = pk;
+#pragma unroll
+        for (int v = 4; v < 16; ++v) d[v] = make_uint4(0u, 0u, 0u, 0u);
     }
 }
 int sp_unfold_w(const bf16* src, bf16* dst, int N, int H, int Ws, int Cs, int Wd, int k, int sign, cudaStream_t st) {
-    unfold_w_kernel<<<blocks_for((size_t)N * H * Wd * 16), 256, 0, st>>>(src, dst, N, H, Ws, Cs, Wd, k, sign);
+    unfold_w_kernel<<<blocks_for((size_t)N * H * Wd), 256, 0, st>>>(src, dst, N, H, Ws, Cs, Wd, k, sign);
     CG_LAUNCH_CHECK();
     return CG_OK;
 }

@@ -11,6 +11,7 @@
 //                    the SAME activation tiles, now used as MN-major operands (K = pixels), split-K over the
 //                    pixel range, fp32 vector reductions (red.global.add.v4.f32) into the float32 gradient.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "conv_tc.h"
 #include "prof.h"
@@ -137,6 +138,24 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// column sums of a 32 x 32 tile held one row per lane (v[j] = column j of this lane's row): recursive halving with
+// shuffles -- after the 5 steps lane L holds the sum of column L.  31 shuffles.
+__device__ __forceinline__ float warp_colsum32(float (&s)[32], int lane) {
+#pragma unroll
+    for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (j < n / 2) {
+                const float send = up ? s[j] : s[j + n / 2];
+                const float keep = up ? s[j + n / 2] : s[j];
+                s[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+        }
+    }
+    return s[0];
+}
+
 static constexpr int TC_THREADS = 192;        // 6 warps: TMA, MMA, 4 x epilogue
 static constexpr int A_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
 static constexpr int TMEM_COLS = 512;
@@ -159,6 +178,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     auto tempty = [&](int i) { return bar0 + 8u * (2 * S + 2 + i); };
     const uint32_t tmem_slot = bar0 + 8u * (2 * S + 4);
     volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    float* stat_sm = reinterpret_cast<float*>(smem_raw + (bar0 + 256u - smem_u32(smem_raw)));   // epilogue: per-warp column sums
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA);
@@ -240,6 +260,207 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int c0 = 0; c0 < a.bn; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
+                if (bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(bias + nblk * a.bn + c0 + j));
+                }
+                if (valid) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                    uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) d4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                }
+                if (a.stats) {      // fused instance-norm statistics: per-channel sum and sum of squares of this tile
+                    float s1[32], s2[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { const float x = valid ? __uint_as_float(v[j]) : 0.f; s1[j] = x; s2[j] = x * x; }
+                    const float cs = warp_colsum32(s1, lane), cq = warp_colsum32(s2, lane);
+                    stat_sm[(q * 2 + 0) * 32 + lane] = cs;
+                    stat_sm[(q * 2 + 1) * 32 + lane] = cq;
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (q == 0) {
+                        float* sp = a.stats + ((size_t)img * a.Cout + (size_t)nblk * a.bn + c0 + lane) * 2;
+                        atomicAdd(sp, stat_sm[0 * 32 + lane] + stat_sm[2 * 32 + lane] + stat_sm[4 * 32 + lane] + stat_sm[6 * 32 + lane]);
+                        atomicAdd(sp + 1, stat_sm[1 * 32 + lane] + stat_sm[3 * 32 + lane] + stat_sm[5 * 32 + lane] + stat_sm[7 * 32 + lane]);
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty(acc));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2): a CTA pair (one TPC) computes a 256-pixel x BN tile.  Each CTA loads ITS 128 pixel rows
+// of A and HALF of the B rows; the leader's single thread issues tcgen05.mma.cta_group::2 (M = 256), which reads A/B
+// halves from both CTAs' shared memory and writes 128 accumulator rows into each CTA's TMEM.  Per SM this halves the
+// B bytes written by TMA and read by the MMA -- the 1-CTA kernel above is shared-memory-bandwidth bound
+// (48 KB written + 48 KB read per 512 MMA cycles = 187 B/clk against ~128 B/clk).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                                int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once) on the barrier at the same offset in BOTH CTAs of the pair when the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {      // arrive on CTA 0's copy of `bar`
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(bar) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                bf16* __restrict__ out, const float* __restrict__ bias, const TcConvArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const uint32_t b_half = (uint32_t)(a.bn / 2) * 128u;
+    const uint32_t stage_bytes = A_TILE_BYTES + b_half;
+    const int S = a.stages;
+    const uint32_t bar0 = smem0 + S * stage_bytes;
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (S + s); };
+    auto tfull = [&](int i) { return bar0 + 8u * (2 * S + i); };
+    auto tempty = [&](int i) { return bar0 + 8u * (2 * S + 2 + i); };
+    const uint32_t tmem_slot = bar0 + 8u * (2 * S + 4);
+    volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+        for (int s = 0; s < S; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 8); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int m_pairs = a.nb * a.tiles_per_img / 2;              // host guarantees an even number of M tiles
+    const int total_pairs = m_pairs * a.n_blocks_n;
+    const int n_clusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
+    const int ksteps = a.n_taps * a.cchunks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int p = cluster_id; p < total_pairs; p += n_clusters) {
+                const int nblk = p % a.n_blocks_n, mt = 2 * (p / a.n_blocks_n) + (int)rank;
+                const int img = a.n0 + mt / a.tiles_per_img, ti = mt % a.tiles_per_img;
+                const int w0 = (ti % a.tiles_w) * a.Wb, h0 = (ti / a.tiles_w) * a.Hb;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const int tap = ks / a.cchunks, cc = ks - tap * a.cchunks;
+                    mbar_wait(empty(s), ph ^ 1u);
+                    if (leader) mbar_expect_tx(full(s), 2u * stage_bytes);
+                    const uint32_t sa = smem0 + s * stage_bytes;
+                    tma_load_5d_2sm(sa, &mapA, full(s), cc * 64 + a.dc[tap], w0 + a.dw[tap], a.dp[tap], h0 + a.dh[tap], img);
+                    tma_load_2d_2sm(sa + A_TILE_BYTES, &mapB, full(s), cc * 64,
+                                    a.tb[tap] * a.b_rows_per_tap + nblk * a.bn + (int)rank * (a.bn / 2));
+                    if (++s == S) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            int s = 0; uint32_t ph = 0;
+            int it = 0;
+            for (int p = cluster_id; p < total_pairs; p += n_clusters, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(tempty(acc), acc_ph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(full(s), ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem0 + s * stage_bytes;
+                    const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+                    const uint64_t bdesc = make_smem_desc(sa + A_TILE_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_2sm(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), a.idesc,
+                                      (uint32_t)((ks | k) != 0));
+                    umma_commit_2sm(empty(s));
+                    if (++s == S) { s = 0; ph ^= 1u; }
+                }
+                umma_commit_2sm(tfull(acc));
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        int it = 0;
+        for (int p = cluster_id; p < total_pairs; p += n_clusters, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+            const int nblk = p % a.n_blocks_n, mt = 2 * (p / a.n_blocks_n) + (int)rank;
+            const int img = mt / a.tiles_per_img, ti = mt % a.tiles_per_img;
+            const int w0 = (ti % a.tiles_w) * a.Wb, h0 = (ti / a.tiles_w) * a.Hb;
+            const int lin = h0 * a.out_P + w0 + q * 32 + lane;
+            const int oh = lin / a.out_P, ow = lin - oh * a.out_P;
+            const bool valid = ow < a.out_wvalid && oh < a.out_hvalid;
+            bf16* dst = out + (((size_t)img * a.out_H + (oh * a.out_sy + a.out_oy)) * a.out_W + (ow * a.out_sx + a.out_ox)) * a.Cout +
+                        (size_t)nblk * a.bn;
+            mbar_wait(tfull(acc), acc_ph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < a.bn; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)c0, v);
                 if (valid) {
                     uint32_t pk[16];
 #pragma unroll
@@ -255,14 +476,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty(acc));
+            if (lane == 0) mbar_arrive_leader(tempty(acc));
         }
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        tmem_dealloc_2sm(tmem_base, TMEM_COLS);
     }
 }
 
@@ -494,15 +715,39 @@ static int num_sms() {
 
 int tc_conv_stages(int bn) {
     int stage = A_TILE_BYTES + bn * 128;
-    int s = (227 * 1024 - 2048) / stage;
+    int s = (227 * 1024 - 3072) / stage;
     return s > 6 ? 6 : s;
 }
 
-int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, bf16* out, const float* bias, TcConvArgs a,
-                   double flops, cudaStream_t st) {
+static int g_use_2cta = -1;
+int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, const CUtensorMap* mapB2, bf16* out, const float* bias,
+                   TcConvArgs a, double flops, cudaStream_t st) {
+    // measured on B200 (profiles/r01_tc_kernels.md): the pair kernel lowers L2 traffic (lts 49 % -> 37 %) but not the
+    // duration (119 us vs 117 us at the C3 trunk shape), so the 1-CTA kernel stays the default
+    if (g_use_2cta < 0) { const char* e = getenv("CG_ENABLE_2CTA"); g_use_2cta = (e && e[0] == '1') ? 1 : 0; }
+    if (g_use_2cta && mapB2 && !a.stats && a.bn >= 32 && ((a.nb * a.tiles_per_img) % 2 == 0)) {
+        const int stage = A_TILE_BYTES + (a.bn / 2) * 128;
+        int s2 = (227 * 1024 - 2048) / stage;
+        a.stages = s2 > 8 ? 8 : s2;
+        a.idesc = make_idesc(256, a.bn, 0, 0);
+        const size_t smem = (size_t)a.stages * stage + 1024 + 256;
+        static bool attr2 = false;
+        if (!attr2) {
+            CG_CUDA(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr2 = true;
+        }
+        const int total_pairs = (a.nb * a.tiles_per_img / 2) * a.n_blocks_n;
+        int clusters = num_sms() / 2;
+        if (clusters > total_pairs) clusters = total_pairs;
+        int pi = prof_begin(st);
+        conv_tc2_kernel<<<2 * clusters, TC_THREADS, smem, st>>>(*mapA, *mapB2, out, bias, a);
+        prof_end(pi, st, flops);
+        CG_LAUNCH_CHECK();
+        return CG_OK;
+    }
     a.stages = tc_conv_stages(a.bn);
     a.idesc = make_idesc(128, a.bn, 0, 0);
-    const size_t smem = (size_t)a.stages * (A_TILE_BYTES + a.bn * 128) + 1024 + 256;
+    const size_t smem = (size_t)a.stages * (A_TILE_BYTES + a.bn * 128) + 1024 + 256 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

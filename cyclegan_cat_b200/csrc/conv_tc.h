@@ -13,6 +13,7 @@ struct TcConvArgs {
     int b_rows_per_tap;                         // rows of the packed weight matrix per tap
     int stages;
     uint32_t idesc;
+    float* stats;                               // nullable: [N][Cout][2] running (sum, sum of squares) of the outputs
     // per K-loop tap: TMA coordinate offsets into the 5-D activation view (c, w, p, h, n) and the weight row block
     short dc[49], dw[49], dp[49], dh[49], tb[49];
 };
@@ -33,7 +34,8 @@ struct TcWgradArgs {
 int tc_make_map_act(CUtensorMap* map, const void* base, int C, int W, int H, int N, int parity, int box_w, int box_h);
 int tc_make_map_2d(CUtensorMap* map, const void* base, int cols, int rows, int box_rows);
 int tc_pack_weights(const float* w, bf16* wf, bf16* wd, int taps, int Cin, int Cout, cudaStream_t st);
-int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, bf16* out, const float* bias, TcConvArgs a,
-                   double flops, cudaStream_t st);
+// mapB2 (nullable): the same weight matrix with a box of bn/2 rows, for the 2-CTA kernel
+int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, const CUtensorMap* mapB2, bf16* out, const float* bias,
+                   TcConvArgs a, double flops, cudaStream_t st);
 int tc_wgrad_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* dw, TcWgradArgs a, double flops,
                     cudaStream_t st);

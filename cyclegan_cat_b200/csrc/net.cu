@@ -215,6 +215,7 @@ static int make_conv_launch(TcConvLaunch& L, const void* in, int hi, int wi, int
         }
     CG_TRY(tc_make_map_act(&L.mapA, in, cin_k, wi, hi, N, s == 2, a.Wb, a.Hb));
     CG_TRY(tc_make_map_2d(&L.mapB, wmat, cin_k, k * k * n_out, a.bn));
+    CG_TRY(tc_make_map_2d(&L.mapB2, wmat, cin_k, k * k * n_out, (a.bn) / 2 >= 8 ? (a.bn) / 2 : 8));
     return CG_OK;
 }
 
@@ -249,6 +250,7 @@ static int make_class_launches(std::vector<TcConvLaunch>& out, const void* dy, i
         total_taps += a.n_taps;
         CG_TRY(tc_make_map_act(&L.mapA, dy, cout_f, wo, ho, N, 0, a.Wb, a.Hb));
         CG_TRY(tc_make_map_2d(&L.mapB, wd, cout_f, k * k * cin_f, a.bn));
+        CG_TRY(tc_make_map_2d(&L.mapB2, wd, cout_f, k * k * cin_f, (a.bn) / 2 >= 8 ? (a.bn) / 2 : 8));
     }
     for (auto& L : out) L.flop_share = (double)L.a.n_taps / (double)(total_taps ? total_taps : 1);
     return CG_OK;
@@ -321,6 +323,7 @@ int net_bind(CallCtx* c) {
                 }
             CG_TRY(tc_make_map_act(&t.dgrad[0].mapA, dy, d.cout, HP * P, 1, c->N, 0, 128, 1));
             CG_TRY(tc_make_map_2d(&t.dgrad[0].mapB, wd, d.cout, k * k * d.cin, a.bn));
+            CG_TRY(tc_make_map_2d(&t.dgrad[0].mapB2, wd, d.cout, k * k * d.cin, (a.bn) / 2 >= 8 ? (a.bn) / 2 : 8));
             CG_TRY(make_wgrad(t, x, hi, wi, d.cin, dy, ho, wo, d.cout, c->N, k, 1, 0, 0, hl));
         } else if (L.tc == TC_CONV_S2) {
             int pt, pl;
@@ -345,6 +348,7 @@ int net_bind(CallCtx* c) {
                 for (int kh = 0; kh < k; ++kh) { a.tb[kh] = (short)kh; a.dh[kh] = (short)kh; }
                 CG_TRY(tc_make_map_act(&t.fwd[0].mapA, U, 128, wo, hi, c->N, 0, a.Wb, a.Hb));
                 CG_TRY(tc_make_map_2d(&t.fwd[0].mapB, wf, 64, k * d.cout, a.bn));
+                CG_TRY(tc_make_map_2d(&t.fwd[0].mapB2, wf, 64, k * d.cout, (a.bn) / 2 >= 8 ? (a.bn) / 2 : 8));
             }
             if (!c->bwd) continue;
             {
@@ -376,6 +380,7 @@ int net_bind(CallCtx* c) {
                 for (int kh = 0; kh < k; ++kh) { a.tb[kh] = (short)kh; a.dw[kh] = (short)(kh * wi); }
                 CG_TRY(tc_make_map_act(&t.fwd[0].mapA, x, d.cin, hi * wi, 1, c->N, 0, 128, 1));
                 CG_TRY(tc_make_map_2d(&t.fwd[0].mapB, wf, d.cin, k * 32, 32));
+                CG_TRY(tc_make_map_2d(&t.fwd[0].mapB2, wf, d.cin, k * 32, (32) / 2 >= 8 ? (32) / 2 : 8));
                 (void)S;
             }
             if (!c->bwd) continue;
@@ -393,6 +398,7 @@ int net_bind(CallCtx* c) {
                 for (int kh = 0; kh < k; ++kh) { a.tb[kh] = (short)kh; a.dw[kh] = (short)(-kh * wi); }
                 CG_TRY(tc_make_map_act(&t.dgrad[0].mapA, T, 128, ho * wi, 1, c->N, 0, 128, 1));
                 CG_TRY(tc_make_map_2d(&t.dgrad[0].mapB, wd, 64, k * d.cin, a.bn));
+                CG_TRY(tc_make_map_2d(&t.dgrad[0].mapB2, wd, 64, k * d.cin, (a.bn) / 2 >= 8 ? (a.bn) / 2 : 8));
             }
             {
                 TcWgradArgs& a = t.wa;
@@ -426,12 +432,20 @@ template <typename T>
 static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
     const cg_net_s* net = c->net;
     const int N = c->N;
+    std::vector<char> stats_done(net->layers.size() + 1, 0);
     for (size_t i = 0; i < net->layers.size(); ++i) {
         const LayerInfo& L = net->layers[i];
         if (L.skipped) continue;
         const cg_layer_desc& d = L.d;
         const int tin = d.in0, tout = L.out_t;
         const T* x = (const T*)c->act(tin);
+        // a tensor-core conv that feeds only an instance norm accumulates that norm's statistics in its epilogue
+        float* fused_stats = nullptr;
+        if (c->tc[i].on && L.bias_grad_zero && L.tc != TC_HEAD && i + 1 < net->layers.size()) {
+            fused_stats = (float*)(c->base + c->stat_off[i + 1]);
+            CG_CUDA(cudaMemsetAsync(fused_stats, 0, sizeof(float) * 2 * (size_t)N * d.cout, st));
+            stats_done[i + 1] = 1;
+        }
         T* y = (T*)c->act(tout);
         const int h = c->th[tin], w = c->tw[tin], oh = c->th[tout], ow = c->tw[tout];
         switch (d.op) {
@@ -444,18 +458,20 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
                     CG_TRY(sp_unfold_w((const bf16*)x, (bf16*)c->tcs, N, h, w, d.cin, ow, d.k, +1, st));
                     TcConvArgs a = tl.a;
                     a.nb = N;
-                    CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, (bf16*)y, bias, a, fl, st));
+                    a.stats = fused_stats;
+                    CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, (bf16*)y, bias, a, fl, st));
                 } else if (c->tc[i].on && L.tc == TC_HEAD) {
                     const TcConvLaunch& tl = c->tc[i].fwd[0];
                     TcConvArgs a = tl.a;
                     a.nb = N;
-                    CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, (bf16*)c->tcs, nullptr, a, fl, st));
+                    CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, (bf16*)c->tcs, nullptr, a, fl, st));
                     CG_TRY(sp_diag_sum((const bf16*)c->tcs, bias, (bf16*)y, N, oh, ow, w, d.k, d.cout, st));
                 } else if (c->tc[i].on) {
                     for (const TcConvLaunch& tl : c->tc[i].fwd) {
                         TcConvArgs a = tl.a;
                         a.nb = N;
-                        CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, (bf16*)y, bias, a, tl.flop_share * fl, st));
+                        a.stats = fused_stats;
+                        CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, (bf16*)y, bias, a, tl.flop_share * fl, st));
                     }
                 } else {
                     CG_TRY(k_conv_fwd<T>(x, params + L.w_off, bias, y, g, 0, st));
@@ -468,7 +484,8 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
                     for (const TcConvLaunch& tl : c->tc[i].fwd) {
                         TcConvArgs a = tl.a;
                         a.nb = N;
-                        CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, (bf16*)y, L.b_off >= 0 ? params + L.b_off : nullptr, a,
+                        a.stats = fused_stats;
+                        CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, (bf16*)y, L.b_off >= 0 ? params + L.b_off : nullptr, a,
                                               tl.flop_share * 2.0 * N * h * w * (double)d.cout * d.k * d.k * d.cin, st));
                     }
                 } else {
@@ -478,7 +495,8 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
             }
             case CG_OP_INORM: {
                 float* stats = (float*)(c->base + c->stat_off[i]);
-                CG_TRY(k_in_stats<T>(x, stats, N, h * w, d.cin, d.eps, st));
+                if (stats_done[i]) CG_TRY(k_in_finalize(stats, N * d.cin, h * w, d.eps, st));
+                else CG_TRY(k_in_stats<T>(x, stats, N, h * w, d.cin, d.eps, st));
                 CG_TRY(k_in_apply<T>(x, y, stats, L.g_off >= 0 ? params + L.g_off : nullptr,
                                      L.be_off >= 0 ? params + L.be_off : nullptr, L.fused_act, L.fused_slope, N,
                                      h * w, d.cin, st));
@@ -559,7 +577,7 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                             a.n0 = 0; a.nb = nb;
                             CG_TRY(tc_wgrad_launch(&c->tc[i].mapXw, &c->tc[i].mapDYw, tmp, a, fl, st));
                             CG_TRY(sp_unpack_dw(tmp, grads + L.w_off, d.k, d.cin, d.cout, 0, st));
-                            if (L.b_off >= 0) CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
+                            if (L.b_off >= 0 && !L.bias_grad_zero) CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
                         }
                         if (want_dx) CG_TRY(k_conv_dgrad<T>(dy, params + L.w_off, nullptr, dx, g, 0, st));
                     } else {
@@ -570,13 +588,13 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                             a.n0 = n0; a.nb = nb;
                             CG_TRY(tc_wgrad_launch(&c->tc[i].mapXw, &c->tc[i].mapDYw, tmp, a, fl, st));
                             CG_TRY(sp_unpack_dw(tmp, grads + L.w_off, d.k, d.cin, d.cout, 1, st));
-                            if (L.b_off >= 0) CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
+                            if (L.b_off >= 0 && !L.bias_grad_zero) CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
                         }
                         if (want_dx) {
                             const TcConvLaunch& tl = c->tc[i].dgrad[0];
                             TcConvArgs a = tl.a;
                             a.nb = nb;
-                            CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, (bf16*)dx, nullptr, a, fl, st));
+                            CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, (bf16*)dx, nullptr, a, fl, st));
                         }
                     }
                     break;
@@ -589,21 +607,21 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                         TcWgradArgs a = c->tc[i].wa;
                         a.n0 = n0; a.nb = nb;
                         CG_TRY(tc_wgrad_launch(&c->tc[i].mapXw, &c->tc[i].mapDYw, grads + L.w_off, a, fl, st));
-                        if (L.b_off >= 0)
+                        if (L.b_off >= 0 && !L.bias_grad_zero)
                             CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * (oh + 2 * hl) * (ow + 2 * hl), d.cout, st));
                     }
                     if (want_dx)
                         for (const TcConvLaunch& tl : c->tc[i].dgrad) {
                             TcConvArgs a = tl.a;
                             a.nb = nb;
-                            CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, (bf16*)dx, nullptr, a, tl.flop_share * fl, st));
+                            CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, (bf16*)dx, nullptr, a, tl.flop_share * fl, st));
                         }
                     break;
                 }
                 if (c->grad_halo[tout]) { cg_set_error("layer %d: zero-bordered dY needs the tensor-core path", i); return CG_ERR_STATE; }
                 if (grads) {
                     CG_TRY(k_conv_wgrad<T>(A(tin), dy, grads + L.w_off, g, st));
-                    if (L.b_off >= 0) CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
+                    if (L.b_off >= 0 && !L.bias_grad_zero) CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
                 }
                 if (want_dx) CG_TRY(k_conv_dgrad<T>(dy, params + L.w_off, nullptr, dx, g, acc, st));
                 break;
@@ -616,19 +634,19 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                         TcWgradArgs a = c->tc[i].wa;      // X operand = dY (arena, sub-batch relative), dY operand = x (absolute)
                         a.n0 = 0; a.nb = nb; a.y_n0 = n0;
                         CG_TRY(tc_wgrad_launch(&c->tc[i].mapXw, &c->tc[i].mapDYw, grads + L.w_off, a, fl, st));
-                        if (L.b_off >= 0) CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
+                        if (L.b_off >= 0 && !L.bias_grad_zero) CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
                     }
                     if (want_dx)
                         for (const TcConvLaunch& tl : c->tc[i].dgrad) {
                             TcConvArgs a = tl.a;
                             a.nb = nb;
-                            CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, (bf16*)dx, nullptr, a, tl.flop_share * fl, st));
+                            CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, (bf16*)dx, nullptr, a, tl.flop_share * fl, st));
                         }
                     break;
                 }
                 if (grads) {
                     CG_TRY(k_conv_wgrad<T>(dy, A(tin), grads + L.w_off, g, st));
-                    if (L.b_off >= 0) CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
+                    if (L.b_off >= 0 && !L.bias_grad_zero) CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
                 }
                 if (want_dx) CG_TRY(k_conv_fwd<T>(dy, params + L.w_off, nullptr, dx, g, acc, st));
                 break;

