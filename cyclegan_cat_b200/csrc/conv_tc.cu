@@ -548,11 +548,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                 mbar_wait(empty(s), ph ^ 1u);
                 mbar_expect_tx(full(s), stage_bytes);
                 const uint32_t sa = smem0 + s * stage_bytes;
-                for (int b = 0; b < x_boxes; ++b)
-                    tma_load_5d(sa + x_off + b * 8192u, &mapX, full(s), x_c0 + b * 64 + a.dc[tap], w0 + a.dw[tap], a.dp[tap],
-                                h0 + a.dh[tap], a.n0 + img);
-                for (int b = 0; b < y_boxes; ++b)
-                    tma_load_5d(sa + y_off + b * 8192u, &mapDY, full(s), y_c0 + b * 64, w0 + a.dy_off, 0, h0 + a.dy_off, a.y_n0 + img);
+                // (measured: every TMA instruction costs ~115 cycles of the K step on top of the MMA time, so dense
+                // operands are fetched with ONE grouped box instead of one box per 64 channels)
+                if (a.x_grouped)
+                    tma_load_5d(sa + x_off, &mapX, full(s), 0, w0 + a.dw[tap], h0 + a.dh[tap], x_c0 / 64, a.n0 + img);
+                else
+                    for (int b = 0; b < x_boxes; ++b)
+                        tma_load_5d(sa + x_off + b * 8192u, &mapX, full(s), x_c0 + b * 64 + a.dc[tap], w0 + a.dw[tap], a.dp[tap],
+                                    h0 + a.dh[tap], a.n0 + img);
+                if (a.y_grouped)
+                    tma_load_5d(sa + y_off, &mapDY, full(s), 0, w0 + a.dy_off, h0 + a.dy_off, y_c0 / 64, a.y_n0 + img);
+                else
+                    for (int b = 0; b < y_boxes; ++b)
+                        tma_load_5d(sa + y_off + b * 8192u, &mapDY, full(s), y_c0 + b * 64, w0 + a.dy_off, 0, h0 + a.dy_off,
+                                    a.y_n0 + img);
                 if (++s == S) { s = 0; ph ^= 1u; }
             }
         }
@@ -680,6 +689,25 @@ int tc_make_map_act(CUtensorMap* map, const void* base, int C, int W, int H, int
     if (r != CUDA_SUCCESS) {
         cg_set_error("cuTensorMapEncodeTiled(act C=%d W=%d H=%d N=%d parity=%d box %dx%d) failed: %d", C, W, H, N, parity,
                      box_w, box_h, (int)r);
+        return CG_ERR_CUDA;
+    }
+    return CG_OK;
+}
+
+int tc_make_map_act_grouped(CUtensorMap* map, const void* base, int C, int W, int H, int N, int box_w, int box_h, int groups) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { cg_set_error("cuTensorMapEncodeTiled is not available from the driver"); return CG_ERR_CUDA; }
+    // the group dimension sits OUTSIDE (w, h) so that the box lands as [group][h][w][64]
+    cuuint64_t dims[5] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(C / 64), (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, 128, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)groups, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        cg_set_error("cuTensorMapEncodeTiled(grouped C=%d W=%d H=%d N=%d box %dx%d x%d) failed: %d", C, W, H, N, box_w, box_h,
+                     groups, (int)r);
         return CG_ERR_CUDA;
     }
     return CG_OK;

@@ -20,6 +20,7 @@ struct TcConvArgs {
 
 struct TcWgradArgs {
     int n_taps, a_blocks, b_blocks, bn, splits, stages;   // M = 128-row blocks of operand A, N = bn-column blocks of B
+    int x_grouped, y_grouped;                   // operand map is the channel-grouped 5-D view: ONE TMA box loads all groups
     int transposed;                             // 0: A = X (rows = ci), B = dY (cols = co);  1: A = dY (rows = co), B = X
     int n0, nb, y_n0;                           // image offsets: X operand starts at n0, dY operand at y_n0
     int chunks_per_img, chunks_w, Wk, Hk;       // K chunk = 64 pixels = Wk x Hk box of the dY grid
@@ -32,6 +33,9 @@ struct TcWgradArgs {
 // 5-D activation view (c, w, p, h, n).  parity = 0: dense NHWC tensor, p is a dummy dim of size 1.
 // parity = 1: stride-2 view of an NHWC tensor with even H, W: c' = pw*C + c (size 2C), w' = w/2, p = h%2, h' = h/2.
 int tc_make_map_act(CUtensorMap* map, const void* base, int C, int W, int H, int N, int parity, int box_w, int box_h);
+// channel-grouped dense view (c%64, w, h, c/64, n): one box {64, box_w, groups, box_h, 1} lands as `groups` consecutive
+// [box_h*box_w][64] tiles -- the MN-major operand layout of wgrad_tc_kernel -- with a single TMA instruction
+int tc_make_map_act_grouped(CUtensorMap* map, const void* base, int C, int W, int H, int N, int box_w, int box_h, int groups);
 int tc_make_map_2d(CUtensorMap* map, const void* base, int cols, int rows, int box_rows);
 int tc_pack_weights(const float* w, bf16* wf, bf16* wd, int taps, int Cin, int Cout, cudaStream_t st);
 // mapB2 (nullable): the same weight matrix with a box of bn/2 rows, for the 2-CTA kernel

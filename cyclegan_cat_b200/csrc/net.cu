@@ -278,8 +278,16 @@ static int make_wgrad(TcLayer& t, const void* x, int hi, int wi, int cin_f, cons
                 a.dc[tp] = (short)((ow - 2 * aw) * cin_f); a.dw[tp] = (short)aw; a.dp[tp] = (short)(oh - 2 * ah); a.dh[tp] = (short)ah;
             }
         }
-    CG_TRY(tc_make_map_act(&t.mapXw, x, cin_f, wi, hi, N, s == 2, a.Wk, a.Hk));
-    CG_TRY(tc_make_map_act(&t.mapDYw, dy, cout_f, wo + 2 * dy_halo, ho + 2 * dy_halo, N, 0, a.Wk, a.Hk));
+    // operand roles: A (128 rows = 2 channel groups) and B (bn columns = bn/64 groups)
+    const int x_groups = a.transposed ? a.bn / 64 : 2, y_groups = a.transposed ? 2 : a.bn / 64;
+    if (s == 1) {
+        a.x_grouped = 1;
+        CG_TRY(tc_make_map_act_grouped(&t.mapXw, x, cin_f, wi, hi, N, a.Wk, a.Hk, x_groups));
+    } else {
+        CG_TRY(tc_make_map_act(&t.mapXw, x, cin_f, wi, hi, N, 1, a.Wk, a.Hk));
+    }
+    a.y_grouped = 1;
+    CG_TRY(tc_make_map_act_grouped(&t.mapDYw, dy, cout_f, wo + 2 * dy_halo, ho + 2 * dy_halo, N, a.Wk, a.Hk, y_groups));
     return CG_OK;
 }
 
@@ -359,8 +367,9 @@ int net_bind(CallCtx* c) {
                 a.chunks_w = wo / a.Wk; a.chunks_per_img = a.chunks_w * (ho / a.Hk);
                 a.Cin = 128; a.Cout = d.cout;
                 for (int kh = 0; kh < k; ++kh) a.dh[kh] = (short)kh;
-                CG_TRY(tc_make_map_act(&t.mapXw, U, 128, wo, hi, c->N, 0, a.Wk, a.Hk));
-                CG_TRY(tc_make_map_act(&t.mapDYw, dy, d.cout, wo, ho, c->N, 0, a.Wk, a.Hk));
+                a.x_grouped = a.y_grouped = 1;
+                CG_TRY(tc_make_map_act_grouped(&t.mapXw, U, 128, wo, hi, c->N, a.Wk, a.Hk, 2));
+                CG_TRY(tc_make_map_act_grouped(&t.mapDYw, dy, d.cout, wo, ho, c->N, a.Wk, a.Hk, d.cout / 64));
             }
         } else if (L.tc == TC_HEAD) {
             if (!c->tcs) { cg_set_error("net_bind: no scratch for the unfolded head tensors"); return CG_ERR_STATE; }
@@ -408,8 +417,9 @@ int net_bind(CallCtx* c) {
                 a.chunks_per_img = ho * wi / 64; a.chunks_w = a.chunks_per_img;
                 a.Cin = d.cin; a.Cout = 128;
                 for (int kh = 0; kh < k; ++kh) a.dw[kh] = (short)(kh * wi);
-                CG_TRY(tc_make_map_act(&t.mapXw, x, d.cin, hi * wi, 1, c->N, 0, 64, 1));
-                CG_TRY(tc_make_map_act(&t.mapDYw, T, 128, ho * wi, 1, c->N, 0, 64, 1));
+                a.x_grouped = a.y_grouped = 1;
+                CG_TRY(tc_make_map_act_grouped(&t.mapXw, x, d.cin, hi * wi, 1, c->N, 64, 1, d.cin / 64));
+                CG_TRY(tc_make_map_act_grouped(&t.mapDYw, T, 128, ho * wi, 1, c->N, 64, 1, 2));
             }
         } else if (L.tc == TC_CONVT_S2) {
             // F: (ho x wo x cout) -> (hi x wi x cin), stride 2, 'same' padding computed on the big grid

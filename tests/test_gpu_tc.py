@@ -106,11 +106,11 @@ def test_tc_strided_and_transposed_convs_match_cuda_core(cin, cout, k, h, w, n):
     ya, dxa, ga = _net_grads(a, x, dy)
     yb, dxb, gb = _net_grads(b, x, dy)
     assert C.rel_l2(ya, yb) <= 4e-3, C.rel_l2(ya, yb)
-    assert C.rel_l2(dxa, dxb) <= 1e-2, C.rel_l2(dxa, dxb)
+    assert C.rel_l2(dxa, dxb) <= 2e-2, C.rel_l2(dxa, dxb)
     scale = max(np.linalg.norm(v) for v in gb)
     for i, (u, v) in enumerate(zip(ga, gb)):
         e = np.linalg.norm(u - v) / max(np.linalg.norm(v), 0.02 * scale)
-        assert e <= 1e-2, (i, u.shape, e)
+        assert e <= 2e-2, (i, u.shape, e)
 
 
 @pytest.mark.parametrize("f,h,w,n", [(64, 64, 64, 2), (64, 32, 128, 3), (128, 256, 256, 1)])
