@@ -209,10 +209,16 @@ def run_gpu(args, wl):
     lib.cg_prof_enable(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    prof_range = os.environ.get("CG_PROFILE_STEP") == "1"      # ncu --profile-from-start off: capture exactly the timed steps
+    if prof_range:
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(args.steps):
         m = gan.train_step(a_dev, b_dev)
     e1.record()
+    if prof_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop()
