@@ -57,7 +57,26 @@ __global__ void __launch_bounds__(256) in_reduce_kernel(const T* __restrict__ x,
             rstd = stats[((size_t)n * C + c) * 2 + 1];
             if (gamma) { ga = gamma[c]; be = beta[c]; }
         }
-        for (int p = p0 + warp; p < p1; p += 8) {
+        int p = p0 + warp;
+        for (; p + 24 < p1; p += 32) {      // 4 independent pixels in flight per lane
+            float v[4], gy[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v[u] = ldf(x + base + (size_t)(p + 8 * u) * C);
+                if (MODE == 1) gy[u] = ldf(dy + base + (size_t)(p + 8 * u) * C);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (MODE == 0) { s += v[u]; ss += v[u] * v[u]; }
+                else {
+                    float xh = (v[u] - mean) * rstd;
+                    float g = gy[u] * act_grad_from_out(xh * ga + be, act, slope);
+                    s += g;
+                    ss += g * xh;
+                }
+            }
+        }
+        for (; p < p1; p += 8) {
             float v = ldf(x + base + (size_t)p * C);
             if (MODE == 0) {
                 s += v;
@@ -166,7 +185,20 @@ __global__ void __launch_bounds__(256) in_apply_fast_kernel(const T* __restrict_
         sh[j] = be - mean * sc[j];
     }
     const size_t base = (size_t)n * P * C + (size_t)cv * VEC;
-    for (int p = blockIdx.x * ppb + prow; p < P; p += gridDim.x * ppb) {
+    const int stride = gridDim.x * ppb;
+    int p = blockIdx.x * ppb + prow;
+    for (; p + 3 * stride < P; p += 4 * stride) {       // 4 independent 16-byte loads in flight per thread
+        float v[4][VEC];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) load_vec<T, VEC>(x + base + (size_t)(p + u * stride) * C, v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) v[u][j] = act_fwd(fmaf(v[u][j], sc[j], sh[j]), act, slope);
+            store_vec<T, VEC>(y + base + (size_t)(p + u * stride) * C, v[u]);
+        }
+    }
+    for (; p < P; p += stride) {
         float v[VEC];
         load_vec<T, VEC>(x + base + (size_t)p * C, v);
 #pragma unroll
