@@ -171,7 +171,7 @@ extern "C" int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode
                 kind = TC_CONV_S2;
             else if (d.op == CG_OP_CONVT && d.stride == 2 && (d.k == 3 || d.k == 4) && chan_ok(d.cout, d.cin))
                 kind = TC_CONVT_S2;
-            else if (d.op == CG_OP_CONV && d.stride == 1 && !d.same && d.k >= 3 && d.cin <= 4 && d.k * d.cin <= 64 &&
+            else if (d.op == CG_OP_CONV && d.stride == 1 && !d.same && d.k >= 3 && d.cin <= 4 && d.k * d.cin <= 32 &&
                      d.cout % 64 == 0 && d.cout <= 256)
                 kind = TC_STEM;         // c7s1-f stem (resnet.py:39-40): horizontal taps unfolded into channels
             else if (d.op == CG_OP_CONV && d.stride == 1 && !d.same && d.k >= 3 && d.cout <= 4 && d.k * d.cout <= 32 &&
@@ -180,6 +180,7 @@ extern "C" int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode
             if (kind == TC_STEM) {
                 L.tc = kind;
                 L.pk_f = (long long)pk; pk += align_up((size_t)d.k * d.cout * 64 * 2, 1024);
+                L.pk_d = (long long)pk; pk += align_up((size_t)d.k * 32 * d.cout * 2, 1024);
             } else if (kind == TC_HEAD) {
                 L.tc = kind;
                 L.pk_f = (long long)pk; pk += align_up((size_t)d.k * 32 * d.cin * 2, 1024);

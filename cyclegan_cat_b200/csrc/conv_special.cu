@@ -92,23 +92,43 @@ int sp_pack_head(const float* w, bf16* wh, bf16* whd, int k, int Cin, int Cout, 
     return CG_OK;
 }
 
-// head forward, second half: y[n][oh][ow][co] = bias[co] + sum_kw S[n][oh][ow+kw][kw*Cout+co]   (S has 32 channels)
+// second half of the unfolded 7x1 convs: y[n][r][x][c] = bias[c] + sum_kw S[n][r][x + sign*kw][kw*C + c]  (S: 32 channels,
+// width Ws; terms outside [0, Ws) are zero).  sign = +1: head forward (x < Wo <= Ws - k + 1);  sign = -1: stem data gradient.
 __global__ void diag_sum_kernel(const bf16* __restrict__ S, const float* __restrict__ bias, bf16* __restrict__ y, int N,
-                                int Ho, int Wo, int Wp, int k, int Cout) {
-    const size_t total = (size_t)N * Ho * Wo;
+                                int R, int Wy, int Ws, int k, int C, int sign) {
+    const size_t total = (size_t)N * R * Wy;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int ow = (int)(i % Wo);
-        const size_t row = i / Wo;                          // n*Ho + oh
+        const int x = (int)(i % Wy);
+        const size_t row = i / Wy;                          // n*R + r
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         for (int kw = 0; kw < k; ++kw) {
-            const bf16* p = S + (row * Wp + ow + kw) * 32 + kw * Cout;
-            for (int c = 0; c < Cout; ++c) acc[c] += __bfloat162float(p[c]);
+            const int xs = x + sign * kw;
+            if (xs < 0 || xs >= Ws) continue;
+            const bf16* p = S + (row * Ws + xs) * 32 + kw * C;
+            for (int c = 0; c < C; ++c) acc[c] += __bfloat162float(p[c]);
         }
-        for (int c = 0; c < Cout; ++c) y[i * Cout + c] = __float2bfloat16(acc[c] + (bias ? bias[c] : 0.f));
+        for (int c = 0; c < C; ++c) y[i * C + c] = __float2bfloat16(acc[c] + (bias ? bias[c] : 0.f));
     }
 }
-int sp_diag_sum(const bf16* S, const float* bias, bf16* y, int N, int Ho, int Wo, int Wp, int k, int Cout, cudaStream_t st) {
-    diag_sum_kernel<<<blocks_for((size_t)N * Ho * Wo), 256, 0, st>>>(S, bias, y, N, Ho, Wo, Wp, k, Cout);
+int sp_diag_sum(const bf16* S, const float* bias, bf16* y, int N, int R, int Wy, int Ws, int k, int C, int sign,
+                cudaStream_t st) {
+    diag_sum_kernel<<<blocks_for((size_t)N * R * Wy), 256, 0, st>>>(S, bias, y, N, R, Wy, Ws, k, C, sign);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+// stem data-gradient weights: w[kh][kw][ci][co] -> Wsd[kh][kw*Cin+ci (32 rows)][co]
+__global__ void pack_stem_d_kernel(const float* __restrict__ w, bf16* __restrict__ wsd, int k, int Cin, int Cout) {
+    const int total = k * 32 * Cout;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int co = i % Cout, row = (i / Cout) % 32, kh = i / (Cout * 32);
+        float v = 0.f;
+        if (row < k * Cin) { const int kw = row / Cin, ci = row - kw * Cin; v = w[(((size_t)kh * k + kw) * Cin + ci) * Cout + co]; }
+        wsd[i] = __float2bfloat16(v);
+    }
+}
+int sp_pack_stem_d(const float* w, bf16* wsd, int k, int Cin, int Cout, cudaStream_t st) {
+    pack_stem_d_kernel<<<blocks_for((size_t)k * 32 * Cout), 256, 0, st>>>(w, wsd, k, Cin, Cout);
     CG_LAUNCH_CHECK();
     return CG_OK;
 }

@@ -164,6 +164,7 @@ int net_pack(const cg_net_s* net, const float* params, void* packed, cudaStream_
         if (!L.tc) continue;
         if (L.tc == TC_STEM) {
             CG_TRY(sp_pack_stem(params + L.w_off, (bf16*)((char*)packed + L.pk_f), L.d.k, L.d.cin, L.d.cout, st));
+            CG_TRY(sp_pack_stem_d(params + L.w_off, (bf16*)((char*)packed + L.pk_d), L.d.k, L.d.cin, L.d.cout, st));
             continue;
         }
         if (L.tc == TC_HEAD) {
@@ -371,6 +372,25 @@ int net_bind(CallCtx* c) {
                 CG_TRY(tc_make_map_act_grouped(&t.mapXw, U, 128, wo, hi, c->N, a.Wk, a.Hk, 2));
                 CG_TRY(tc_make_map_act_grouped(&t.mapDYw, dy, d.cout, wo, ho, c->N, a.Wk, a.Hk, d.cout / 64));
             }
+            // data gradient (only needed when the stem's input is itself a generated image: the cycle calls):
+            //   S'[ih][q][kw*cin+ci] = sum_kh dy[ih-kh][q][:] . Wsd[kh][kw*cin+ci][:]  (flat mode, 7 vertical taps), then a
+            //   horizontal diagonal sum; S' lives in the scratch
+            t.dgrad.assign(1, TcConvLaunch());
+            {
+                TcConvArgs& a = t.dgrad[0].a;
+                memset(&a, 0, sizeof(a));
+                a.Wb = 128; a.Hb = 1;
+                a.n_taps = k; a.cchunks = d.cout / 64; a.bn = 32; a.n_blocks_n = 1;
+                a.tiles_per_img = (hi * wo + 127) / 128; a.tiles_w = a.tiles_per_img;
+                a.nb = c->N;
+                a.out_P = wo; a.out_wvalid = wo; a.out_hvalid = hi; a.out_H = hi; a.out_W = wo; a.Cout = 32;
+                a.out_sy = a.out_sx = 1;
+                a.b_rows_per_tap = 32;
+                for (int kh = 0; kh < k; ++kh) { a.tb[kh] = (short)kh; a.dw[kh] = (short)(-kh * wo); }
+                CG_TRY(tc_make_map_act(&t.dgrad[0].mapA, dy, d.cout, ho * wo, 1, c->N, 0, 128, 1));
+                CG_TRY(tc_make_map_2d(&t.dgrad[0].mapB, wd, d.cout, k * 32, 32));
+                CG_TRY(tc_make_map_2d(&t.dgrad[0].mapB2, wd, d.cout, k * 32, 16));
+            }
         } else if (L.tc == TC_HEAD) {
             if (!c->tcs) { cg_set_error("net_bind: no scratch for the unfolded head tensors"); return CG_ERR_STATE; }
             const void* S = c->tcs;                         // forward:  [N][ho][wi][32]
@@ -475,7 +495,7 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
                     TcConvArgs a = tl.a;
                     a.nb = N;
                     CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, (bf16*)c->tcs, nullptr, a, fl, st));
-                    CG_TRY(sp_diag_sum((const bf16*)c->tcs, bias, (bf16*)y, N, oh, ow, w, d.k, d.cout, st));
+                    CG_TRY(sp_diag_sum((const bf16*)c->tcs, bias, (bf16*)y, N, oh, ow, w, d.k, d.cout, +1, st));
                 } else if (c->tc[i].on) {
                     for (const TcConvLaunch& tl : c->tc[i].fwd) {
                         TcConvArgs a = tl.a;
@@ -589,7 +609,13 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                             CG_TRY(sp_unpack_dw(tmp, grads + L.w_off, d.k, d.cin, d.cout, 0, st));
                             if (L.b_off >= 0 && !L.bias_grad_zero) CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
                         }
-                        if (want_dx) CG_TRY(k_conv_dgrad<T>(dy, params + L.w_off, nullptr, dx, g, 0, st));
+                        if (want_dx) {
+                            const TcConvLaunch& tl = c->tc[i].dgrad[0];
+                            TcConvArgs a = tl.a;
+                            a.nb = nb;
+                            CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, big, nullptr, a, fl, st));
+                            CG_TRY(sp_diag_sum(big, nullptr, (bf16*)dx, nb, h, w, ow, d.k, d.cin, -1, st));
+                        }
                     } else {
                         CG_TRY(sp_unfold_w((const bf16*)dy, big, nb, oh, ow, d.cout, w, d.k, -1, st));
                         if (grads) {
