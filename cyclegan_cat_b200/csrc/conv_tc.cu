@@ -769,7 +769,7 @@ int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, const CUten
         if (clusters > total_pairs) clusters = total_pairs;
         int pi = prof_begin(st);
         conv_tc2_kernel<<<2 * clusters, TC_THREADS, smem, st>>>(*mapA, *mapB2, out, bias, a);
-        prof_end(pi, st, flops);
+        prof_end(pi, st, flops, prof_key(2, a.n_taps, a.cchunks, a.bn, a.tiles_per_img, a.nb));
         CG_LAUNCH_CHECK();
         return CG_OK;
     }
@@ -785,7 +785,7 @@ int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, const CUten
     int grid = total < num_sms() ? total : num_sms();
     int pi = prof_begin(st);
     conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(*mapA, *mapB, out, bias, a);
-    prof_end(pi, st, flops);
+    prof_end(pi, st, flops, prof_key(1, a.n_taps, a.cchunks, a.bn, a.tiles_per_img, a.nb));
     CG_LAUNCH_CHECK();
     return CG_OK;
 }
@@ -810,7 +810,7 @@ int tc_wgrad_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* dw
     }
     int pi = prof_begin(st);
     wgrad_tc_kernel<<<units * splits, TC_THREADS, smem, st>>>(*mapX, *mapDY, dw, a);
-    prof_end(pi, st, flops);
+    prof_end(pi, st, flops, prof_key(3, a.n_taps, a.a_blocks * a.b_blocks, a.bn, a.chunks_per_img, a.nb));
     CG_LAUNCH_CHECK();
     return CG_OK;
 }

@@ -207,9 +207,11 @@ __global__ void __launch_bounds__(256) in_apply_fast_kernel(const T* __restrict_
     }
 }
 
-// dx = rstd*gamma*(g - S1/P - xhat*S2/P), optionally into a zero-bordered [H+2h][W+2h] buffer (halo > 0)
-template <typename T, int VEC>
-__global__ void __launch_bounds__(256) in_bwd_apply_fast_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+// dx = rstd*gamma*(g - S1/P - xhat*S2/P), optionally into a zero-bordered [H+2h][W+2h] buffer (halo > 0).
+// Per-channel constants are folded to keep the register count (and with it the occupancy) in check:
+//   xhat = v*a + b,  r = k*gg - c1 - xhat*c2   with a = rstd, b = -mean*rstd, k = rstd*gamma, c1 = k*S1/P, c2 = k*S2/P
+template <typename T, int VEC, bool AFFINE>
+__global__ void __launch_bounds__(256, AFFINE ? 2 : 4) in_bwd_apply_fast_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                                 T* __restrict__ dx, const float* __restrict__ stats,
                                                                 const float* __restrict__ sums,
                                                                 const float* __restrict__ gamma,
@@ -218,24 +220,26 @@ __global__ void __launch_bounds__(256) in_bwd_apply_fast_kernel(const T* __restr
                                                                 int accumulate) {
     const int CV = C / VEC, n = blockIdx.y;
     const int cv = threadIdx.x % CV, prow = threadIdx.x / CV, ppb = 256 / CV;
-    float mean[VEC], rstd[VEC], ga[VEC], be[VEC], s1[VEC], s2[VEC];
+    float ca[VEC], cb[VEC], ck[VEC], c1[VEC], c2[VEC], cg[AFFINE ? VEC : 1], ce[AFFINE ? VEC : 1];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
         const int c = cv * VEC + j;
-        mean[j] = stats[((size_t)n * C + c) * 2];
-        rstd[j] = stats[((size_t)n * C + c) * 2 + 1];
-        ga[j] = gamma ? gamma[c] : 1.f;
-        be[j] = beta ? beta[c] : 0.f;
-        s1[j] = sums[((size_t)n * C + c) * 2] * invP;
-        s2[j] = sums[((size_t)n * C + c) * 2 + 1] * invP;
+        const float mean = stats[((size_t)n * C + c) * 2], rstd = stats[((size_t)n * C + c) * 2 + 1];
+        const float ga = AFFINE ? gamma[c] : 1.f;
+        ca[j] = rstd;
+        cb[j] = -mean * rstd;
+        ck[j] = rstd * ga;
+        c1[j] = ck[j] * sums[((size_t)n * C + c) * 2] * invP;
+        c2[j] = ck[j] * sums[((size_t)n * C + c) * 2 + 1] * invP;
+        if (AFFINE) { cg[j] = ga; ce[j] = beta[c]; }
     }
     const int Hp = H + 2 * halo, Wp = W + 2 * halo;
     const int PP = Hp * Wp;
     const size_t in_base = (size_t)n * H * W * C + (size_t)cv * VEC;
     const size_t out_base = (size_t)n * PP * C + (size_t)cv * VEC;
     for (int pp = blockIdx.x * ppb + prow; pp < PP; pp += gridDim.x * ppb) {
-        const int hp = pp / Wp, wp = pp - hp * Wp;
-        const int h = hp - halo, w = wp - halo;
+        int h = 0, w = pp;
+        if (halo > 0) { const int hp = pp / Wp; w = pp - hp * Wp - halo; h = hp - halo; }
         float o[VEC];
         if (h >= 0 && h < H && w >= 0 && w < W) {
             const size_t e = in_base + ((size_t)h * W + w) * C;
@@ -245,9 +249,10 @@ __global__ void __launch_bounds__(256) in_bwd_apply_fast_kernel(const T* __restr
             if (accumulate) load_vec<T, VEC>(dx + out_base + (size_t)pp * C, o);
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
-                const float xh = (v[j] - mean[j]) * rstd[j];
-                const float gg = g[j] * act_grad_from_out(fmaf(xh, ga[j], be[j]), act, slope);
-                const float r = rstd[j] * ga[j] * (gg - s1[j] - xh * s2[j]);
+                const float xh = fmaf(v[j], ca[j], cb[j]);
+                const float pre = AFFINE ? fmaf(xh, cg[j], ce[j]) : xh;
+                const float gg = g[j] * act_grad_from_out(pre, act, slope);
+                const float r = fmaf(ck[j], gg, -fmaf(xh, c2[j], c1[j]));
                 o[j] = accumulate ? o[j] + r : r;
             }
         } else {
@@ -372,6 +377,8 @@ template <typename T> int k_in_bwd(const T* x, const T* dy, T* dx, const float* 
                                    const float* beta, float* dgamma, float* dbeta, float* scratch, int act,
                                    float slope, int N, int P, int C, int accumulate, cudaStream_t st, int halo, int W) {
     CG_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * 2 * (size_t)N * C, st));
+    // (a register-resident, 16-byte-vector variant of this reduction was measured slower -- 51 us vs 43 us per trunk
+    // launch -- than the lanes-over-channels kernel with its 6 resident blocks per SM, so the simple kernel stays)
     dim3 grid; int pchunk;
     in_reduce_grid(N, P, C, grid, pchunk);
     in_reduce_kernel<T, 1><<<grid, 256, 0, st>>>(x, dy, stats, gamma, beta, scratch, P, C, pchunk, act, slope);
@@ -384,8 +391,12 @@ template <typename T> int k_in_bwd(const T* x, const T* dy, T* dx, const float* 
         constexpr int VW = VecWidth<T>::value;
         const int Wd = halo > 0 ? W : P, Hd = halo > 0 ? P / W : 1;     // halo == 0: treat the plane as one row
         dim3 g2(fast_blocks((Hd + 2 * halo) * (Wd + 2 * halo), C, VW, N), N);
-        in_bwd_apply_fast_kernel<T, VW><<<g2, 256, 0, st>>>(x, dy, dx, stats, scratch, gamma, beta, act, slope, Hd, Wd, C,
-                                                           halo, 1.f / (float)P, accumulate);
+        if (gamma)
+            in_bwd_apply_fast_kernel<T, VW, true><<<g2, 256, 0, st>>>(x, dy, dx, stats, scratch, gamma, beta, act, slope, Hd,
+                                                                     Wd, C, halo, 1.f / (float)P, accumulate);
+        else
+            in_bwd_apply_fast_kernel<T, VW, false><<<g2, 256, 0, st>>>(x, dy, dx, stats, scratch, gamma, beta, act, slope, Hd,
+                                                                      Wd, C, halo, 1.f / (float)P, accumulate);
         CG_LAUNCH_CHECK();
     } else if (dx && halo > 0) {
         constexpr int VW = VecWidth<T>::value;

@@ -1,5 +1,8 @@
 // CUDA-event timing of one kernel family inside a running step (bench.py's roofline numbers):
 // every launch of the family is bracketed by two events on the launching stream.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <mutex>
 #include <vector>
 
@@ -13,6 +16,8 @@ bool on = false;
 std::vector<Pair> pool;
 size_t used = 0;
 double flops = 0.0;
+std::vector<double> rec_flops;
+std::vector<unsigned long long> rec_key;
 }   // namespace
 
 bool prof_enabled() { return on; }
@@ -29,11 +34,14 @@ int prof_begin(cudaStream_t st) {
     return (int)used++;
 }
 
-void prof_end(int idx, cudaStream_t st, double fl) {
+void prof_end(int idx, cudaStream_t st, double fl, unsigned long long key) {
     if (idx < 0) return;
     std::lock_guard<std::mutex> lk(mu);
     cudaEventRecord(pool[idx].b, st);
     flops += fl;
+    if (rec_flops.size() <= (size_t)idx) { rec_flops.resize(idx + 1); rec_key.resize(idx + 1); }
+    rec_flops[idx] = fl;
+    rec_key[idx] = key;
 }
 
 extern "C" int cg_prof_enable(int enable) {
@@ -48,10 +56,19 @@ extern "C" int cg_prof_read(double* total_ms, int64_t* launches, double* total_f
     CG_CUDA(cudaDeviceSynchronize());
     std::lock_guard<std::mutex> lk(mu);
     double ms = 0.0;
+    const char* dump = getenv("CG_PROF_DUMP");       // per-launch CSV: key, flops, ms
+    FILE* f = dump ? fopen(dump, "w") : nullptr;
+    if (f) fprintf(f, "kind,taps,cchunks,bn,tiles,nb,flops,ms\n");
     for (size_t i = 0; i < used; ++i) {
         float t = 0.f;
         if (cudaEventElapsedTime(&t, pool[i].a, pool[i].b) == cudaSuccess) ms += t;
+        if (f && i < rec_key.size()) {
+            const unsigned long long k = rec_key[i];
+            fprintf(f, "%llu,%llu,%llu,%llu,%llu,%llu,%.0f,%.5f\n", k >> 60, (k >> 52) & 0xff, (k >> 44) & 0xff, (k >> 32) & 0xfff,
+                    (k >> 12) & 0xfffff, k & 0xfff, rec_flops[i], t);
+        }
     }
+    if (f) fclose(f);
     if (total_ms) *total_ms = ms;
     if (launches) *launches = (int64_t)used;
     if (total_flops) *total_flops = flops;
