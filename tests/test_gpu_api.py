@@ -1,0 +1,107 @@
+"""GPU tests of the reference-facing API beyond the single step: epoch loop, checkpoint round trip
+(model.py:156-231, 304-362), predict path (predict.py:20-39), C-ABI error behaviour."""
+import ctypes
+import os
+import shutil
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from cyclegan_cat_b200 import _lib, ir
+from cyclegan_cat_b200.cyclegan.model import CycleGan, create_model
+from cyclegan_cat_b200.runtime import _ptr, _stream_ptr
+from cyclegan_cat_b200.transform.data_load import normalize
+from tests import common as C
+
+pytestmark = pytest.mark.gpu
+
+
+def _gan(folder, new=True, mode="fp32"):
+    mc = C.model_config(C.SMALL_RESNET, C.SMALL_SIMPLE)
+    mc.location, mc.name, mc.new = folder, "m", new
+    tc = C.train_config(batch_size=2)
+    tc.epochs = 2
+    tc.summary = dict(samples=2, images=1, model=1)
+    return CycleGan(mc, tc, mode=mode)
+
+
+def _dataset(n, size=32, seed=0):
+    rng = np.random.RandomState(seed)
+    return [(rng.uniform(-1, 1, (size, size, 3)).astype(np.float32),
+             rng.uniform(-1, 1, (size, size, 3)).astype(np.float32)) for _ in range(n)]
+
+
+def test_epoch_loop_checkpoint_and_resume():
+    folder = tempfile.mkdtemp(prefix="cg_b200_")
+    try:
+        gan = _gan(folder)
+        train, val = _dataset(5), _dataset(3, seed=1)      # 5 samples, batch 2 -> ragged last batch (model.py:197)
+        gan.train(train, val)
+        assert gan.model_config.current_epoch == 2 and gan.model_config.new is False
+        for f in ("g_AB/variables.npz", "d_B/variables.npz", "g_AB_optimizer.npy", "a_samples.npy", "model_config.yaml"):
+            assert os.path.exists(os.path.join(folder, "m", f)), f
+        w_before = gan.g_AB.get_weights()
+        opt_before = gan.g_AB_optimizer.get_weights()
+        assert int(opt_before[0]) == 2 * 3                  # 2 epochs x 3 batches
+        # resume: new=False -> load_model(); optimizer slots restored once the trainer exists
+        gan2 = _gan(folder, new=False)
+        for a, b in zip(w_before, gan2.g_AB.get_weights()):
+            assert np.array_equal(a, b)
+        gan2.prepare(2, 32, 32)
+        gan2.restore_optimizers()
+        opt_after = gan2.g_AB_optimizer.get_weights()
+        assert int(opt_after[0]) == 6
+        for a, b in zip(opt_before[1:], opt_after[1:]):
+            assert np.array_equal(a, b)
+        # both continue identically for one more step (same weights, same Adam state)
+        a, b = np.stack([t[0] for t in train[:2]]), np.stack([t[1] for t in train[:2]])
+        m1, m2 = gan.train_step(a, b), gan2.train_step(a, b)
+        for k in m1:
+            assert abs(float(m1[k]) - float(m2[k])) <= 1e-5 * max(1.0, abs(float(m1[k]))), k
+    finally:
+        shutil.rmtree(folder, ignore_errors=True)
+
+
+def test_predict_path_like_predict_py():
+    """predict.py:20-39: uint8 image -> normalize -> model(x)[0] -> (y+1)*127.5 -> uint8."""
+    g = create_model(C.FIX_RESNET, mode="bf16")
+    img = np.random.RandomState(0).randint(0, 256, (64, 64, 3)).astype(np.uint8)
+    x = normalize(img)[np.newaxis, ...]
+    y = g(x)
+    out = np.array((y[0] + 1) * 127.5, np.uint8)
+    assert out.shape == (64, 64, 3) and out.dtype == np.uint8
+    p = g.predict(np.concatenate([x, x, x]), batch_size=2)
+    # same image in different batches / runs: equal up to bf16 re-rounding (fp32 atomic order in the IN statistics)
+    assert p.shape == (3, 64, 64, 3) and C.rel_l2(p[0], p[2]) <= 2e-2
+    assert C.rel_l2(p[0], y.numpy()[0]) <= 2e-2
+
+
+def test_c_abi_error_codes():
+    lib = _lib.load()
+    m = create_model(C.SMALL_SIMPLE, mode="fp32")
+    h, p = m.handle(), m.device_params()
+    x = torch.zeros((1, 32, 32, 3), device="cuda")
+    y = torch.zeros(m.out_shape(1, 32, 32), device="cuda")
+    small = torch.empty(64, dtype=torch.uint8, device="cuda")
+    st = _stream_ptr(torch)
+    rc = lib.cg_net_forward(h, _ptr(p), _ptr(x), _ptr(y), _ptr(small), small.numel(), 1, 32, 32, 0, st)
+    assert rc == -3 and b"workspace" in lib.cg_last_error()                     # CG_ERR_WORKSPACE
+    rc = lib.cg_net_backward(h, _ptr(p), _ptr(y), None, None, 0, _ptr(small), small.numel(), st)
+    assert rc == -4                                                              # CG_ERR_STATE: no forward on this workspace
+    assert lib.cg_net_forward(h, None, _ptr(x), _ptr(y), _ptr(small), 64, 1, 32, 32, 0, st) == -1      # null params
+    out = (ctypes.c_int * 4)()
+    assert lib.cg_net_out_shape(h, 1, 30, 30, ctypes.byref(out)) == 0            # simple D accepts any size (ceil)
+    with pytest.raises(ValueError):
+        CycleGan(C.model_config(C.SMALL_RESNET, C.SMALL_SIMPLE), C.train_config()).train_step(
+            np.zeros((2, 32, 32, 3), np.float32), np.zeros((1, 32, 32, 3), np.float32))
+
+
+def test_mixed_modes_rejected():
+    from cyclegan_cat_b200.ir import TrainCfg
+    a, b = create_model(C.SMALL_RESNET, mode="bf16"), create_model(C.SMALL_SIMPLE, mode="fp32")
+    h = ctypes.c_void_p()
+    cfg = TrainCfg()
+    rc = _lib.load().cg_trainer_create(a.handle(), a.handle(), b.handle(), b.handle(), ctypes.byref(cfg), ctypes.byref(h))
+    assert rc == -1 and b"mode" in _lib.load().cg_last_error()
