@@ -146,9 +146,11 @@ extern "C" int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode
     // reference computes rounding noise there; this library writes the exact value 0 and skips the reduction.
     for (int i = 0; i + 1 < n_layers; ++i) {
         LayerInfo& L = net->layers[i];
-        if ((L.d.op == CG_OP_CONV || L.d.op == CG_OP_CONVT) && L.d.has_bias && net->n_consumers[i + 1] == 1 &&
-            net->layers[i + 1].d.op == CG_OP_INORM && net->layers[i + 1].d.in0 == i + 1)
-            L.bias_grad_zero = true;
+        if ((L.d.op == CG_OP_CONV || L.d.op == CG_OP_CONVT) && net->n_consumers[i + 1] == 1 &&
+            net->layers[i + 1].d.op == CG_OP_INORM && net->layers[i + 1].d.in0 == i + 1) {
+            L.feeds_in = true;
+            L.bias_grad_zero = L.d.has_bias != 0;
+        }
     }
     // tensor-core layers (bf16 mode): 3x3 stride-1 'valid' convs with Cin % 128 == 0 and Cout % 64 == 0 whose output
     // feeds exactly one instance norm (its backward writes the zero-bordered dY the TMA loads expect)
@@ -177,6 +179,9 @@ extern "C" int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode
             else if (d.op == CG_OP_CONV && d.stride == 1 && !d.same && d.k >= 3 && d.cout <= 4 && d.k * d.cout <= 32 &&
                      d.cin % 64 == 0 && d.cin <= 256)
                 kind = TC_HEAD;         // c7s1-3 tanh head (resnet.py:82)
+            else if (d.op == CG_OP_CONV && d.stride == 1 && (d.same || d.k == 1) && d.k <= 7 && d.cin % 16 == 0 &&
+                     d.cout % 16 == 0 && d.cout <= 256 && d.cin <= 256 * 8)
+                kind = TC_S1_16;        // U-Net double_conv layers (unet.py:25): channel counts are multiples of 16 only
             if (kind == TC_STEM) {
                 L.tc = kind;
                 L.pk_f = (long long)pk; pk += align_up((size_t)d.k * d.cout * 64 * 2, 1024);

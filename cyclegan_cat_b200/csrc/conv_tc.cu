@@ -61,6 +61,12 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -120,6 +126,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     d |= (uint64_t)2 << 61;                               // layout type: SWIZZLE_128B
     return d;
 }
+// same for SWIZZLE_32B K-major tiles: rows of 32 bytes (16 bf16 = one MMA K), 8-row atoms of 256 bytes
+__device__ __forceinline__ uint64_t make_smem_desc32(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;                               // LBO (unused for swizzled K-major)
+    d |= (uint64_t)(256 >> 4) << 32;                      // SBO = 256 B
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;                               // layout type: SWIZZLE_32B
+    return d;
+}
 // instruction descriptor (cute::UMMA::InstrDescriptor): BF16 x BF16 -> F32, dense
 static inline uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
     uint32_t d = 0;
@@ -169,7 +185,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t stage_bytes = A_TILE_BYTES + (uint32_t)a.bn * 128u;
+    const uint32_t a_bytes = a.bk16 ? (uint32_t)a.groups * 4096u : (uint32_t)A_TILE_BYTES;
+    const uint32_t stage_bytes = a.bk16 ? (uint32_t)a.groups * (4096u + (uint32_t)a.bn * 32u) : A_TILE_BYTES + (uint32_t)a.bn * 128u;
     const int S = a.stages;
     const uint32_t bar0 = smem0 + S * stage_bytes;          // full[S], empty[S], tfull[2], tempty[2], tmem ptr
     auto full = [&](int s) { return bar0 + 8u * s; };
@@ -194,7 +211,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     const int total_tiles = a.nb * a.tiles_per_img * a.n_blocks_n;
-    const int ksteps = a.n_taps * a.cchunks;
+    const int ksteps = a.n_taps * a.cchunks;       // bk16: cchunks = K steps per tap (blocks of `groups` 16-channel groups)
 
     if (warp == 0) {
         if (lane == 0) {
@@ -208,8 +225,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     mbar_wait(empty(s), ph ^ 1u);
                     mbar_expect_tx(full(s), stage_bytes);
                     const uint32_t sa = smem0 + s * stage_bytes;
-                    tma_load_5d(sa, &mapA, full(s), cc * 64 + a.dc[tap], w0 + a.dw[tap], a.dp[tap], h0 + a.dh[tap], img);
-                    tma_load_2d(sa + A_TILE_BYTES, &mapB, full(s), cc * 64, a.tb[tap] * a.b_rows_per_tap + nblk * a.bn);
+                    if (a.bk16) {       // one box = `groups` 16-channel groups of this tap (out-of-range groups are zero-filled)
+                        tma_load_5d(sa, &mapA, full(s), 0, w0 + a.dw[tap], h0 + a.dh[tap], cc * a.groups, img);
+                        tma_load_3d(sa + a_bytes, &mapB, full(s), 0, a.tb[tap] * a.b_rows_per_tap + nblk * a.bn, cc * a.groups);
+                    } else {
+                        tma_load_5d(sa, &mapA, full(s), cc * 64 + a.dc[tap], w0 + a.dw[tap], a.dp[tap], h0 + a.dh[tap], img);
+                        tma_load_2d(sa + A_TILE_BYTES, &mapB, full(s), cc * 64, a.tb[tap] * a.b_rows_per_tap + nblk * a.bn);
+                    }
                     if (++s == S) { s = 0; ph ^= 1u; }
                 }
             }
@@ -228,12 +250,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     mbar_wait(full(s), ph);
                     tc_fence_after();
                     const uint32_t sa = smem0 + s * stage_bytes;
-                    const uint64_t adesc = make_smem_desc(sa, 16, 1024);
-                    const uint64_t bdesc = make_smem_desc(sa + A_TILE_BYTES, 16, 1024);
+                    if (a.bk16) {       // one K = 16 MMA per 16-channel group
+                        const int cc = ks % a.cchunks;
+                        const int ng = min(a.groups, a.cin16 - cc * a.groups);
+                        for (int gq = 0; gq < ng; ++gq)
+                            umma_bf16(d_tmem, make_smem_desc32(sa + (uint32_t)gq * 4096u),
+                                      make_smem_desc32(sa + a_bytes + (uint32_t)gq * (uint32_t)a.bn * 32u), a.idesc,
+                                      (uint32_t)((ks | gq) != 0));
+                    } else {
+                        const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+                        const uint64_t bdesc = make_smem_desc(sa + A_TILE_BYTES, 16, 1024);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)     // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle row
-                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), a.idesc,
-                                  (uint32_t)((ks | k) != 0));
+                        for (int k = 0; k < 4; ++k)     // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle row
+                            umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), a.idesc,
+                                      (uint32_t)((ks | k) != 0));
+                    }
                     umma_commit(empty(s));
                     if (++s == S) { s = 0; ph ^= 1u; }
                 }
@@ -260,9 +291,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int c0 = 0; c0 < a.bn; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
+                const int cols = min(32, a.bn - c0);          // 16 when the N tile is not a multiple of 32
                 if (bias) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(bias + nblk * a.bn + c0 + j));
+                    for (int j = 0; j < 32; ++j)
+                        if (j < cols) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(bias + nblk * a.bn + c0 + j));
                 }
                 if (valid) {
                     uint32_t pk[16];
@@ -270,7 +303,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
                     uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) d4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    for (int j = 0; j < 4; ++j)
+                        if (j * 8 < cols) d4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
                 }
                 if (a.stats) {      // fused instance-norm statistics: per-channel sum and sum of squares of this tile
                     float s1[32], s2[32];
@@ -280,7 +314,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     stat_sm[(q * 2 + 0) * 32 + lane] = cs;
                     stat_sm[(q * 2 + 1) * 32 + lane] = cq;
                     asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (q == 0) {
+                    if (q == 0 && lane < cols) {
                         float* sp = a.stats + ((size_t)img * a.Cout + (size_t)nblk * a.bn + c0 + lane) * 2;
                         atomicAdd(sp, stat_sm[0 * 32 + lane] + stat_sm[2 * 32 + lane] + stat_sm[4 * 32 + lane] + stat_sm[6 * 32 + lane]);
                         atomicAdd(sp + 1, stat_sm[1 * 32 + lane] + stat_sm[3 * 32 + lane] + stat_sm[5 * 32 + lane] + stat_sm[7 * 32 + lane]);
@@ -713,6 +747,41 @@ int tc_make_map_act_grouped(CUtensorMap* map, const void* base, int C, int W, in
     return CG_OK;
 }
 
+int tc_make_map_act16(CUtensorMap* map, const void* base, int C, int W, int H, int N, int box_w, int box_h, int groups) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { cg_set_error("cuTensorMapEncodeTiled is not available from the driver"); return CG_ERR_CUDA; }
+    cuuint64_t dims[5] = {16, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(C / 16), (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, 32, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[5] = {16, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)groups, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        cg_set_error("cuTensorMapEncodeTiled(act16 C=%d W=%d H=%d N=%d box %dx%d x%d) failed: %d", C, W, H, N, box_w, box_h,
+                     groups, (int)r);
+        return CG_ERR_CUDA;
+    }
+    return CG_OK;
+}
+
+int tc_make_map_w16(CUtensorMap* map, const void* base, int cols, int rows, int box_rows, int groups) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { cg_set_error("cuTensorMapEncodeTiled is not available from the driver"); return CG_ERR_CUDA; }
+    cuuint64_t dims[3] = {16, (cuuint64_t)rows, (cuuint64_t)(cols / 16)};
+    cuuint64_t strides[2] = {(cuuint64_t)cols * 2, 32};
+    cuuint32_t box[3] = {16, (cuuint32_t)box_rows, (cuuint32_t)groups};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        cg_set_error("cuTensorMapEncodeTiled(w16 cols=%d rows=%d box %d x%d) failed: %d", cols, rows, box_rows, groups, (int)r);
+        return CG_ERR_CUDA;
+    }
+    return CG_OK;
+}
+
 int tc_make_map_2d(CUtensorMap* map, const void* base, int cols, int rows, int box_rows) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { cg_set_error("cuTensorMapEncodeTiled is not available from the driver"); return CG_ERR_CUDA; }
@@ -753,7 +822,7 @@ int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, const CUten
     // measured on B200 (profiles/r01_tc_kernels.md): the pair kernel lowers L2 traffic (lts 49 % -> 37 %) but not the
     // duration (119 us vs 117 us at the C3 trunk shape), so the 1-CTA kernel stays the default
     if (g_use_2cta < 0) { const char* e = getenv("CG_ENABLE_2CTA"); g_use_2cta = (e && e[0] == '1') ? 1 : 0; }
-    if (g_use_2cta && mapB2 && !a.stats && a.bn >= 32 && ((a.nb * a.tiles_per_img) % 2 == 0)) {
+    if (g_use_2cta && mapB2 && !a.stats && !a.bk16 && a.bn >= 32 && ((a.nb * a.tiles_per_img) % 2 == 0)) {
         const int stage = A_TILE_BYTES + (a.bn / 2) * 128;
         int s2 = (227 * 1024 - 2048) / stage;
         a.stages = s2 > 8 ? 8 : s2;
@@ -773,9 +842,13 @@ int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, const CUten
         CG_LAUNCH_CHECK();
         return CG_OK;
     }
-    a.stages = tc_conv_stages(a.bn);
+    const int stage_b = a.bk16 ? a.groups * (4096 + a.bn * 32) : (A_TILE_BYTES + a.bn * 128);
+    {
+        int sN = (227 * 1024 - 3072) / stage_b;
+        a.stages = sN > 8 ? 8 : sN;
+    }
     a.idesc = make_idesc(128, a.bn, 0, 0);
-    const size_t smem = (size_t)a.stages * (A_TILE_BYTES + a.bn * 128) + 1024 + 256 + 1024;
+    const size_t smem = (size_t)a.stages * stage_b + 1024 + 256 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

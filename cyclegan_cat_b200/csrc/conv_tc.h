@@ -13,6 +13,7 @@ struct TcConvArgs {
     int b_rows_per_tap;                         // rows of the packed weight matrix per tap
     int stages;
     uint32_t idesc;
+    int bk16, groups, cin16;                    // 16-channel K groups (SWIZZLE_32B): `groups` per K step, cin16 = Cin/16 in total
     float* stats;                               // nullable: [N][Cout][2] running (sum, sum of squares) of the outputs
     // per K-loop tap: TMA coordinate offsets into the 5-D activation view (c, w, p, h, n) and the weight row block
     short dc[49], dw[49], dp[49], dh[49], tb[49];
@@ -37,6 +38,11 @@ int tc_make_map_act(CUtensorMap* map, const void* base, int C, int W, int H, int
 // [box_h*box_w][64] tiles -- the MN-major operand layout of wgrad_tc_kernel -- with a single TMA instruction
 int tc_make_map_act_grouped(CUtensorMap* map, const void* base, int C, int W, int H, int N, int box_w, int box_h, int groups);
 int tc_make_map_2d(CUtensorMap* map, const void* base, int cols, int rows, int box_rows);
+// 16-channel-group views (SWIZZLE_32B) for layers whose channel counts are multiples of 16 but not of 64 (the U-Nets):
+//   activation (c%16, w, h, c/16, n), box {16, box_w, box_h, groups, 1}  ->  smem [group][box_h*box_w][16]
+//   weights    (k%16, row, k/16),     box {16, box_rows, groups}         ->  smem [group][box_rows][16]
+int tc_make_map_act16(CUtensorMap* map, const void* base, int C, int W, int H, int N, int box_w, int box_h, int groups);
+int tc_make_map_w16(CUtensorMap* map, const void* base, int cols, int rows, int box_rows, int groups);
 int tc_pack_weights(const float* w, bf16* wf, bf16* wd, int taps, int Cin, int Cout, cudaStream_t st);
 // mapB2 (nullable): the same weight matrix with a box of bn/2 rows, for the 2-CTA kernel
 int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, const CUtensorMap* mapB2, bf16* out, const float* bias,

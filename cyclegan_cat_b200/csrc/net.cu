@@ -123,7 +123,9 @@ int net_plan(const cg_net_s* net, int N, int H, int W, bool bwd, CallCtx* ctx) {
         } else if (kind == TC_CONVT_S2) {      // fwd classes on (hi,wi) = half the output grid; its dgrad tiles on (hi,wi)
             ok = boxable(wi, hi, 128) && boxable(wi, hi, 64);
         }
-        else if (kind == TC_STEM) {
+        else if (kind == TC_S1_16) {
+            ok = boxable(wo, ho, 128) && d.cin <= 256;      // dgrad N tile = Cin
+        } else if (kind == TC_STEM) {
             ok = boxable(wo, ho, 128) && boxable(wo, ho, 64);
         } else if (kind == TC_HEAD) {
             ok = ((size_t)ho * wi) % 64 == 0 && (size_t)hi * wi < (1u << 30);
@@ -343,6 +345,38 @@ int net_bind(CallCtx* c) {
             if (!c->bwd) continue;
             CG_TRY(make_class_launches(t.dgrad, dy, ho, wo, d.cout, c->N, wd, d.cin, k, pt, pl, hi, wi));
             CG_TRY(make_wgrad(t, x, hi, wi, d.cin, dy, ho, wo, d.cout, c->N, k, 2, pt, pl, 0));
+        } else if (L.tc == TC_S1_16) {
+            // stride-1 'same' conv with 16-multiple channels: forward and data gradient are both box-mode convs whose
+            // zero padding is TMA out-of-bounds fill; K runs over 16-channel groups (SWIZZLE_32B tiles)
+            int pt = 0, pl = 0;
+            if (d.same) { same_pad(hi, k, 1, &pt); same_pad(wi, k, 1, &pl); }
+            auto make16 = [&](TcConvLaunch& Ln, const void* in, int cin_k, const bf16* wmat, int n_out, bool flip) -> int {
+                TcConvArgs& a = Ln.a;
+                memset(&a, 0, sizeof(a));
+                set_tiles(a, wo, ho);
+                a.n_taps = k * k;
+                a.bk16 = 1; a.cin16 = cin_k / 16; a.groups = a.cin16 < 8 ? a.cin16 : 8;
+                a.cchunks = (a.cin16 + a.groups - 1) / a.groups;
+                a.bn = n_out; a.n_blocks_n = 1;
+                a.nb = c->N; a.out_H = ho; a.out_W = wo; a.Cout = n_out; a.out_sy = a.out_sx = 1;
+                a.b_rows_per_tap = n_out;
+                for (int kh = 0; kh < k; ++kh)
+                    for (int kw = 0; kw < k; ++kw) {
+                        const int tp = kh * k + kw;
+                        a.tb[tp] = (short)tp;
+                        a.dw[tp] = (short)(flip ? pl - kw : kw - pl);
+                        a.dh[tp] = (short)(flip ? pt - kh : kh - pt);
+                    }
+                CG_TRY(tc_make_map_act16(&Ln.mapA, in, cin_k, wo, ho, c->N, a.Wb, a.Hb, a.groups));
+                CG_TRY(tc_make_map_w16(&Ln.mapB, wmat, cin_k, k * k * n_out, n_out, a.groups));
+                Ln.mapB2 = Ln.mapB;
+                return CG_OK;
+            };
+            t.fwd.assign(1, TcConvLaunch());
+            CG_TRY(make16(t.fwd[0], x, d.cin, wf, d.cout, false));
+            if (!c->bwd) continue;
+            t.dgrad.assign(1, TcConvLaunch());
+            CG_TRY(make16(t.dgrad[0], dy, d.cout, wd, d.cin, true));
         } else if (L.tc == TC_STEM) {
             if (!c->tcs) { cg_set_error("net_bind: no scratch for the unfolded stem input"); return CG_ERR_STATE; }
             const void* U = c->tcs;                         // [N][hi][wo][128]: U[r][ow][kw*cin+ci] = x[r][ow+kw][ci]
@@ -471,7 +505,7 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
         const T* x = (const T*)c->act(tin);
         // a tensor-core conv that feeds only an instance norm accumulates that norm's statistics in its epilogue
         float* fused_stats = nullptr;
-        if (c->tc[i].on && L.bias_grad_zero && L.tc != TC_HEAD && i + 1 < net->layers.size()) {
+        if (c->tc[i].on && L.feeds_in && L.tc != TC_HEAD && i + 1 < net->layers.size()) {
             fused_stats = (float*)(c->base + c->stat_off[i + 1]);
             CG_CUDA(cudaMemsetAsync(fused_stats, 0, sizeof(float) * 2 * (size_t)N * d.cout, st));
             stats_done[i + 1] = 1;
@@ -595,6 +629,25 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
         switch (d.op) {
             case CG_OP_CONV: {
                 ConvGeom g = conv_geom(d, nb, h, w, oh, ow);
+                if (c->tc[i].on && L.tc == TC_S1_16) {
+                    if (grads) {
+                        CG_TRY(k_conv_wgrad<T>(A(tin), dy, grads + L.w_off, g, st));
+                        if (L.b_off >= 0 && !L.bias_grad_zero)
+                            CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
+                    }
+                    if (want_dx) {
+                        if (acc) {
+                            CG_TRY(k_conv_dgrad<T>(dy, params + L.w_off, nullptr, dx, g, acc, st));
+                        } else {
+                            const TcConvLaunch& tl = c->tc[i].dgrad[0];
+                            TcConvArgs a = tl.a;
+                            a.nb = nb;
+                            CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, (bf16*)dx, nullptr, a,
+                                                  2.0 * nb * oh * ow * (double)d.cout * d.k * d.k * d.cin, st));
+                        }
+                    }
+                    break;
+                }
                 if (c->tc[i].on && !acc && (L.tc == TC_STEM || L.tc == TC_HEAD)) {
                     const double fl = 2.0 * nb * oh * ow * (double)d.cout * d.k * d.k * d.cin;
                     float* tmp = (float*)(c->tcs + c->tc[i].sc_tmp);

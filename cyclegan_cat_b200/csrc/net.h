@@ -19,7 +19,7 @@ struct TcLayer {
     int wg_x_is_dy = 0;                 // Conv2DTranspose: the "X" operand of the weight gradient is dY
     size_t sc_tmp = 0;                  // TC_STEM / TC_HEAD: offset of the fp32 weight-gradient staging buffer in the scratch
 };
-enum { TC_NONE = 0, TC_S1_VALID = 1, TC_CONV_S2 = 2, TC_CONVT_S2 = 3, TC_STEM = 4, TC_HEAD = 5 };
+enum { TC_NONE = 0, TC_S1_VALID = 1, TC_CONV_S2 = 2, TC_CONVT_S2 = 3, TC_STEM = 4, TC_HEAD = 5, TC_S1_16 = 6 };
 
 struct LayerInfo {
     cg_layer_desc d;
@@ -28,6 +28,7 @@ struct LayerInfo {
     bool skipped = false;   // ACT folded into the preceding INORM
     int fused_act = CG_ACT_NONE;
     float fused_slope = 0.f;
+    bool feeds_in = false;         // the conv output feeds ONLY an instance norm (statistics fused into the conv epilogue)
     bool bias_grad_zero = false;   // the conv output feeds ONLY an instance norm: d(loss)/d(bias) == 0 exactly
     int tc = 0;             // TC_* kind: which convs run on the tcgen05 kernels in bf16 mode
     long long pk_f = 0, pk_d = 0;   // byte offsets of the packed bf16 weights ([tap][Cout][Cin] / [tap][Cin][Cout])

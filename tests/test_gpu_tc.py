@@ -61,6 +61,17 @@ def _stem_head_net(f):
     return g
 
 
+def _double_conv_net(cin, cout, k):
+    """unet.py:20-36 double_conv: 2 x (Conv k s1 'same' no bias -> affine IN -> ReLU); channel counts are multiples of 16."""
+    g = ir.Graph(channels=[cin])
+    x = g.input
+    for _ in range(2):
+        x = g.conv(x, cout, k, stride=1, padding='same', use_bias=False)
+        x = g.instance_norm(x, affine=True)
+        x = g.act(x, ir.ACT_RELU)
+    return g
+
+
 def _make(graph, tc, seed=0):
     os.environ["CG_DISABLE_TC"] = "0" if tc else "1"
     try:
@@ -107,6 +118,30 @@ def test_tc_strided_and_transposed_convs_match_cuda_core(cin, cout, k, h, w, n):
     yb, dxb, gb = _net_grads(b, x, dy)
     assert C.rel_l2(ya, yb) <= 4e-3, C.rel_l2(ya, yb)
     assert C.rel_l2(dxa, dxb) <= 2e-2, C.rel_l2(dxa, dxb)
+    scale = max(np.linalg.norm(v) for v in gb)
+    for i, (u, v) in enumerate(zip(ga, gb)):
+        e = np.linalg.norm(u - v) / max(np.linalg.norm(v), 0.02 * scale)
+        assert e <= 2e-2, (i, u.shape, e)
+
+
+@pytest.mark.parametrize("cin,cout,k,h,w,n", [(16, 16, 4, 64, 64, 2), (80, 32, 4, 32, 128, 1), (160, 64, 4, 32, 32, 2),
+                                              (192, 128, 4, 16, 16, 3), (16, 32, 5, 128, 128, 1), (32, 64, 3, 64, 64, 2),
+                                              (48, 32, 7, 16, 64, 1)])
+def test_tc_unet_double_conv_matches_cuda_core(cin, cout, k, h, w, n):
+    """16-channel-group (SWIZZLE_32B) mode of conv_tc_kernel: forward and data gradient of the U-Net convs, including the
+    asymmetric 'same' padding of even kernels (k4 s1 -> (1,2)) that comes from TMA out-of-bounds fill."""
+    g = _double_conv_net(cin, cout, k)
+    a, b = _make(g, True), _make(g, False)
+    rng = np.random.RandomState(6)
+    ws = [_bf16_round(v + (rng.normal(0, 0.05, v.shape) if v.ndim == 1 else 0)) for v in a.get_weights()]
+    a.set_weights(ws)
+    b.set_weights(ws)
+    x = _bf16_round(rng.uniform(-1, 1, (n, h, w, cin)))
+    dy = _bf16_round(rng.normal(0, 1, (n, h, w, cout)))
+    ya, dxa, ga = _net_grads(a, x, dy)
+    yb, dxb, gb = _net_grads(b, x, dy)
+    assert C.rel_l2(ya, yb) <= 4e-3, C.rel_l2(ya, yb)
+    assert C.rel_l2(dxa, dxb) <= 5e-2, C.rel_l2(dxa, dxb)
     scale = max(np.linalg.norm(v) for v in gb)
     for i, (u, v) in enumerate(zip(ga, gb)):
         e = np.linalg.norm(u - v) / max(np.linalg.norm(v), 0.02 * scale)
