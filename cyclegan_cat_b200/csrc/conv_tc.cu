@@ -657,6 +657,126 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------
+// weight gradient for 16-multiple channel counts (U-Net layers).  The GEMM M dimension is the flattened (tap, ci) index
+// of TF's HWIO kernel, cut into blocks of 128 rows = 8 slots of 16 channels; every slot is its own TMA box of the
+// activation (16 channels x 64 pixels, shifted by the slot's tap; zero padding = out-of-bounds fill), so one block may
+// stack several taps.  B = the dY chunk (all Cout channels, one grouped box).  MN-major SWIZZLE_32B operands,
+// K = 64 pixels per stage, split-K over pixels, fp32 reductions straight into dW[(tap*Cin+ci)][co].
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t make_smem_desc32_mn(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;     // next 16-channel group
+    d |= (uint64_t)(256 >> 4) << 32;                      // SBO: next 8-pixel group
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;                               // SWIZZLE_32B
+    return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad16_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDY,
+                  float* __restrict__ dw, const TcWgrad16Args a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ygroups = a.Cout / 16;
+    const uint32_t stage_bytes = (uint32_t)(8 + ygroups) * 2048u;
+    const int S = a.stages;
+    const uint32_t bar0 = smem0 + S * stage_bytes;
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (S + s); };
+    const uint32_t tfull = bar0 + 8u * (2 * S);
+    const uint32_t tmem_slot = bar0 + 8u * (2 * S + 1);
+    volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapX);
+        tma_prefetch_desc(&mapDY);
+        for (int s = 0; s < S; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int split = blockIdx.x % a.splits, mb = blockIdx.x / a.splits;
+    const int total_chunks = a.nb * a.chunks_per_img;
+    const int per = (total_chunks + a.splits - 1) / a.splits;
+    const int q_begin = split * per;
+    const int q_end = min(total_chunks, q_begin + per);
+    const int nq = q_end - q_begin;
+    const int rows_total = a.n_taps * a.Cin;
+    const int nslots = min(8, (rows_total - mb * 128 + 15) / 16);      // live 16-row slots of this block
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int q = q_begin; q < q_end; ++q) {
+                const int img = q / a.chunks_per_img, r = q % a.chunks_per_img;
+                const int w0 = (r % a.chunks_w) * a.Wk, h0 = (r / a.chunks_w) * a.Hk;
+                mbar_wait(empty(s), ph ^ 1u);
+                mbar_expect_tx(full(s), (uint32_t)(nslots + ygroups) * 2048u);
+                const uint32_t sa = smem0 + s * stage_bytes;
+                for (int j = 0; j < nslots; ++j) {
+                    const int row0 = (mb * 8 + j) * 16;
+                    const int tap = row0 / a.Cin, cg = (row0 - tap * a.Cin) / 16;
+                    tma_load_5d(sa + (uint32_t)j * 2048u, &mapX, full(s), 0, w0 + a.dw[tap], h0 + a.dh[tap], cg, a.n0 + img);
+                }
+                tma_load_5d(sa + 8u * 2048u, &mapDY, full(s), 0, w0, h0, 0, img);
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && nq > 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int i = 0; i < nq; ++i) {
+                mbar_wait(full(s), ph);
+                tc_fence_after();
+                const uint32_t sa = smem0 + s * stage_bytes;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)       // K = 16 pixels = 512 bytes inside each 2 KB group
+                    umma_bf16(tmem_base, make_smem_desc32_mn(sa + (uint32_t)k * 512u, 2048),
+                              make_smem_desc32_mn(sa + 8u * 2048u + (uint32_t)k * 512u, 2048), a.idesc, (uint32_t)((i | k) != 0));
+                umma_commit(empty(s));
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
+            umma_commit(tfull);
+        }
+    } else if (nq > 0) {
+        const int q = warp & 3;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        const int row = mb * 128 + q * 32 + lane;
+        const bool live = row < rows_total && (q * 32 + lane) < nslots * 16;
+        float* dst = dw + (size_t)row * a.Cout;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int c0 = 0; c0 < a.Cout; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + (uint32_t)c0, v);
+            const int cols = min(32, a.Cout - c0);
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (j * 4 < cols)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + 4 * j),
+                                     "f"(__uint_as_float(v[4 * j])), "f"(__uint_as_float(v[4 * j + 1])),
+                                     "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3]))
+                                     : "memory");
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // weight packing: float32 HWIO -> bf16 [tap][Cout][Cin] (forward B operand) and bf16 [tap][Cin][Cout]
 // (data-gradient B operand; same order as HWIO)
 // ------------------------------------------------------------------------------------------
@@ -884,6 +1004,31 @@ int tc_wgrad_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* dw
     int pi = prof_begin(st);
     wgrad_tc_kernel<<<units * splits, TC_THREADS, smem, st>>>(*mapX, *mapDY, dw, a);
     prof_end(pi, st, flops, prof_key(3, a.n_taps, a.a_blocks * a.b_blocks, a.bn, a.chunks_per_img, a.nb));
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+int tc_wgrad16_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* dw, TcWgrad16Args a, double flops,
+                      cudaStream_t st) {
+    const int stage = (8 + a.Cout / 16) * 2048;
+    int s = (227 * 1024 - 2048) / stage;
+    a.stages = s > 8 ? 8 : s;
+    a.idesc = make_idesc(128, a.Cout, 1, 1);
+    a.m_blocks = (a.n_taps * a.Cin + 127) / 128;
+    const int total_chunks = a.nb * a.chunks_per_img;
+    int splits = (2 * num_sms()) / a.m_blocks;              // ~2 CTAs per SM in total: the units are short
+    if (splits < 1) splits = 1;
+    if (splits > total_chunks) splits = total_chunks;
+    a.splits = splits;
+    const size_t smem = (size_t)a.stages * stage + 1024 + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CG_CUDA(cudaFuncSetAttribute(wgrad16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    int pi = prof_begin(st);
+    wgrad16_tc_kernel<<<a.m_blocks * splits, TC_THREADS, smem, st>>>(*mapX, *mapDY, dw, a);
+    prof_end(pi, st, flops, prof_key(4, a.n_taps, a.m_blocks, a.Cout, a.chunks_per_img, a.nb));
     CG_LAUNCH_CHECK();
     return CG_OK;
 }

@@ -33,6 +33,16 @@ struct TcWgradArgs {
 
 // 5-D activation view (c, w, p, h, n).  parity = 0: dense NHWC tensor, p is a dummy dim of size 1.
 // parity = 1: stride-2 view of an NHWC tensor with even H, W: c' = pw*C + c (size 2C), w' = w/2, p = h%2, h' = h/2.
+// weight gradient of stride-1 convs whose channel counts are multiples of 16 only (tap-stacked M, wgrad16_tc_kernel)
+struct TcWgrad16Args {
+    int n_taps, Cin, Cout, m_blocks, splits, stages;
+    int n0, nb;                                 // X images start at n0 (dY is sub-batch relative)
+    int chunks_per_img, chunks_w, Wk, Hk;
+    uint32_t idesc;
+    short dw[49], dh[49];
+};
+int tc_wgrad16_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* dw, TcWgrad16Args a, double flops,
+                      cudaStream_t st);
 int tc_make_map_act(CUtensorMap* map, const void* base, int C, int W, int H, int N, int parity, int box_w, int box_h);
 // channel-grouped dense view (c%64, w, h, c/64, n): one box {64, box_w, groups, box_h, 1} lands as `groups` consecutive
 // [box_h*box_w][64] tiles -- the MN-major operand layout of wgrad_tc_kernel -- with a single TMA instruction

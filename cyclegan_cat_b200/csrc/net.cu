@@ -377,6 +377,19 @@ int net_bind(CallCtx* c) {
             if (!c->bwd) continue;
             t.dgrad.assign(1, TcConvLaunch());
             CG_TRY(make16(t.dgrad[0], dy, d.cout, wd, d.cin, true));
+            const char* no16 = getenv("CG_DISABLE_WGRAD16");      // test hook: CUDA-core weight gradient for these layers
+            if (!(no16 && no16[0] == '1') && ((wo % 64 == 0) || (64 % wo == 0 && ho % (64 / wo) == 0))) {      // weight gradient with tap-stacked M (wgrad16_tc_kernel)
+                TcWgrad16Args& a = t.wa16;
+                memset(&a, 0, sizeof(a));
+                a.n_taps = k * k; a.Cin = d.cin; a.Cout = d.cout;
+                a.Wk = wo % 64 == 0 ? 64 : wo; a.Hk = 64 / a.Wk;
+                a.chunks_w = wo / a.Wk; a.chunks_per_img = a.chunks_w * (ho / a.Hk);
+                for (int kh = 0; kh < k; ++kh)
+                    for (int kw = 0; kw < k; ++kw) { a.dw[kh * k + kw] = (short)(kw - pl); a.dh[kh * k + kw] = (short)(kh - pt); }
+                CG_TRY(tc_make_map_act16(&t.mapXw, x, d.cin, wi, hi, c->N, a.Wk, a.Hk, 1));
+                CG_TRY(tc_make_map_act16(&t.mapDYw, dy, d.cout, wo, ho, c->N, a.Wk, a.Hk, d.cout / 16));
+                t.wg16 = true;
+            }
         } else if (L.tc == TC_STEM) {
             if (!c->tcs) { cg_set_error("net_bind: no scratch for the unfolded stem input"); return CG_ERR_STATE; }
             const void* U = c->tcs;                         // [N][hi][wo][128]: U[r][ow][kw*cin+ci] = x[r][ow+kw][ci]
@@ -631,7 +644,14 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                 ConvGeom g = conv_geom(d, nb, h, w, oh, ow);
                 if (c->tc[i].on && L.tc == TC_S1_16) {
                     if (grads) {
-                        CG_TRY(k_conv_wgrad<T>(A(tin), dy, grads + L.w_off, g, st));
+                        if (c->tc[i].wg16) {
+                            TcWgrad16Args a = c->tc[i].wa16;
+                            a.n0 = n0; a.nb = nb;
+                            CG_TRY(tc_wgrad16_launch(&c->tc[i].mapXw, &c->tc[i].mapDYw, grads + L.w_off, a,
+                                                     2.0 * nb * oh * ow * (double)d.cout * d.k * d.k * d.cin, st));
+                        } else {
+                            CG_TRY(k_conv_wgrad<T>(A(tin), dy, grads + L.w_off, g, st));
+                        }
                         if (L.b_off >= 0 && !L.bias_grad_zero)
                             CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
                     }

@@ -16,6 +16,8 @@ struct TcLayer {
     std::vector<TcConvLaunch> dgrad;    // 1 launch (stride 1: flat mode; Conv2DTranspose: a stride-2 conv of dY) or 4 classes
     CUtensorMap mapXw, mapDYw;
     TcWgradArgs wa;
+    TcWgrad16Args wa16;
+    bool wg16 = false;
     int wg_x_is_dy = 0;                 // Conv2DTranspose: the "X" operand of the weight gradient is dY
     size_t sc_tmp = 0;                  // TC_STEM / TC_HEAD: offset of the fp32 weight-gradient staging buffer in the scratch
 };

@@ -49,6 +49,12 @@ extern "C" int cg_prof_enable(int enable) {
     on = enable != 0;
     used = 0;
     flops = 0.0;
+    while ((long long)pool.size() < (long long)enable) {      // enable > 1: pre-create that many event pairs (keeps creation out of a timed loop)
+        Pair p;
+        CG_CUDA(cudaEventCreate(&p.a));
+        CG_CUDA(cudaEventCreate(&p.b));
+        pool.push_back(p);
+    }
     return CG_OK;
 }
 

@@ -162,7 +162,8 @@ int cg_comm_unique_id(char id_out[128]);
 int cg_trainer_comm_init(cg_trainer_t tr, const char id[128], int rank, int world);
 
 /* ---- instrumentation for bench.py: CUDA-event timing of one kernel family */
-int cg_prof_enable(int enable);                 /* brackets every tensor-core conv launch with events */
+int cg_prof_enable(int enable);                 /* brackets every tensor-core conv launch with events; 0 = off, 1 = on,
+                                                   n > 1 = on with n event pairs created up front */
 int cg_prof_read(double* total_ms, int64_t* launches, double* total_flops);  /* syncs, resets */
 int cg_launch_count(int64_t* launches, int reset);  /* kernels launched by this library */
 

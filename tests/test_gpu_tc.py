@@ -145,7 +145,34 @@ def test_tc_unet_double_conv_matches_cuda_core(cin, cout, k, h, w, n):
     scale = max(np.linalg.norm(v) for v in gb)
     for i, (u, v) in enumerate(zip(ga, gb)):
         e = np.linalg.norm(u - v) / max(np.linalg.norm(v), 0.02 * scale)
-        assert e <= 2e-2, (i, u.shape, e)
+        # a fraction p of ReLU masks flips between the arms (|y| below the bf16 rounding of y): relative error ~ sqrt(p),
+        # the same bound as dx above; test_tc_wgrad16_matches_cuda_core is the tight check of the weight-gradient kernel
+        assert e <= 5e-2, (i, u.shape, e)
+
+
+@pytest.mark.parametrize("cin,cout,k,h,w,n", [(16, 16, 4, 64, 64, 2), (32, 16, 4, 128, 128, 1), (80, 32, 4, 32, 128, 1),
+                                              (192, 128, 4, 16, 16, 3), (16, 32, 5, 16, 64, 2), (48, 32, 7, 16, 64, 1),
+                                              (128, 64, 3, 32, 32, 2), (16, 16, 4, 256, 256, 1)])
+def test_tc_wgrad16_matches_cuda_core(cin, cout, k, h, w, n):
+    """wgrad16_tc_kernel (tap-stacked M, 16-channel SWIZZLE_32B boxes) in isolation: one conv -> affine IN -> ReLU, so both arms
+    see the same dY up to the bf16 rounding of the conv output."""
+    g = ir.Graph(channels=[cin])
+    x_ = g.conv(g.input, cout, k, stride=1, padding='same', use_bias=False)
+    x_ = g.instance_norm(x_, affine=True)
+    x_ = g.act(x_, ir.ACT_LEAKY, 0.2)
+    a, b = _make(g, True), _make(g, False)
+    rng = np.random.RandomState(8)
+    ws = [_bf16_round(v + (rng.normal(0, 0.05, v.shape) if v.ndim == 1 else 0)) for v in a.get_weights()]
+    a.set_weights(ws)
+    b.set_weights(ws)
+    x = _bf16_round(rng.uniform(-1, 1, (n, h, w, cin)))
+    dy = _bf16_round(rng.normal(0, 1, (n, h, w, cout)))
+    ya, dxa, ga = _net_grads(a, x, dy)
+    yb, dxb, gb = _net_grads(b, x, dy)
+    assert C.rel_l2(ya, yb) <= 4e-3, C.rel_l2(ya, yb)
+    assert C.rel_l2(dxa, dxb) <= 1e-2, C.rel_l2(dxa, dxb)
+    assert ga[0].shape == (k, k, cin, cout)
+    assert C.rel_l2(ga[0], gb[0]) <= 1e-2, C.rel_l2(ga[0], gb[0])
 
 
 @pytest.mark.parametrize("f,h,w,n", [(64, 64, 64, 2), (64, 32, 128, 3), (128, 256, 256, 1)])
