@@ -14,39 +14,12 @@
 #include <stdlib.h>
 
 #include "conv_tc.h"
+#include "ptx_async.h"
 #include "prof.h"
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// Spin on a phase parity.  A bounded spin + trap turns a protocol bug into an error instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
-    for (uint32_t spin = 0; !ok; ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (spin > (1u << 26)) __trap();
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
     asm volatile(
@@ -179,14 +152,17 @@ static constexpr int TMEM_COLS = 512;
 // ------------------------------------------------------------------------------------------
 // forward / data-gradient kernel
 // ------------------------------------------------------------------------------------------
+// BK16 (the 16-channel-group SWIZZLE_32B mode of the U-Net layers) is a template parameter: as a run-time branch it cost
+// the 64-channel instance 19 % (1216 -> 987 TFLOP/s at the C3 trunk shape, same box, back to back).
+template <bool BK16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                bf16* __restrict__ out, const float* __restrict__ bias, const TcConvArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t a_bytes = a.bk16 ? (uint32_t)a.groups * 4096u : (uint32_t)A_TILE_BYTES;
-    const uint32_t stage_bytes = a.bk16 ? (uint32_t)a.groups * (4096u + (uint32_t)a.bn * 32u) : A_TILE_BYTES + (uint32_t)a.bn * 128u;
+    const uint32_t a_bytes = BK16 ? (uint32_t)a.groups * 4096u : (uint32_t)A_TILE_BYTES;
+    const uint32_t stage_bytes = BK16 ? (uint32_t)a.groups * (4096u + (uint32_t)a.bn * 32u) : A_TILE_BYTES + (uint32_t)a.bn * 128u;
     const int S = a.stages;
     const uint32_t bar0 = smem0 + S * stage_bytes;          // full[S], empty[S], tfull[2], tempty[2], tmem ptr
     auto full = [&](int s) { return bar0 + 8u * s; };
@@ -225,7 +201,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     mbar_wait(empty(s), ph ^ 1u);
                     mbar_expect_tx(full(s), stage_bytes);
                     const uint32_t sa = smem0 + s * stage_bytes;
-                    if (a.bk16) {       // one box = `groups` 16-channel groups of this tap (out-of-range groups are zero-filled)
+                    if constexpr (BK16) {       // one box = `groups` 16-channel groups of this tap (out-of-range groups are zero-filled)
                         tma_load_5d(sa, &mapA, full(s), 0, w0 + a.dw[tap], h0 + a.dh[tap], cc * a.groups, img);
                         tma_load_3d(sa + a_bytes, &mapB, full(s), 0, a.tb[tap] * a.b_rows_per_tap + nblk * a.bn, cc * a.groups);
                     } else {
@@ -250,7 +226,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     mbar_wait(full(s), ph);
                     tc_fence_after();
                     const uint32_t sa = smem0 + s * stage_bytes;
-                    if (a.bk16) {       // one K = 16 MMA per 16-channel group
+                    if constexpr (BK16) {       // one K = 16 MMA per 16-channel group
                         const int cc = ks % a.cchunks;
                         const int ng = min(a.groups, a.cin16 - cc * a.groups);
                         for (int gq = 0; gq < ng; ++gq)
@@ -291,7 +267,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int c0 = 0; c0 < a.bn; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
-                const int cols = min(32, a.bn - c0);          // 16 when the N tile is not a multiple of 32
+                const int cols = BK16 ? min(32, a.bn - c0) : 32;          // 16 when the N tile is not a multiple of 32 (BK16 only)
                 if (bias) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
@@ -971,13 +947,15 @@ int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, const CUten
     const size_t smem = (size_t)a.stages * stage_b + 1024 + 256 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     const int total = a.nb * a.tiles_per_img * a.n_blocks_n;
     int grid = total < num_sms() ? total : num_sms();
     int pi = prof_begin(st);
-    conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(*mapA, *mapB, out, bias, a);
+    if (a.bk16) conv_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(*mapA, *mapB, out, bias, a);
+    else conv_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(*mapA, *mapB, out, bias, a);
     prof_end(pi, st, flops, prof_key(1, a.n_taps, a.cchunks, a.bn, a.tiles_per_img, a.nb));
     CG_LAUNCH_CHECK();
     return CG_OK;

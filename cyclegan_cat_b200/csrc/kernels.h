@@ -19,6 +19,16 @@ template <typename T> int k_in_stats(const T* x, float* stats, int N, int P, int
 int k_in_finalize(float* stats, int NC, int P, float eps, cudaStream_t st);
 template <typename T> int k_in_apply(const T* x, T* y, const float* stats, const float* gamma, const float* beta,
                                      int act, float slope, int N, int P, int C, cudaStream_t st);
+// bulk-copy pipelined variants (kernels_stream.cu); k_in_stream_ok says whether a (P, C) plane qualifies
+template <typename T> bool k_in_stream_ok(const void* p0, const void* p1, const void* p2, int P, int C);
+template <typename T> int k_in_apply_stream(const T* x, T* y, const float* stats, const float* gamma, const float* beta,
+                                            int act, float slope, int N, int P, int C, cudaStream_t st);
+template <typename T> int k_in_bwd_reduce_stream(const T* x, const T* dy, const float* stats, const float* gamma,
+                                                 const float* beta, float* sums, int act, float slope, int N, int P, int C,
+                                                 cudaStream_t st);
+template <typename T> int k_in_bwd_apply_stream(const T* x, const T* dy, T* dx, const float* stats, const float* sums,
+                                                const float* gamma, const float* beta, int act, float slope, int N, int P,
+                                                int C, int W, int halo, cudaStream_t st);
 template <typename T> int k_in_bwd(const T* x, const T* dy, T* dx, const float* stats, const float* gamma,
                                    const float* beta, float* dgamma, float* dbeta, float* scratch, int act,
                                    float slope, int N, int P, int C, int accumulate, cudaStream_t st,

@@ -280,6 +280,7 @@ template <typename T> int k_in_apply(const T* x, T* y, const float* stats, const
                                      int act, float slope, int N, int P, int C, cudaStream_t st) {
     constexpr int VW = VecWidth<T>::value;
     size_t PC = (size_t)P * C;
+    if (k_in_stream_ok<T>(x, y, nullptr, P, C)) return k_in_apply_stream<T>(x, y, stats, gamma, beta, act, slope, N, P, C, st);
     if (fast_cv_ok(C, VW)) {
         dim3 grid(fast_blocks(P, C, VW, N), N);
         in_apply_fast_kernel<T, VW><<<grid, 256, 0, st>>>(x, y, stats, gamma, beta, act, slope, P, C);
@@ -379,15 +380,22 @@ template <typename T> int k_in_bwd(const T* x, const T* dy, T* dx, const float* 
     CG_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * 2 * (size_t)N * C, st));
     // (a register-resident, 16-byte-vector variant of this reduction was measured slower -- 51 us vs 43 us per trunk
     // launch -- than the lanes-over-channels kernel with its 6 resident blocks per SM, so the simple kernel stays)
-    dim3 grid; int pchunk;
-    in_reduce_grid(N, P, C, grid, pchunk);
-    in_reduce_kernel<T, 1><<<grid, 256, 0, st>>>(x, dy, stats, gamma, beta, scratch, P, C, pchunk, act, slope);
-    CG_LAUNCH_CHECK();
+    const bool stream = k_in_stream_ok<T>(x, dy, dx, P, C);
+    if (stream) {
+        CG_TRY(k_in_bwd_reduce_stream<T>(x, dy, stats, gamma, beta, scratch, act, slope, N, P, C, st));
+    } else {
+        dim3 grid; int pchunk;
+        in_reduce_grid(N, P, C, grid, pchunk);
+        in_reduce_kernel<T, 1><<<grid, 256, 0, st>>>(x, dy, stats, gamma, beta, scratch, P, C, pchunk, act, slope);
+        CG_LAUNCH_CHECK();
+    }
     if (dgamma) {
         in_param_grad_kernel<<<cdiv(C, 128), 128, 0, st>>>(scratch, dgamma, dbeta, N, C);
         CG_LAUNCH_CHECK();
     }
-    if (dx && fast_cv_ok(C, VecWidth<T>::value) && (halo == 0 || (!accumulate && W > 0 && P % W == 0))) {
+    if (dx && stream && !accumulate && (halo == 0 || (W > 0 && P % W == 0))) {
+        CG_TRY(k_in_bwd_apply_stream<T>(x, dy, dx, stats, scratch, gamma, beta, act, slope, N, P, C, W, halo, st));
+    } else if (dx && fast_cv_ok(C, VecWidth<T>::value) && (halo == 0 || (!accumulate && W > 0 && P % W == 0))) {
         constexpr int VW = VecWidth<T>::value;
         const int Wd = halo > 0 ? W : P, Hd = halo > 0 ? P / W : 1;     // halo == 0: treat the plane as one row
         dim3 g2(fast_blocks((Hd + 2 * halo) * (Wd + 2 * halo), C, VW, N), N);

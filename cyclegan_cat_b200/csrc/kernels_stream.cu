@@ -1,0 +1,287 @@
+// Bulk-copy pipelined instance-norm kernels (forward apply, backward reduction, backward apply) for sm_100a.
+//
+// These three passes are pure HBM streaming (2-3 activation tensors per launch, tens to hundreds of MB) and the
+// register-resident versions in kernels_elem.cu are limited by the number of loads a thread can keep in flight
+// (in_bwd_apply_fast_kernel: 2 x 16 B per thread, ~32 KB per SM -> 2.4-3 TB/s).  Here the loads are issued by ONE
+// producer thread per CTA as 8 KB cp.async.bulk copies into a shared-memory ring (mbarrier complete_tx), so
+// 2 CTAs x 5-8 stages x 8-16 KB = 130-190 KB per SM is in flight independent of the consumers' registers; the 8 consumer
+// warps read a tile from shared memory, free the slot, do the per-channel arithmetic with constants held in registers
+// and store 16-byte vectors straight to global memory.
+//
+//   tile   = 8192 contiguous bytes of one image of one operand (= 512 16-byte channel vectors = 512/CV pixels)
+//   grid   = (G, N) with G*N ~ 2 CTAs per SM; CTA (g, n) walks tiles g, g+G, ... of image n
+//   block  = 288 threads: warps 0-7 consume, warp 8 lane 0 produces
+// Semantics are those of in_apply_fast_kernel / in_reduce_kernel<MODE 1> / in_bwd_apply_fast_kernel (kernels_elem.cu),
+// i.e. TFA InstanceNormalization forward and its gradient (reference: cyclegan/unet.py:28-33, resnet.py:26-34 use
+// tfa.layers.InstanceNormalization followed by ReLU / LeakyReLU).
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "common.h"
+#include "kernels.h"
+#include "ptx_async.h"
+
+namespace {
+constexpr int ST_TILE = 8192;
+constexpr int ST_CONSUMERS = 256;
+constexpr int ST_THREADS = ST_CONSUMERS + 32;
+
+template <typename T>
+struct StreamArgs {
+    const T* x;
+    const T* dy;
+    T* out;
+    const float* stats;
+    const float* sums_in;
+    float* sums_out;
+    const float* gamma;
+    const float* beta;
+    int act;
+    float slope;
+    int P, C, W, halo;
+    float invP;
+    int stages, tiles_per_img;
+};
+
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(ST_CONSUMERS) : "memory"); }
+
+// MODE 0: out = act(x*sc + sh)                     (forward apply; one operand)
+// MODE 1: sums_out += (sum g, sum g*xhat)          (backward reduction; x and dy)
+// MODE 2: out = k*g - c1 - xhat*c2                 (backward apply; x and dy; optional zero-bordered output)
+template <typename T, int VEC, int MODE, bool AFFINE>
+__global__ void __launch_bounds__(ST_THREADS, 2) in_stream_kernel(const StreamArgs<T> a) {
+    extern __shared__ __align__(128) uint8_t st_smem[];
+    constexpr int NOPS = MODE == 0 ? 1 : 2;
+    const int S = a.stages;
+    const uint32_t tiles_u32 = smem_u32(st_smem);
+    const uint32_t bars_u32 = tiles_u32 + S * NOPS * ST_TILE;       // full[S], empty[S]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = blockIdx.y, G = gridDim.x, TI = a.tiles_per_img;
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(bars_u32 + 8 * s, 1);
+            mbar_init(bars_u32 + 8 * (S + s), ST_CONSUMERS / 32);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    const size_t img_elems = (size_t)a.P * a.C;
+    if (warp == ST_CONSUMERS / 32) {                 // ---- producer ----
+        if (lane == 0) {
+            const uint8_t* xs = reinterpret_cast<const uint8_t*>(a.x + (size_t)n * img_elems);
+            const uint8_t* gs = NOPS == 2 ? reinterpret_cast<const uint8_t*>(a.dy + (size_t)n * img_elems) : nullptr;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = blockIdx.x; t < TI; t += G) {
+                mbar_wait(bars_u32 + 8 * (S + s), ph ^ 1);
+                const uint32_t full = bars_u32 + 8 * s;
+                const uint32_t dst = tiles_u32 + s * NOPS * ST_TILE;
+                mbar_expect_tx(full, NOPS * ST_TILE);
+                bulk_load(dst, xs + (size_t)t * ST_TILE, ST_TILE, full);
+                if (NOPS == 2) bulk_load(dst + ST_TILE, gs + (size_t)t * ST_TILE, ST_TILE, full);
+                if (++s == S) { s = 0; ph ^= 1; }
+            }
+        }
+        return;
+    }
+
+    // ---- consumers ----
+    const int C = a.C, CV = C / VEC;
+    const int cv = tid % CV, prow = tid / CV, rows = ST_CONSUMERS / CV;      // a tile holds 2*rows pixels
+    float k0[VEC], k1[VEC], k2[MODE == 2 ? VEC : 1], k3[MODE == 2 ? VEC : 1], k4[MODE == 2 ? VEC : 1];
+    float kg[(AFFINE && MODE != 0) ? VEC : 1], ke[(AFFINE && MODE != 0) ? VEC : 1];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        const int c = cv * VEC + j;
+        const float mean = a.stats[((size_t)n * C + c) * 2], rstd = a.stats[((size_t)n * C + c) * 2 + 1];
+        const float ga = AFFINE ? a.gamma[c] : 1.f, be = AFFINE ? a.beta[c] : 0.f;
+        if constexpr (MODE == 0) {
+            k0[j] = rstd * ga;                     // y = act(v*k0 + k1)
+            k1[j] = be - mean * k0[j];
+        } else {
+            k0[j] = rstd;                          // xhat = v*k0 + k1
+            k1[j] = -mean * rstd;
+            if constexpr (AFFINE) { kg[j] = ga; ke[j] = be; }
+            if constexpr (MODE == 2) {
+                k2[j] = rstd * ga;                 // r = k2*g - (xhat*k4 + k3)
+                k3[j] = k2[j] * a.sums_in[((size_t)n * C + c) * 2] * a.invP;
+                k4[j] = k2[j] * a.sums_in[((size_t)n * C + c) * 2 + 1] * a.invP;
+            }
+        }
+    }
+    float acc_s[MODE == 1 ? VEC : 1], acc_ss[MODE == 1 ? VEC : 1];
+    if constexpr (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc_s[j] = acc_ss[j] = 0.f;
+    }
+    const int Wp = a.W + 2 * a.halo;
+    const size_t out_img = MODE == 2 && a.halo > 0 ? (size_t)(a.P / a.W + 2 * a.halo) * Wp * C : img_elems;
+    T* outp = MODE == 1 ? nullptr : a.out + (size_t)n * out_img + (size_t)cv * VEC;
+
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < TI; t += G) {
+        mbar_wait(bars_u32 + 8 * s, ph);
+        const uint8_t* tile = st_smem + s * NOPS * ST_TILE;
+        float v[2][VEC], g[NOPS == 2 ? 2 : 1][VEC];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            load_vec<T, VEC>(reinterpret_cast<const T*>(tile + (tid + u * ST_CONSUMERS) * 16), v[u]);
+            if constexpr (NOPS == 2) load_vec<T, VEC>(reinterpret_cast<const T*>(tile + ST_TILE + (tid + u * ST_CONSUMERS) * 16), g[u]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars_u32 + 8 * (S + s));         // slot is free as soon as the tile sits in registers
+        if (++s == S) { s = 0; ph ^= 1; }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int p = t * 2 * rows + u * rows + prow;              // pixel index inside the image
+            if constexpr (MODE == 0) {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) v[u][j] = act_fwd(fmaf(v[u][j], k0[j], k1[j]), a.act, a.slope);
+                store_vec<T, VEC>(outp + (size_t)p * C, v[u]);
+            } else {
+                float o[VEC];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    const float xh = fmaf(v[u][j], k0[j], k1[j]);
+                    float pre = xh;
+                    if constexpr (AFFINE) pre = fmaf(xh, kg[j], ke[j]);
+                    const float gg = g[u][j] * act_grad_from_out(pre, a.act, a.slope);
+                    if constexpr (MODE == 1) {
+                        acc_s[j] += gg;
+                        acc_ss[j] = fmaf(gg, xh, acc_ss[j]);
+                    } else {
+                        o[j] = fmaf(k2[j], gg, -fmaf(xh, k4[j], k3[j]));
+                    }
+                }
+                if constexpr (MODE == 2) {
+                    size_t po = p;
+                    if (a.halo > 0) {
+                        const int h = p / a.W, w = p - h * a.W;
+                        po = (size_t)(h + a.halo) * Wp + (w + a.halo);
+                    }
+                    store_vec<T, VEC>(outp + po * C, o);
+                }
+            }
+        }
+    }
+
+    if constexpr (MODE == 2) if (a.halo > 0) {      // zero border of the [H+2h][W+2h] output
+        const int H = a.P / a.W, hl = a.halo;
+        const int nb = 2 * hl * Wp + 2 * hl * H;
+        float z[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) z[j] = 0.f;
+        for (int b = blockIdx.x * rows + prow; b < nb; b += G * rows) {
+            int hp, wp;
+            if (b < 2 * hl * Wp) {
+                hp = b / Wp;
+                wp = b - hp * Wp;
+                if (hp >= hl) hp += H;
+            } else {
+                const int r = b - 2 * hl * Wp;
+                const int h = r / (2 * hl), j = r - h * 2 * hl;
+                hp = h + hl;
+                wp = j < hl ? j : a.W + j;
+            }
+            store_vec<T, VEC>(outp + ((size_t)hp * Wp + wp) * C, z);
+        }
+    }
+
+    if constexpr (MODE == 1) {                      // CTA-level reduction over the pixel rows, then one atomic per channel
+        consumer_sync();                            // every consumer is past its last tile read: reuse the ring
+        float* red = reinterpret_cast<float*>(st_smem);              // [256][2*VEC+1]
+        constexpr int RS = 2 * VEC + 1;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            red[tid * RS + j] = acc_s[j];
+            red[tid * RS + VEC + j] = acc_ss[j];
+        }
+        consumer_sync();
+        for (int o = tid; o < 2 * C; o += ST_CONSUMERS) {
+            const int c = o >> 1, which = o & 1;
+            const int ccv = c / VEC, j = c - ccv * VEC;
+            float sum = 0.f;
+            for (int r = 0; r < rows; ++r) sum += red[(r * CV + ccv) * RS + which * VEC + j];
+            atomicAdd(&a.sums_out[((size_t)n * C + c) * 2 + which], sum);
+        }
+    }
+}
+
+inline bool cv_ok(int C, int VW) {
+    if (C % VW) return false;
+    const int cv = C / VW;
+    return cv <= ST_CONSUMERS && (ST_CONSUMERS % cv) == 0;
+}
+
+template <typename T, int MODE, bool AFFINE>
+int launch_stream(StreamArgs<T>& a, int N, cudaStream_t st) {
+    constexpr int VW = VecWidth<T>::value;
+    constexpr int NOPS = MODE == 0 ? 1 : 2;
+    a.tiles_per_img = (int)(((size_t)a.P * a.C * sizeof(T)) / ST_TILE);
+    a.stages = MODE == 0 ? 8 : 6;
+    size_t smem = (size_t)a.stages * NOPS * ST_TILE + 16 * a.stages;
+    if (MODE == 1) {
+        const size_t red = (size_t)ST_CONSUMERS * (2 * VW + 1) * sizeof(float);
+        if (smem < red) smem = red;
+    }
+    auto kern = in_stream_kernel<T, VW, MODE, AFFINE>;
+    static bool attr_done = false;                  // one flag per template instantiation
+    if (!attr_done) {
+        CG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(6 * 2 * ST_TILE + 1024)));
+        attr_done = true;
+    }
+    int G = (2 * 148) / N;                           // all CTAs resident at once (2 per SM), no second wave
+    if (G > a.tiles_per_img) G = a.tiles_per_img;
+    if (G < 1) G = 1;
+    kern<<<dim3(G, N), ST_THREADS, smem, st>>>(a);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+}   // namespace
+
+template <typename T> bool k_in_stream_ok(const void* p0, const void* p1, const void* p2, int P, int C) {
+    static const bool off = [] { const char* e = getenv("CG_DISABLE_STREAM"); return e && e[0] == '1'; }();   // test hook
+    if (off) return false;
+    if (!cv_ok(C, VecWidth<T>::value)) return false;
+    if (((size_t)P * C * sizeof(T)) % ST_TILE) return false;
+    return !(((uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2) & 15);
+}
+
+template <typename T> int k_in_apply_stream(const T* x, T* y, const float* stats, const float* gamma, const float* beta,
+                                            int act, float slope, int N, int P, int C, cudaStream_t st) {
+    StreamArgs<T> a{};
+    a.x = x; a.out = y; a.stats = stats; a.gamma = gamma; a.beta = beta; a.act = act; a.slope = slope;
+    a.P = P; a.C = C; a.W = P; a.halo = 0; a.invP = 1.f / (float)P;
+    return gamma ? launch_stream<T, 0, true>(a, N, st) : launch_stream<T, 0, false>(a, N, st);
+}
+
+template <typename T> int k_in_bwd_reduce_stream(const T* x, const T* dy, const float* stats, const float* gamma,
+                                                 const float* beta, float* sums, int act, float slope, int N, int P, int C,
+                                                 cudaStream_t st) {
+    StreamArgs<T> a{};
+    a.x = x; a.dy = dy; a.stats = stats; a.sums_out = sums; a.gamma = gamma; a.beta = beta; a.act = act; a.slope = slope;
+    a.P = P; a.C = C; a.W = P; a.halo = 0; a.invP = 1.f / (float)P;
+    return gamma ? launch_stream<T, 1, true>(a, N, st) : launch_stream<T, 1, false>(a, N, st);
+}
+
+template <typename T> int k_in_bwd_apply_stream(const T* x, const T* dy, T* dx, const float* stats, const float* sums,
+                                                const float* gamma, const float* beta, int act, float slope, int N, int P,
+                                                int C, int W, int halo, cudaStream_t st) {
+    StreamArgs<T> a{};
+    a.x = x; a.dy = dy; a.out = dx; a.stats = stats; a.sums_in = sums; a.gamma = gamma; a.beta = beta; a.act = act;
+    a.slope = slope; a.P = P; a.C = C; a.W = halo > 0 ? W : P; a.halo = halo; a.invP = 1.f / (float)P;
+    return gamma ? launch_stream<T, 2, true>(a, N, st) : launch_stream<T, 2, false>(a, N, st);
+}
+
+#define INSTANTIATE(T)                                                                                                     \
+    template bool k_in_stream_ok<T>(const void*, const void*, const void*, int, int);                                      \
+    template int k_in_apply_stream<T>(const T*, T*, const float*, const float*, const float*, int, float, int, int, int,   \
+                                      cudaStream_t);                                                                       \
+    template int k_in_bwd_reduce_stream<T>(const T*, const T*, const float*, const float*, const float*, float*, int,      \
+                                           float, int, int, int, cudaStream_t);                                            \
+    template int k_in_bwd_apply_stream<T>(const T*, const T*, T*, const float*, const float*, const float*, const float*,  \
+                                          int, float, int, int, int, int, int, cudaStream_t);
+INSTANTIATE(float)
+INSTANTIATE(bf16)
