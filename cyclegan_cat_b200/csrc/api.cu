@@ -173,10 +173,10 @@ extern "C" int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode
                 kind = TC_CONV_S2;
             else if (d.op == CG_OP_CONVT && d.stride == 2 && (d.k == 3 || d.k == 4) && chan_ok(d.cout, d.cin))
                 kind = TC_CONVT_S2;
-            else if (d.op == CG_OP_CONV && d.stride == 1 && !d.same && d.k >= 3 && d.cin <= 4 && d.k * d.cin <= 32 &&
+            else if (d.op == CG_OP_CONV && d.stride == 1 && !d.same && d.k >= 3 && d.cin <= 4 && d.k * d.cin <= 21 && d.k <= 12 &&
                      d.cout % 64 == 0 && d.cout <= 256)
                 kind = TC_STEM;         // c7s1-f stem (resnet.py:39-40): horizontal taps unfolded into channels
-            else if (d.op == CG_OP_CONV && d.stride == 1 && !d.same && d.k >= 3 && d.cout <= 4 && d.k * d.cout <= 32 &&
+            else if (d.op == CG_OP_CONV && d.stride == 1 && !d.same && d.k >= 3 && d.cout <= 4 && d.k * d.cout <= 21 && d.k <= 12 &&
                      d.cin % 64 == 0 && d.cin <= 256)
                 kind = TC_HEAD;         // c7s1-3 tanh head (resnet.py:82)
             else if (d.op == CG_OP_CONV && d.stride == 1 && (d.same || d.k == 1) && d.k <= 7 && d.cin % 16 == 0 &&

@@ -1,12 +1,16 @@
 // Helper kernels that put the two image-side 7x7 convolutions of the ResNet generator on the tcgen05 kernels.
 //
-// A 7x7 conv with 3 channels on one side is a bad GEMM (K = 147 or N = 3).  Unfolding the HORIZONTAL taps into the
-// channel dimension turns it into a 7x1 (vertical) conv with 21 -> 64/128 "channels":
-//   stem (3 -> C):  U[r][ow][kw*3+ci] = xp[r][ow+kw][ci];      y[oh][ow][co]   = sum_kh U[oh+kh][ow][:] . Wv[kh][co][:]
+// A 7x7 conv with 3 channels on one side is a bad GEMM (K = 147 or N = 3).
+// Thin INPUT side (stem forward, head data gradient, both weight gradients): the 7 horizontal taps AND 3 vertical taps are
+// unfolded into the channel dimension, 3*7*3 = 63 live channels of a dense 64-channel tensor (one SWIZZLE_128B K chunk),
+// which leaves a 3-tap vertical conv with row offsets 0, 3, 6 (weights of the non-existing kernel rows 7, 8 are zero):
+//   stem (3 -> C):  U[r][ow][(j*7+kw)*3+ci] = xp[r+j][ow+kw][ci], j<3;   y[oh][ow][co] = sum_t U[oh+3t][ow][:] . Wv[t][co][:]
+//   head dgrad:     T[r][q][(j*7+kw)*3+co]  = dy[r-j][q-kw][co];         dxp[ih][q][ci] = sum_t T[ih-3t][q][:] . Whd[t][ci][:]
+//   weight grads:   U / T are the X operand of wgrad_tc_kernel (two taps stacked into its 128 rows), the 64-channel
+//                   activation (dy of the stem, padded input of the head) is the other; small kernels fold the result back.
+// Thin OUTPUT side (head forward, stem data gradient): only the horizontal taps are unfolded, into the GEMM N dimension:
 //   head (C -> 3):  S[oh][q][kw*3+co] = sum_kh xp[oh+kh][q][:] . Wh[kh][kw*3+co][:];  y[oh][ow][co] = sum_kw S[oh][ow+kw][kw*3+co]
-//   head dgrad:     T[r][q][kw*3+co]  = dy[r][q-kw][co];       dxp[ih][q][ci]  = sum_kh T[ih-kh][q][:] . Whd[kh][ci][:]
-//   weight grads:   the same U / T tensors are the operands of wgrad_tc_kernel; small kernels fold the result back.
-// The vertical convs run on conv_tc_kernel (box or flat mode), so the activation is re-read 7x instead of 49x.
+// All of these run on conv_tc_kernel / wgrad_tc_kernel (box or flat mode).
 #include "conv_special.h"
 
 static inline int blocks_for(size_t n) {
@@ -14,58 +18,63 @@ static inline int blocks_for(size_t n) {
     return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
 }
 
-// dst[n][h][q][kw*Cs + c] = src[n][h][q + sign*kw][c]  (0 outside [0,Ws)), channels >= k*Cs are zero; dst has 128 channels.
-// One thread = one destination pixel: it gathers the k*Cs (<= 32) live values once and writes 16 x 16-byte vectors.
-__global__ void unfold_w_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int N, int H, int Ws, int Cs, int Wd,
-                                int k, int sign) {
-    const size_t total = (size_t)N * H * Wd;
-    const int live = k * Cs;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int q = (int)(i % Wd);
-        const size_t row = i / Wd;                          // n*H + h
-        const bf16* srow = src + row * Ws * Cs;
-        uint4* d = reinterpret_cast<uint4*>(dst + i * 128);
-        const bf16 zero = __float2bfloat16(0.f);
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            Pack<bf16, 8> pk;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int ch = v * 8 + j;
-                bf16 val = zero;
-                if (ch < live) {
-                    const int kw = ch / Cs, c = ch - kw * Cs;
-                    const int ws = q + sign * kw;
-                    if (ws >= 0 && ws < Ws) val = srow[(size_t)ws * Cs + c];
-                }
-                pk.v[j] = val;
-            }
-            d[v] = *reinterpret_cast<uint4*>(&pk);
+// dst[n][r][q][(j*k + kw)*Cs + c] = src[n][r + sign*j][q + sign*kw][c]  for j < 3 (0 outside the source), 64 channels,
+// channels >= 3*k*Cs are zero.  grid = (N*Hd rows, 32-pixel blocks of a row); one thread = one 16-byte vector of one
+// destination pixel; the channel -> (j, kw, c) decode (two integer divisions) is done once per block into shared memory.
+__global__ void __launch_bounds__(256) unfold_w_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int Hs, int Ws,
+                                                       int Cs, int Hd, int Wd, int k, int sign) {
+    __shared__ int lut[64];                              // (dj << 16) | (dkw << 8) | c, or -1 for a zero channel
+    if (threadIdx.x < 64) {
+        const int ch = threadIdx.x, row_live = k * Cs;
+        int e = -1;
+        if (ch < 3 * row_live) {
+            const int j = ch / row_live, rem = ch - j * row_live, kw = rem / Cs, c = rem - kw * Cs;
+            e = (j << 16) | (kw << 8) | c;
         }
-#pragma unroll
-        for (int v = 4; v < 16; ++v) d[v] = make_uint4(0u, 0u, 0u, 0u);
+        lut[ch] = e;
     }
+    __syncthreads();
+    const int v = threadIdx.x & 7, q = blockIdx.y * 32 + (threadIdx.x >> 3);
+    if (q >= Wd) return;
+    const int row = blockIdx.x, n = row / Hd, r = row - n * Hd;
+    const bf16* simg = src + (size_t)n * Hs * Ws * Cs;
+    const bf16 zero = __float2bfloat16(0.f);
+    Pack<bf16, 8> pk;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int d = lut[v * 8 + e];
+        bf16 val = zero;
+        if (d >= 0) {
+            const int hs = r + sign * (d >> 16), ws = q + sign * ((d >> 8) & 0xff);
+            if (hs >= 0 && hs < Hs && ws >= 0 && ws < Ws) val = simg[((size_t)hs * Ws + ws) * Cs + (d & 0xff)];
+        }
+        pk.v[e] = val;
+    }
+    reinterpret_cast<uint4*>(dst)[((size_t)row * Wd + q) * 8 + v] = *reinterpret_cast<uint4*>(&pk);
 }
-int sp_unfold_w(const bf16* src, bf16* dst, int N, int H, int Ws, int Cs, int Wd, int k, int sign, cudaStream_t st) {
-    unfold_w_kernel<<<blocks_for((size_t)N * H * Wd), 256, 0, st>>>(src, dst, N, H, Ws, Cs, Wd, k, sign);
+int sp_unfold_w(const bf16* src, bf16* dst, int N, int Hs, int Ws, int Cs, int Hd, int Wd, int k, int sign, cudaStream_t st) {
+    unfold_w_kernel<<<dim3(N * Hd, (Wd + 31) / 32), 256, 0, st>>>(src, dst, Hs, Ws, Cs, Hd, Wd, k, sign);
     CG_LAUNCH_CHECK();
     return CG_OK;
 }
 
-// stem weights: w[kh][kw][ci][co] (fp32 HWIO) -> Wv[kh][co][kw*Cin+ci] bf16, 64 columns (zero padded)
+// stem weights: w[kh][kw][ci][co] (fp32 HWIO) -> Wv[t][co][(j*k+kw)*Cin+ci] bf16 with kh = 3t+j, 64 columns (zero padded)
 __global__ void pack_stem_kernel(const float* __restrict__ w, bf16* __restrict__ wv, int k, int Cin, int Cout) {
-    const int total = k * Cout * 64;
+    const int nt = (k + 2) / 3, total = nt * Cout * 64;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int col = i % 64, co = (i / 64) % Cout, kh = i / (64 * Cout);
+        const int col = i % 64, co = (i / 64) % Cout, t = i / (64 * Cout);
         float v = 0.f;
-        if (col < k * Cin) { const int kw = col / Cin, ci = col - kw * Cin; v = w[(((size_t)kh * k + kw) * Cin + ci) * Cout + co]; }
+        if (col < 3 * k * Cin) {
+            const int j = col / (k * Cin), rem = col - j * k * Cin, kw = rem / Cin, ci = rem - kw * Cin, kh = 3 * t + j;
+            if (kh < k) v = w[(((size_t)kh * k + kw) * Cin + ci) * Cout + co];
+        }
         wv[i] = __float2bfloat16(v);
     }
 }
-// head weights: -> Wh[kh][kw*Cout+co (32 rows)][ci] and Whd[kh][ci][kw*Cout+co (64 columns)]
+// head weights: -> Wh[kh][kw*Cout+co (32 rows)][ci] and Whd[t][ci][(j*k+kw)*Cout+co (64 columns)] with kh = 3t+j
 __global__ void pack_head_kernel(const float* __restrict__ w, bf16* __restrict__ wh, bf16* __restrict__ whd, int k, int Cin,
                                  int Cout) {
-    const int n1 = k * 32 * Cin, n2 = k * Cin * 64;
+    const int n1 = k * 32 * Cin, n2 = ((k + 2) / 3) * Cin * 64;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += gridDim.x * blockDim.x) {
         if (i < n1) {
             const int ci = i % Cin, row = (i / Cin) % 32, kh = i / (Cin * 32);
@@ -74,15 +83,18 @@ __global__ void pack_head_kernel(const float* __restrict__ w, bf16* __restrict__
             wh[i] = __float2bfloat16(v);
         } else {
             const int j = i - n1;
-            const int col = j % 64, ci = (j / 64) % Cin, kh = j / (64 * Cin);
+            const int col = j % 64, ci = (j / 64) % Cin, t = j / (64 * Cin);
             float v = 0.f;
-            if (col < k * Cout) { const int kw = col / Cout, co = col - kw * Cout; v = w[(((size_t)kh * k + kw) * Cin + ci) * Cout + co]; }
+            if (col < 3 * k * Cout) {
+                const int jj = col / (k * Cout), rem = col - jj * k * Cout, kw = rem / Cout, co = rem - kw * Cout, kh = 3 * t + jj;
+                if (kh < k) v = w[(((size_t)kh * k + kw) * Cin + ci) * Cout + co];
+            }
             whd[j] = __float2bfloat16(v);
         }
     }
 }
 int sp_pack_stem(const float* w, bf16* wv, int k, int Cin, int Cout, cudaStream_t st) {
-    pack_stem_kernel<<<blocks_for((size_t)k * Cout * 64), 256, 0, st>>>(w, wv, k, Cin, Cout);
+    pack_stem_kernel<<<blocks_for((size_t)((k + 2) / 3) * Cout * 64), 256, 0, st>>>(w, wv, k, Cin, Cout);
     CG_LAUNCH_CHECK();
     return CG_OK;
 }
@@ -134,13 +146,14 @@ int sp_pack_stem_d(const float* w, bf16* wsd, int k, int Cin, int Cout, cudaStre
 }
 
 // fold the tensor-core weight-gradient results back into TF's HWIO layout (+=)
-//   stem: t[kh][kw*Cin+ci (128 rows)][co]   -> dw[kh][kw][ci][co]
-//   head: t[kh][ci][kw*Cout+co (128 cols)]  -> dw[kh][kw][ci][co]
+//   stem: t[kh/3][((kh%3)*k+kw)*Cin+ci (64 rows)][co]    -> dw[kh][kw][ci][co]
+//   head: t[kh/3][((kh%3)*k+kw)*Cout+co (64 rows)][ci]   -> dw[kh][kw][ci][co]
 __global__ void unpack_dw_kernel(const float* __restrict__ t, float* __restrict__ dw, int k, int Cin, int Cout, int head) {
     const int total = k * k * Cin * Cout;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int co = i % Cout, ci = (i / Cout) % Cin, kw = (i / (Cout * Cin)) % k, kh = i / (Cout * Cin * k);
-        const float v = head ? t[((size_t)kh * Cin + ci) * 128 + kw * Cout + co] : t[((size_t)kh * 128 + kw * Cin + ci) * Cout + co];
+        const int tt = kh / 3, j = kh - 3 * tt;
+        const float v = head ? t[((size_t)tt * 64 + (j * k + kw) * Cout + co) * Cin + ci] : t[((size_t)tt * 64 + (j * k + kw) * Cin + ci) * Cout + co];
         dw[i] += v;
     }
 }

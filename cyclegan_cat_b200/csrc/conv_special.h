@@ -1,6 +1,6 @@
 #pragma once
 #include "common.h"
-int sp_unfold_w(const bf16* src, bf16* dst, int N, int H, int Ws, int Cs, int Wd, int k, int sign, cudaStream_t st);
+int sp_unfold_w(const bf16* src, bf16* dst, int N, int Hs, int Ws, int Cs, int Hd, int Wd, int k, int sign, cudaStream_t st);
 int sp_pack_stem(const float* w, bf16* wv, int k, int Cin, int Cout, cudaStream_t st);
 int sp_pack_head(const float* w, bf16* wh, bf16* whd, int k, int Cin, int Cout, cudaStream_t st);
 int sp_diag_sum(const bf16* S, const float* bias, bf16* y, int N, int R, int Wy, int Ws, int k, int C, int sign, cudaStream_t st);

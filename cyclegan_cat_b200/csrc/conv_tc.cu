@@ -562,6 +562,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                 // operands are fetched with ONE grouped box instead of one box per 64 channels)
                 if (a.x_grouped)
                     tma_load_5d(sa + x_off, &mapX, full(s), 0, w0 + a.dw[tap], h0 + a.dh[tap], x_c0 / 64, a.n0 + img);
+                else if (a.stack2)      // 64-channel X: the two 64-row halves of the A tile are two different taps
+                    for (int b = 0; b < 2; ++b)
+                        tma_load_5d(sa + x_off + b * 8192u, &mapX, full(s), 0, w0 + a.dw[2 * tap + b], 0, h0 + a.dh[2 * tap + b],
+                                    a.n0 + img);
                 else
                     for (int b = 0; b < x_boxes; ++b)
                         tma_load_5d(sa + x_off + b * 8192u, &mapX, full(s), x_c0 + b * 64 + a.dc[tap], w0 + a.dw[tap], a.dp[tap],
@@ -701,7 +705,7 @@ wgrad16_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                     const int tap = row0 / a.Cin, cg = (row0 - tap * a.Cin) / 16;
                     tma_load_5d(sa + (uint32_t)j * 2048u, &mapX, full(s), 0, w0 + a.dw[tap], h0 + a.dh[tap], cg, a.n0 + img);
                 }
-                tma_load_5d(sa + 8u * 2048u, &mapDY, full(s), 0, w0, h0, 0, img);
+                tma_load_5d(sa + 8u * 2048u, &mapDY, full(s), 0, w0, h0, 0, a.y_n0 + img);
                 if (++s == S) { s = 0; ph ^= 1u; }
             }
         }

@@ -23,6 +23,7 @@ struct TcWgradArgs {
     int n_taps, a_blocks, b_blocks, bn, splits, stages;   // M = 128-row blocks of operand A, N = bn-column blocks of B
     int x_grouped, y_grouped;                   // operand map is the channel-grouped 5-D view: ONE TMA box loads all groups
     int transposed;                             // 0: A = X (rows = ci), B = dY (cols = co);  1: A = dY (rows = co), B = X
+    int stack2;                                 // X has 64 channels: A rows 0-63 = tap 2u, rows 64-127 = tap 2u+1 (n_taps = units)
     int n0, nb, y_n0;                           // image offsets: X operand starts at n0, dY operand at y_n0
     int chunks_per_img, chunks_w, Wk, Hk;       // K chunk = 64 pixels = Wk x Hk box of the dY grid
     int dy_off;                                 // halo of the dY buffer
@@ -36,8 +37,9 @@ struct TcWgradArgs {
 // weight gradient of stride-1 convs whose channel counts are multiples of 16 only (tap-stacked M, wgrad16_tc_kernel)
 struct TcWgrad16Args {
     int n_taps, Cin, Cout, m_blocks, splits, stages;
-    int n0, nb;                                 // X images start at n0 (dY is sub-batch relative)
-    int chunks_per_img, chunks_w, Wk, Hk;
+    int n0, nb;                                 // X images start at n0, dY images at y_n0
+    int y_n0;
+    int chunks_per_img, chunks_w, Wk, Hk;       // chunks_w may round up: out-of-range pixels are zero in both operands
     uint32_t idesc;
     short dw[49], dh[49];
 };

@@ -128,13 +128,15 @@ int net_plan(const cg_net_s* net, int N, int H, int W, bool bwd, CallCtx* ctx) {
         } else if (kind == TC_STEM) {
             ok = boxable(wo, ho, 128) && boxable(wo, ho, 64);
         } else if (kind == TC_HEAD) {
-            ok = ((size_t)ho * wi) % 64 == 0 && (size_t)hi * wi < (1u << 30);
+            ok = (size_t)hi * wi < (1u << 30) && 6 * wi < 32767;
         }
         ctx->tc[i].on = ok;
         if (ok && (kind == TC_STEM || kind == TC_HEAD)) {
-            // scratch: the unfolded tensor (128 channels) [+ S for the head forward, smaller] then the fp32 dW staging
-            const size_t big = kind == TC_STEM ? (size_t)N * hi * wo * 128 * 2 : (size_t)N * ho * wi * 128 * 2;
-            const size_t tmp = kind == TC_STEM ? (size_t)d.k * 128 * d.cout * 4 : (size_t)d.k * d.cin * 128 * 4;
+            // scratch: the unfolded tensor (64 channels; S of the head forward is smaller) then the fp32 dW staging
+            // ([vertical taps rounded up to pairs][64][C])
+            const int ntp = 2 * (((d.k + 2) / 3 + 1) / 2);
+            const size_t big = kind == TC_STEM ? (size_t)N * hi * wo * 64 * 2 : (size_t)N * (ho + 2) * wi * 64 * 2;
+            const size_t tmp = (size_t)ntp * 64 * (kind == TC_STEM ? d.cout : d.cin) * 4;
             ctx->tc[i].sc_tmp = align_up(big, 1024);
             const size_t need = ctx->tc[i].sc_tmp + align_up(tmp, 1024);
             if (need > ctx->tcs_bytes) ctx->tcs_bytes = need;
@@ -191,6 +193,33 @@ static void set_tiles(TcConvArgs& a, int w, int h) {
     a.tiles_w = w / a.Wb;
     a.tiles_per_img = a.tiles_w * (h / a.Hb);
     a.out_P = w; a.out_wvalid = w; a.out_hvalid = h;
+}
+
+// 16-channel-group (SWIZZLE_32B) conv launch: out[n, p, :] = sum_taps in[n, p + (dw, dh)[tap], :] * W[tap]   with
+// zero fill outside `in` (TMA out-of-bounds).  Box mode tiles the (out_w x out_h) grid; flat mode walks the output as
+// one line of out_w*out_h pixels in 128-pixel tiles and `in` as one line of map_w pixels (map_h = 1, dw = flat offsets).
+static int make_conv16(TcConvLaunch& Ln, const void* in, int cin_k, int map_w, int map_h, int N, const bf16* wmat, int n_out,
+                       int n_taps, const short* dw, const short* dh, bool flat, int out_w, int out_h) {
+    TcConvArgs& a = Ln.a;
+    memset(&a, 0, sizeof(a));
+    if (flat) {
+        a.Wb = 128; a.Hb = 1;
+        a.tiles_per_img = (out_w * out_h + 127) / 128; a.tiles_w = a.tiles_per_img;
+        a.out_P = out_w; a.out_wvalid = out_w; a.out_hvalid = out_h;
+    } else {
+        set_tiles(a, out_w, out_h);
+    }
+    a.n_taps = n_taps;
+    a.bk16 = 1; a.cin16 = cin_k / 16; a.groups = a.cin16 < 8 ? a.cin16 : 8;
+    a.cchunks = (a.cin16 + a.groups - 1) / a.groups;
+    a.bn = n_out; a.n_blocks_n = 1;
+    a.nb = N; a.out_H = out_h; a.out_W = out_w; a.Cout = n_out; a.out_sy = a.out_sx = 1;
+    a.b_rows_per_tap = n_out;
+    for (int tp = 0; tp < n_taps; ++tp) { a.tb[tp] = (short)tp; a.dw[tp] = dw[tp]; a.dh[tp] = dh[tp]; }
+    CG_TRY(tc_make_map_act16(&Ln.mapA, in, cin_k, map_w, map_h, N, a.Wb, a.Hb, a.groups));
+    CG_TRY(tc_make_map_w16(&Ln.mapB, wmat, cin_k, n_taps * n_out, n_out, a.groups));
+    Ln.mapB2 = Ln.mapB;
+    return CG_OK;
 }
 
 // conv-type launch: out[n,oh,ow,:] = sum_taps in[n, oh*s + kh - pt, ow*s + kw - pl, :] * Wf[tap]  (+ bias)
@@ -351,26 +380,13 @@ int net_bind(CallCtx* c) {
             int pt = 0, pl = 0;
             if (d.same) { same_pad(hi, k, 1, &pt); same_pad(wi, k, 1, &pl); }
             auto make16 = [&](TcConvLaunch& Ln, const void* in, int cin_k, const bf16* wmat, int n_out, bool flip) -> int {
-                TcConvArgs& a = Ln.a;
-                memset(&a, 0, sizeof(a));
-                set_tiles(a, wo, ho);
-                a.n_taps = k * k;
-                a.bk16 = 1; a.cin16 = cin_k / 16; a.groups = a.cin16 < 8 ? a.cin16 : 8;
-                a.cchunks = (a.cin16 + a.groups - 1) / a.groups;
-                a.bn = n_out; a.n_blocks_n = 1;
-                a.nb = c->N; a.out_H = ho; a.out_W = wo; a.Cout = n_out; a.out_sy = a.out_sx = 1;
-                a.b_rows_per_tap = n_out;
+                short tdw[49], tdh[49];
                 for (int kh = 0; kh < k; ++kh)
                     for (int kw = 0; kw < k; ++kw) {
-                        const int tp = kh * k + kw;
-                        a.tb[tp] = (short)tp;
-                        a.dw[tp] = (short)(flip ? pl - kw : kw - pl);
-                        a.dh[tp] = (short)(flip ? pt - kh : kh - pt);
+                        tdw[kh * k + kw] = (short)(flip ? pl - kw : kw - pl);
+                        tdh[kh * k + kw] = (short)(flip ? pt - kh : kh - pt);
                     }
-                CG_TRY(tc_make_map_act16(&Ln.mapA, in, cin_k, wo, ho, c->N, a.Wb, a.Hb, a.groups));
-                CG_TRY(tc_make_map_w16(&Ln.mapB, wmat, cin_k, k * k * n_out, n_out, a.groups));
-                Ln.mapB2 = Ln.mapB;
-                return CG_OK;
+                return make_conv16(Ln, in, cin_k, wo, ho, c->N, wmat, n_out, k * k, tdw, tdh, false, wo, ho);
             };
             t.fwd.assign(1, TcConvLaunch());
             CG_TRY(make16(t.fwd[0], x, d.cin, wf, d.cout, false));
@@ -392,31 +408,32 @@ int net_bind(CallCtx* c) {
             }
         } else if (L.tc == TC_STEM) {
             if (!c->tcs) { cg_set_error("net_bind: no scratch for the unfolded stem input"); return CG_ERR_STATE; }
-            const void* U = c->tcs;                         // [N][hi][wo][128]: U[r][ow][kw*cin+ci] = x[r][ow+kw][ci]
+            const void* U = c->tcs;                         // [N][hi][wo][64]: U[r][ow][(j*k+kw)*cin+ci] = x[r+j][ow+kw][ci], j < 3
+            const int nt = (k + 2) / 3;                     // vertical taps left after the unfolding: row offsets 0, 3, 6
             t.fwd.assign(1, TcConvLaunch());
             {
                 TcConvArgs& a = t.fwd[0].a;
                 memset(&a, 0, sizeof(a));
                 set_tiles(a, wo, ho);
-                a.n_taps = k; a.cchunks = 1; a.bn = d.cout; a.n_blocks_n = 1;
+                a.n_taps = nt; a.cchunks = 1; a.bn = d.cout; a.n_blocks_n = 1;
                 a.nb = c->N; a.out_H = ho; a.out_W = wo; a.Cout = d.cout; a.out_sy = a.out_sx = 1;
                 a.b_rows_per_tap = d.cout;
-                for (int kh = 0; kh < k; ++kh) { a.tb[kh] = (short)kh; a.dh[kh] = (short)kh; }
-                CG_TRY(tc_make_map_act(&t.fwd[0].mapA, U, 128, wo, hi, c->N, 0, a.Wb, a.Hb));
-                CG_TRY(tc_make_map_2d(&t.fwd[0].mapB, wf, 64, k * d.cout, a.bn));
-                CG_TRY(tc_make_map_2d(&t.fwd[0].mapB2, wf, 64, k * d.cout, (a.bn) / 2 >= 8 ? (a.bn) / 2 : 8));
+                for (int tp = 0; tp < nt; ++tp) { a.tb[tp] = (short)tp; a.dh[tp] = (short)(3 * tp); }
+                CG_TRY(tc_make_map_act(&t.fwd[0].mapA, U, 64, wo, hi, c->N, 0, a.Wb, a.Hb));
+                CG_TRY(tc_make_map_2d(&t.fwd[0].mapB, wf, 64, nt * d.cout, a.bn));
+                CG_TRY(tc_make_map_2d(&t.fwd[0].mapB2, wf, 64, nt * d.cout, (a.bn) / 2 >= 8 ? (a.bn) / 2 : 8));
             }
             if (!c->bwd) continue;
-            {
+            {   // dWv[t][64 rows][co] = sum_pixels U[oh+3t][ow][:] (x) dy[oh][ow][co]; two taps share the 128 MMA rows
                 TcWgradArgs& a = t.wa;
                 memset(&a, 0, sizeof(a));
                 a.Wk = wo % 64 == 0 ? 64 : wo; a.Hk = 64 / a.Wk;
-                a.n_taps = k; a.transposed = 0; a.a_blocks = 1; a.bn = d.cout; a.b_blocks = 1;
+                a.n_taps = (nt + 1) / 2; a.stack2 = 1; a.transposed = 0; a.a_blocks = 1; a.bn = d.cout; a.b_blocks = 1;
                 a.chunks_w = wo / a.Wk; a.chunks_per_img = a.chunks_w * (ho / a.Hk);
                 a.Cin = 128; a.Cout = d.cout;
-                for (int kh = 0; kh < k; ++kh) a.dh[kh] = (short)kh;
-                a.x_grouped = a.y_grouped = 1;
-                CG_TRY(tc_make_map_act_grouped(&t.mapXw, U, 128, wo, hi, c->N, a.Wk, a.Hk, 2));
+                for (int tp = 0; tp < 2 * a.n_taps; ++tp) a.dh[tp] = (short)(tp < nt ? 3 * tp : 20000);   // odd tap count: the last half is out of bounds = 0
+                a.x_grouped = 0; a.y_grouped = 1;
+                CG_TRY(tc_make_map_act(&t.mapXw, U, 64, wo, hi, c->N, 0, a.Wk, a.Hk));
                 CG_TRY(tc_make_map_act_grouped(&t.mapDYw, dy, d.cout, wo, ho, c->N, a.Wk, a.Hk, d.cout / 64));
             }
             // data gradient (only needed when the stem's input is itself a generated image: the cycle calls):
@@ -441,7 +458,7 @@ int net_bind(CallCtx* c) {
         } else if (L.tc == TC_HEAD) {
             if (!c->tcs) { cg_set_error("net_bind: no scratch for the unfolded head tensors"); return CG_ERR_STATE; }
             const void* S = c->tcs;                         // forward:  [N][ho][wi][32]
-            const void* T = c->tcs;                         // backward: [N][ho][wi][128], T[r][q][kw*cout+co] = dy[r][q-kw][co]
+            const void* T = c->tcs;                         // backward: [N][ho+2][wi][64], T[r][q][(j*k+kw)*cout+co] = dy[r-j][q-kw][co]
             t.fwd.assign(1, TcConvLaunch());
             {
                 TcConvArgs& a = t.fwd[0].a;
@@ -460,33 +477,35 @@ int net_bind(CallCtx* c) {
                 (void)S;
             }
             if (!c->bwd) continue;
+            const int nt = (k + 2) / 3, Hd = ho + 2;
             t.dgrad.assign(1, TcConvLaunch());
-            {
+            {   // dxp[ih][q][ci] = sum_t T[ih-3t][q][:] . Whd[t][ci][:]   (flat mode over the padded input grid)
                 TcConvArgs& a = t.dgrad[0].a;
                 memset(&a, 0, sizeof(a));
                 a.Wb = 128; a.Hb = 1;
-                a.n_taps = k; a.cchunks = 1; a.bn = d.cin; a.n_blocks_n = 1;
+                a.n_taps = nt; a.cchunks = 1; a.bn = d.cin; a.n_blocks_n = 1;
                 a.tiles_per_img = (hi * wi + 127) / 128; a.tiles_w = a.tiles_per_img;
                 a.nb = c->N;
                 a.out_P = wi; a.out_wvalid = wi; a.out_hvalid = hi; a.out_H = hi; a.out_W = wi; a.Cout = d.cin;
                 a.out_sy = a.out_sx = 1;
                 a.b_rows_per_tap = d.cin;
-                for (int kh = 0; kh < k; ++kh) { a.tb[kh] = (short)kh; a.dw[kh] = (short)(-kh * wi); }
-                CG_TRY(tc_make_map_act(&t.dgrad[0].mapA, T, 128, ho * wi, 1, c->N, 0, 128, 1));
-                CG_TRY(tc_make_map_2d(&t.dgrad[0].mapB, wd, 64, k * d.cin, a.bn));
-                CG_TRY(tc_make_map_2d(&t.dgrad[0].mapB2, wd, 64, k * d.cin, (a.bn) / 2 >= 8 ? (a.bn) / 2 : 8));
+                for (int tp = 0; tp < nt; ++tp) { a.tb[tp] = (short)tp; a.dw[tp] = (short)(-3 * tp * wi); }
+                CG_TRY(tc_make_map_act(&t.dgrad[0].mapA, T, 64, Hd * wi, 1, c->N, 0, 128, 1));
+                CG_TRY(tc_make_map_2d(&t.dgrad[0].mapB, wd, 64, nt * d.cin, a.bn));
+                CG_TRY(tc_make_map_2d(&t.dgrad[0].mapB2, wd, 64, nt * d.cin, (a.bn) / 2 >= 8 ? (a.bn) / 2 : 8));
             }
-            {
+            {   // dWh[t][64 rows][ci] = sum_{r,q} T[r-3t][q][:] (x) xp[r][q][ci] over the padded input grid; the last 64-pixel
+                // chunk of a row is partly out of bounds: zero-filled in BOTH operands
                 TcWgradArgs& a = t.wa;
                 memset(&a, 0, sizeof(a));
                 a.Wk = 64; a.Hk = 1;
-                a.n_taps = k; a.transposed = 1; a.a_blocks = 1; a.bn = d.cin; a.b_blocks = 1;
-                a.chunks_per_img = ho * wi / 64; a.chunks_w = a.chunks_per_img;
-                a.Cin = d.cin; a.Cout = 128;
-                for (int kh = 0; kh < k; ++kh) a.dw[kh] = (short)(kh * wi);
-                a.x_grouped = a.y_grouped = 1;
-                CG_TRY(tc_make_map_act_grouped(&t.mapXw, x, d.cin, hi * wi, 1, c->N, 64, 1, d.cin / 64));
-                CG_TRY(tc_make_map_act_grouped(&t.mapDYw, T, 128, ho * wi, 1, c->N, 64, 1, 2));
+                a.n_taps = (nt + 1) / 2; a.stack2 = 1; a.transposed = 0; a.a_blocks = 1; a.bn = d.cin; a.b_blocks = 1;
+                a.chunks_w = (wi + 63) / 64; a.chunks_per_img = a.chunks_w * hi;
+                a.Cin = 128; a.Cout = d.cin;
+                for (int tp = 0; tp < 2 * a.n_taps; ++tp) a.dh[tp] = (short)(tp < nt ? -3 * tp : 20000);
+                a.x_grouped = 0; a.y_grouped = 1;
+                CG_TRY(tc_make_map_act(&t.mapXw, T, 64, wi, Hd, c->N, 0, 64, 1));
+                CG_TRY(tc_make_map_act_grouped(&t.mapDYw, x, d.cin, wi, hi, c->N, 64, 1, d.cin / 64));
             }
         } else if (L.tc == TC_CONVT_S2) {
             // F: (ho x wo x cout) -> (hi x wi x cin), stride 2, 'same' padding computed on the big grid
@@ -532,7 +551,7 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
                 const double fl = 2.0 * N * oh * ow * (double)d.cout * d.k * d.k * d.cin;
                 if (c->tc[i].on && L.tc == TC_STEM) {
                     const TcConvLaunch& tl = c->tc[i].fwd[0];
-                    CG_TRY(sp_unfold_w((const bf16*)x, (bf16*)c->tcs, N, h, w, d.cin, ow, d.k, +1, st));
+                    CG_TRY(sp_unfold_w((const bf16*)x, (bf16*)c->tcs, N, h, w, d.cin, h, ow, d.k, +1, st));
                     TcConvArgs a = tl.a;
                     a.nb = N;
                     a.stats = fused_stats;
@@ -672,10 +691,11 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                     const double fl = 2.0 * nb * oh * ow * (double)d.cout * d.k * d.k * d.cin;
                     float* tmp = (float*)(c->tcs + c->tc[i].sc_tmp);
                     bf16* big = (bf16*)c->tcs;
+                    const int ntp = 2 * (((d.k + 2) / 3 + 1) / 2);
                     if (L.tc == TC_STEM) {
                         if (grads) {
-                            CG_TRY(sp_unfold_w((const bf16*)A(tin), big, nb, h, w, d.cin, ow, d.k, +1, st));
-                            CG_CUDA(cudaMemsetAsync(tmp, 0, (size_t)d.k * 128 * d.cout * sizeof(float), st));
+                            CG_TRY(sp_unfold_w((const bf16*)A(tin), big, nb, h, w, d.cin, h, ow, d.k, +1, st));
+                            CG_CUDA(cudaMemsetAsync(tmp, 0, (size_t)ntp * 64 * d.cout * sizeof(float), st));
                             TcWgradArgs a = c->tc[i].wa;
                             a.n0 = 0; a.nb = nb;
                             CG_TRY(tc_wgrad_launch(&c->tc[i].mapXw, &c->tc[i].mapDYw, tmp, a, fl, st));
@@ -690,11 +710,11 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                             CG_TRY(sp_diag_sum(big, nullptr, (bf16*)dx, nb, h, w, ow, d.k, d.cin, -1, st));
                         }
                     } else {
-                        CG_TRY(sp_unfold_w((const bf16*)dy, big, nb, oh, ow, d.cout, w, d.k, -1, st));
+                        CG_TRY(sp_unfold_w((const bf16*)dy, big, nb, oh, ow, d.cout, oh + 2, w, d.k, -1, st));
                         if (grads) {
-                            CG_CUDA(cudaMemsetAsync(tmp, 0, (size_t)d.k * d.cin * 128 * sizeof(float), st));
+                            CG_CUDA(cudaMemsetAsync(tmp, 0, (size_t)ntp * 64 * d.cin * sizeof(float), st));
                             TcWgradArgs a = c->tc[i].wa;
-                            a.n0 = n0; a.nb = nb;
+                            a.n0 = 0; a.y_n0 = n0; a.nb = nb;
                             CG_TRY(tc_wgrad_launch(&c->tc[i].mapXw, &c->tc[i].mapDYw, tmp, a, fl, st));
                             CG_TRY(sp_unpack_dw(tmp, grads + L.w_off, d.k, d.cin, d.cout, 1, st));
                             if (L.b_off >= 0 && !L.bias_grad_zero) CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
