@@ -146,6 +146,12 @@ __device__ __forceinline__ float warp_colsum32(float (&s)[32], int lane) {
 }
 
 static constexpr int TC_THREADS = 192;        // 6 warps: TMA, MMA, 4 x epilogue
+// conv_tc_kernel: 10 warps = TMA, MMA, 8 x epilogue.  The epilogue of a 32-column chunk (tcgen05.ld, bf16 pack, stores,
+// instance-norm column sums) costs a lone warp ~2200 cycles of mostly exposed latency, more than the main loop of every
+// layer but the 9-tap trunk convs; two warps per TMEM lane quarter (each takes every other chunk) hide each other's latency.
+static constexpr int CONV_THREADS = 320;
+static constexpr int EPI_WARPS = 8;
+static constexpr int EPI_SCRATCH = EPI_WARPS * 32 * 17 * 4;      // per warp: a [32 rows][16 columns + 1] float transpose buffer
 static constexpr int A_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
 static constexpr int TMEM_COLS = 512;
 
@@ -155,7 +161,7 @@ static constexpr int TMEM_COLS = 512;
 // BK16 (the 16-channel-group SWIZZLE_32B mode of the U-Net layers) is a template parameter: as a run-time branch it cost
 // the 64-channel instance 19 % (1216 -> 987 TFLOP/s at the C3 trunk shape, same box, back to back).
 template <bool BK16>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                bf16* __restrict__ out, const float* __restrict__ bias, const TcConvArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -171,13 +177,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     auto tempty = [&](int i) { return bar0 + 8u * (2 * S + 2 + i); };
     const uint32_t tmem_slot = bar0 + 8u * (2 * S + 4);
     volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-    float* stat_sm = reinterpret_cast<float*>(smem_raw + (bar0 + 256u - smem_u32(smem_raw)));   // epilogue: per-warp column sums
+    float* stat_sm = reinterpret_cast<float*>(smem_raw + (bar0 + 256u - smem_u32(smem_raw)));   // epilogue: per-warp transpose buffers
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA);
         tma_prefetch_desc(&mapB);
         for (int s = 0; s < S; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -249,6 +255,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
     } else {
         const int q = warp & 3;                   // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;         // two warps per quarter: even / odd 32-column chunks
+        float* tr = stat_sm + (warp - 2) * (32 * 17);
         int it = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -261,10 +269,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const bool valid = ow < a.out_wvalid && oh < a.out_hvalid;
             bf16* dst = out + (((size_t)img * a.out_H + (oh * a.out_sy + a.out_oy)) * a.out_W + (ow * a.out_sx + a.out_ox)) * a.Cout +
                         (size_t)nblk * a.bn;
+            bf16* rowptr[4];                      // output rows this lane stores: row (lane/4 + 8i) of the warp's 32, or null
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const unsigned long long pv = __shfl_sync(0xffffffffu, valid ? (unsigned long long)dst : 0ull, (lane >> 2) + 8 * i);
+                rowptr[i] = reinterpret_cast<bf16*>(pv);
+            }
             mbar_wait(tfull(acc), acc_ph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
-            for (int c0 = 0; c0 < a.bn; c0 += 32) {
+            for (int c0 = half * 32; c0 < a.bn; c0 += 64) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
                 const int cols = BK16 ? min(32, a.bn - c0) : 32;          // 16 when the N tile is not a multiple of 32 (BK16 only)
@@ -273,29 +287,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     for (int j = 0; j < 32; ++j)
                         if (j < cols) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(bias + nblk * a.bn + c0 + j));
                 }
-                if (valid) {
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-                    uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+                {
+                    // a lane owns one pixel row (64 bytes of this chunk): storing it directly makes every warp store touch 32
+                    // different lines with 16 bytes each.  Four 16-byte pieces per lane go through an XOR-swizzled 2 KB
+                    // staging tile instead, and each store instruction writes the whole 64-byte segments of 8 rows.
+                    uint4* stg = reinterpret_cast<uint4*>(tr);
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        if (j * 8 < cols) d4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                }
-                if (a.stats) {      // fused instance-norm statistics: per-channel sum and sum of squares of this tile
-                    float s1[32], s2[32];
+                        stg[lane * 4 + (j ^ ((lane >> 1) & 3))] =
+                            make_uint4(pack_bf16x2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                                       pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                                       pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                                       pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+                    __syncwarp();
+                    const int g = lane & 3;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { const float x = valid ? __uint_as_float(v[j]) : 0.f; s1[j] = x; s2[j] = x * x; }
-                    const float cs = warp_colsum32(s1, lane), cq = warp_colsum32(s2, lane);
-                    stat_sm[(q * 2 + 0) * 32 + lane] = cs;
-                    stat_sm[(q * 2 + 1) * 32 + lane] = cq;
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (q == 0 && lane < cols) {
-                        float* sp = a.stats + ((size_t)img * a.Cout + (size_t)nblk * a.bn + c0 + lane) * 2;
-                        atomicAdd(sp, stat_sm[0 * 32 + lane] + stat_sm[2 * 32 + lane] + stat_sm[4 * 32 + lane] + stat_sm[6 * 32 + lane]);
-                        atomicAdd(sp + 1, stat_sm[1 * 32 + lane] + stat_sm[3 * 32 + lane] + stat_sm[5 * 32 + lane] + stat_sm[7 * 32 + lane]);
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = (lane >> 2) + 8 * i;
+                        const uint4 val = stg[r * 4 + (g ^ ((r >> 1) & 3))];
+                        if (rowptr[i] && g * 8 < cols) *reinterpret_cast<uint4*>(rowptr[i] + c0 + g * 8) = val;
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    __syncwarp();
+                }
+                if (a.stats) {
+                    // fused instance-norm statistics: per-channel sum and sum of squares over this warp's 32 rows, 16
+                    // columns per pass through a padded shared-memory transpose (conflict-free both ways): lanes 0-15 sum
+                    // rows 0-15 of column `lane`, lanes 16-31 rows 16-31 of column `lane-16`; one shuffle joins the halves
+                    // and ONE 128-byte reduction adds {sum, sumsq} x 16 columns to the [img][channel][2] table
+                    float* sp = a.stats + ((size_t)img * a.Cout + (size_t)nblk * a.bn + c0) * 2;
+#pragma unroll
+                    for (int pass = 0; pass < 2; ++pass) {
+                        if (pass * 16 < cols) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) tr[lane * 17 + j] = valid ? __uint_as_float(v[pass * 16 + j]) : 0.f;
+                            __syncwarp();
+                            const float* col = tr + (lane >> 4) * 16 * 17 + (lane & 15);
+                            float s1 = 0.f, s2 = 0.f, s1b = 0.f, s2b = 0.f;
+#pragma unroll
+                            for (int r = 0; r < 16; r += 2) {
+                                const float x0 = col[r * 17], x1 = col[(r + 1) * 17];
+                                s1 += x0; s2 = fmaf(x0, x0, s2);
+                                s1b += x1; s2b = fmaf(x1, x1, s2b);
+                            }
+                            s1 += s1b; s2 += s2b;
+                            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                            s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+                            atomicAdd(sp + pass * 32 + 2 * (lane & 15) + (lane >> 4), (lane >> 4) ? s2 : s1);
+                            __syncwarp();
+                        }
+                    }
                 }
             }
             tc_fence_before();
@@ -944,11 +984,11 @@ int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, const CUten
     }
     const int stage_b = a.bk16 ? a.groups * (4096 + a.bn * 32) : (A_TILE_BYTES + a.bn * 128);
     {
-        int sN = (227 * 1024 - 3072) / stage_b;
+        int sN = (227 * 1024 - 1024 - 256 - EPI_SCRATCH) / stage_b;
         a.stages = sN > 8 ? 8 : sN;
     }
     a.idesc = make_idesc(128, a.bn, 0, 0);
-    const size_t smem = (size_t)a.stages * stage_b + 1024 + 256 + 1024;
+    const size_t smem = (size_t)a.stages * stage_b + 1024 + 256 + EPI_SCRATCH;
     static bool attr_set = false;
     if (!attr_set) {
         CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -958,8 +998,8 @@ int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, const CUten
     const int total = a.nb * a.tiles_per_img * a.n_blocks_n;
     int grid = total < num_sms() ? total : num_sms();
     int pi = prof_begin(st);
-    if (a.bk16) conv_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(*mapA, *mapB, out, bias, a);
-    else conv_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(*mapA, *mapB, out, bias, a);
+    if (a.bk16) conv_tc_kernel<true><<<grid, CONV_THREADS, smem, st>>>(*mapA, *mapB, out, bias, a);
+    else conv_tc_kernel<false><<<grid, CONV_THREADS, smem, st>>>(*mapA, *mapB, out, bias, a);
     prof_end(pi, st, flops, prof_key(1, a.n_taps, a.cchunks, a.bn, a.tiles_per_img, a.nb));
     CG_LAUNCH_CHECK();
     return CG_OK;
