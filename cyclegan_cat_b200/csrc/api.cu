@@ -141,6 +141,19 @@ extern "C" int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode
             net->has_buffer[i + 1] = 0;
         }
     }
+    // an instance norm (+ folded activation) whose only consumer is a reflection pad writes the padded tensor itself
+    for (int i = 0; i < n_layers; ++i) {
+        LayerInfo& L = net->layers[i];
+        if (L.d.op != CG_OP_INORM || L.skipped || L.out_t >= n_layers || net->n_consumers[L.out_t] != 1) continue;
+        for (int j = i + 1; j < n_layers; ++j) {
+            const LayerInfo& R = net->layers[j];
+            if (R.skipped) continue;
+            if (R.d.in0 == L.out_t || ((R.d.op == CG_OP_ADD || R.d.op == CG_OP_CONCAT) && R.d.in1 == L.out_t)) {
+                if (R.d.op == CG_OP_RPAD && R.d.in0 == L.out_t && R.d.pad > 0) L.fuse_rpad = j;
+                break;
+            }
+        }
+    }
     // A conv / transposed-conv bias that feeds ONLY an instance norm has an identically zero gradient: the norm subtracts
     // the per-(sample, channel) mean, so sum_pixels dL/dy == 0 ('zero-by-construction gradients').  The
     // reference computes rounding noise there; this library writes the exact value 0 and skips the reduction.

@@ -19,36 +19,41 @@ static inline int blocks_for(size_t n) {
 }
 
 // dst[n][r][q][(j*k + kw)*Cs + c] = src[n][r + sign*j][q + sign*kw][c]  for j < 3 (0 outside the source), 64 channels,
-// channels >= 3*k*Cs are zero.  grid = (N*Hd rows, 32-pixel blocks of a row); one thread = one 16-byte vector of one
-// destination pixel; the channel -> (j, kw, c) decode (two integer divisions) is done once per block into shared memory.
+// channels >= 3*k*Cs are zero.  grid = (N*Hd rows, 32-pixel blocks of a row).  A block first copies the three source row
+// windows it needs ((32 + k - 1) pixels each, zero outside the source) into shared memory with coalesced loads, then one
+// thread = one 16-byte vector of one destination pixel gathers its 8 values from there; the channel -> (j, kw, c) decode
+// (two integer divisions) is done once per block.
+constexpr int UNF_MAXW = (32 + 15) * 4;                   // window elements per row: k <= 16, Cs <= 4
 __global__ void __launch_bounds__(256) unfold_w_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int Hs, int Ws,
                                                        int Cs, int Hd, int Wd, int k, int sign) {
-    __shared__ int lut[64];                              // (dj << 16) | (dkw << 8) | c, or -1 for a zero channel
+    __shared__ int lut[64];                              // offset into the window: j*winE + kw'*Cs + c, or -1 (zero channel)
+    __shared__ bf16 win[3 * UNF_MAXW];
+    const int row = blockIdx.x, n = row / Hd, r = row - n * Hd, q0 = blockIdx.y * 32;
+    const int winP = 32 + k - 1, winE = winP * Cs;       // window: source columns [c0, c0 + winP)
+    const int c0 = sign > 0 ? q0 : q0 - (k - 1);
     if (threadIdx.x < 64) {
         const int ch = threadIdx.x, row_live = k * Cs;
         int e = -1;
         if (ch < 3 * row_live) {
             const int j = ch / row_live, rem = ch - j * row_live, kw = rem / Cs, c = rem - kw * Cs;
-            e = (j << 16) | (kw << 8) | c;
+            e = j * winE + (sign > 0 ? kw : (k - 1 - kw)) * Cs + c;      // pixel q reads window column (q - q0) + kw'
         }
         lut[ch] = e;
     }
-    __syncthreads();
-    const int v = threadIdx.x & 7, q = blockIdx.y * 32 + (threadIdx.x >> 3);
-    if (q >= Wd) return;
-    const int row = blockIdx.x, n = row / Hd, r = row - n * Hd;
-    const bf16* simg = src + (size_t)n * Hs * Ws * Cs;
     const bf16 zero = __float2bfloat16(0.f);
+    for (int i = threadIdx.x; i < 3 * winE; i += 256) {
+        const int j = i / winE, rem = i - j * winE, px = rem / Cs, c = rem - px * Cs;
+        const int hs = r + sign * j, ws = c0 + px;
+        win[i] = (hs >= 0 && hs < Hs && ws >= 0 && ws < Ws) ? src[(((size_t)n * Hs + hs) * Ws + ws) * Cs + c] : zero;
+    }
+    __syncthreads();
+    const int v = threadIdx.x & 7, ql = threadIdx.x >> 3, q = q0 + ql;
+    if (q >= Wd) return;
     Pack<bf16, 8> pk;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int d = lut[v * 8 + e];
-        bf16 val = zero;
-        if (d >= 0) {
-            const int hs = r + sign * (d >> 16), ws = q + sign * ((d >> 8) & 0xff);
-            if (hs >= 0 && hs < Hs && ws >= 0 && ws < Ws) val = simg[((size_t)hs * Ws + ws) * Cs + (d & 0xff)];
-        }
-        pk.v[e] = val;
+        pk.v[e] = d >= 0 ? win[d + ql * Cs] : zero;
     }
     reinterpret_cast<uint4*>(dst)[((size_t)row * Wd + q) * 8 + v] = *reinterpret_cast<uint4*>(&pk);
 }

@@ -39,6 +39,7 @@ struct StreamArgs {
     int act;
     float slope;
     int P, C, W, halo;
+    int pad;                  // MODE 0: > 0 writes the reflection-padded [H+2p][W+2p] tensor (ReflectionPadding2D fused in)
     float invP;
     int stages, tiles_per_img;
 };
@@ -116,7 +117,8 @@ __global__ void __launch_bounds__(ST_THREADS, 2) in_stream_kernel(const StreamAr
         for (int j = 0; j < VEC; ++j) acc_s[j] = acc_ss[j] = 0.f;
     }
     const int Wp = a.W + 2 * a.halo;
-    const size_t out_img = MODE == 2 && a.halo > 0 ? (size_t)(a.P / a.W + 2 * a.halo) * Wp * C : img_elems;
+    const size_t out_img = MODE == 2 && a.halo > 0 ? (size_t)(a.P / a.W + 2 * a.halo) * Wp * C
+                           : (MODE == 0 && a.pad > 0 ? (size_t)(a.P / a.W + 2 * a.pad) * (a.W + 2 * a.pad) * C : img_elems);
     T* outp = MODE == 1 ? nullptr : a.out + (size_t)n * out_img + (size_t)cv * VEC;
 
     int s = 0;
@@ -139,7 +141,22 @@ __global__ void __launch_bounds__(ST_THREADS, 2) in_stream_kernel(const StreamAr
             if constexpr (MODE == 0) {
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) v[u][j] = act_fwd(fmaf(v[u][j], k0[j], k1[j]), a.act, a.slope);
-                store_vec<T, VEC>(outp + (size_t)p * C, v[u]);
+                if (a.pad == 0) {
+                    store_vec<T, VEC>(outp + (size_t)p * C, v[u]);
+                } else {
+                    // reflection padding (cyclegan/resnet.py:5-23, tf.pad REFLECT): interior pixel (h, w) lands at
+                    // (h+p, w+p) and, when it lies within p of an edge (but not on it), at its mirror image(s) too
+                    const int pd = a.pad, H = a.P / a.W, Wq = a.W + 2 * pd;
+                    const int h = p / a.W, w = p - h * a.W;
+                    int hr[3], wr[3], nh = 1, nw = 1;
+                    hr[0] = h + pd; wr[0] = w + pd;
+                    if (h >= 1 && h <= pd) hr[nh++] = pd - h;
+                    if (h >= H - 1 - pd && h <= H - 2) hr[nh++] = pd + 2 * (H - 1) - h;
+                    if (w >= 1 && w <= pd) wr[nw++] = pd - w;
+                    if (w >= a.W - 1 - pd && w <= a.W - 2) wr[nw++] = pd + 2 * (a.W - 1) - w;
+                    for (int ia = 0; ia < nh; ++ia)
+                        for (int ib = 0; ib < nw; ++ib) store_vec<T, VEC>(outp + ((size_t)hr[ia] * Wq + wr[ib]) * C, v[u]);
+                }
             } else {
                 float o[VEC];
 #pragma unroll
@@ -250,10 +267,10 @@ template <typename T> bool k_in_stream_ok(const void* p0, const void* p1, const 
 }
 
 template <typename T> int k_in_apply_stream(const T* x, T* y, const float* stats, const float* gamma, const float* beta,
-                                            int act, float slope, int N, int P, int C, cudaStream_t st) {
+                                            int act, float slope, int N, int P, int C, cudaStream_t st, int W, int pad) {
     StreamArgs<T> a{};
     a.x = x; a.out = y; a.stats = stats; a.gamma = gamma; a.beta = beta; a.act = act; a.slope = slope;
-    a.P = P; a.C = C; a.W = P; a.halo = 0; a.invP = 1.f / (float)P;
+    a.P = P; a.C = C; a.W = pad > 0 ? W : P; a.pad = pad; a.halo = 0; a.invP = 1.f / (float)P;
     return gamma ? launch_stream<T, 0, true>(a, N, st) : launch_stream<T, 0, false>(a, N, st);
 }
 
@@ -278,7 +295,7 @@ template <typename T> int k_in_bwd_apply_stream(const T* x, const T* dy, T* dx, 
 #define INSTANTIATE(T)                                                                                                     \
     template bool k_in_stream_ok<T>(const void*, const void*, const void*, int, int);                                      \
     template int k_in_apply_stream<T>(const T*, T*, const float*, const float*, const float*, int, float, int, int, int,   \
-                                      cudaStream_t);                                                                       \
+                                      cudaStream_t, int, int);                                                             \
     template int k_in_bwd_reduce_stream<T>(const T*, const T*, const float*, const float*, const float*, float*, int,      \
                                            float, int, int, int, cudaStream_t);                                            \
     template int k_in_bwd_apply_stream<T>(const T*, const T*, T*, const float*, const float*, const float*, const float*,  \

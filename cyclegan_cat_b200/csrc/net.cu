@@ -528,7 +528,7 @@ template <typename T>
 static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
     const cg_net_s* net = c->net;
     const int N = c->N;
-    std::vector<char> stats_done(net->layers.size() + 1, 0);
+    std::vector<char> stats_done(net->layers.size() + 1, 0), rpad_done(net->layers.size() + 1, 0);
     for (size_t i = 0; i < net->layers.size(); ++i) {
         const LayerInfo& L = net->layers[i];
         if (L.skipped) continue;
@@ -593,6 +593,17 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
                 float* stats = (float*)(c->base + c->stat_off[i]);
                 if (stats_done[i]) CG_TRY(k_in_finalize(stats, N * d.cin, h * w, d.eps, st));
                 else CG_TRY(k_in_stats<T>(x, stats, N, h * w, d.cin, d.eps, st));
+                if (L.fuse_rpad >= 0) {
+                    const LayerInfo& R = net->layers[L.fuse_rpad];
+                    T* yp = (T*)c->act(R.out_t);
+                    if (R.d.pad < h && R.d.pad < w && k_in_stream_ok<T>(x, yp, nullptr, h * w, d.cin)) {
+                        CG_TRY(k_in_apply_stream<T>(x, yp, stats, L.g_off >= 0 ? params + L.g_off : nullptr,
+                                                    L.be_off >= 0 ? params + L.be_off : nullptr, L.fused_act, L.fused_slope, N,
+                                                    h * w, d.cin, st, w, R.d.pad));
+                        rpad_done[L.fuse_rpad] = 1;
+                        break;
+                    }
+                }
                 CG_TRY(k_in_apply<T>(x, y, stats, L.g_off >= 0 ? params + L.g_off : nullptr,
                                      L.be_off >= 0 ? params + L.be_off : nullptr, L.fused_act, L.fused_slope, N,
                                      h * w, d.cin, st));
@@ -602,7 +613,7 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
                 CG_TRY(k_act_fwd<T>(x, y, (size_t)N * c->sample_elems(tin), d.act, d.slope, st));
                 break;
             case CG_OP_RPAD:
-                CG_TRY(k_rpad_fwd<T>(x, y, N, h, w, d.cin, d.pad, st));
+                if (!rpad_done[i]) CG_TRY(k_rpad_fwd<T>(x, y, N, h, w, d.cin, d.pad, st));
                 break;
             case CG_OP_ADD:
                 CG_TRY(k_add<T>(x, (const T*)c->act(d.in1), y, (size_t)N * c->sample_elems(tin), st));

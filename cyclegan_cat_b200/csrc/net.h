@@ -30,6 +30,8 @@ struct LayerInfo {
     bool skipped = false;   // ACT folded into the preceding INORM
     int fused_act = CG_ACT_NONE;
     float fused_slope = 0.f;
+    int fuse_rpad = -1;            // INORM whose only consumer is a reflection pad: index of that RPAD layer (the norm's
+                                   // forward writes the padded tensor directly when the streaming kernel applies)
     bool feeds_in = false;         // the conv output feeds ONLY an instance norm (statistics fused into the conv epilogue)
     bool bias_grad_zero = false;   // the conv output feeds ONLY an instance norm: d(loss)/d(bias) == 0 exactly
     int tc = 0;             // TC_* kind: which convs run on the tcgen05 kernels in bf16 mode
