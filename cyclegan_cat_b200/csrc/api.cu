@@ -141,16 +141,28 @@ extern "C" int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode
             net->has_buffer[i + 1] = 0;
         }
     }
-    // an instance norm (+ folded activation) whose only consumer is a reflection pad writes the padded tensor itself
+    // forward fusions of the streaming instance-norm kernel (kernels_stream.cu):
+    //   INORM (+ folded activation) -> RPAD only          : the norm writes the reflection-padded tensor itself
+    //   INORM -> ADD only (the residual sum, resnet.py:34) : the norm adds the skip tensor and writes the sum, and when a
+    //                                                        reflection pad consumes the sum, its padded copy as well
+    auto uses = [&](const LayerInfo& R, int t) {
+        return R.d.in0 == t || ((R.d.op == CG_OP_ADD || R.d.op == CG_OP_CONCAT) && R.d.in1 == t);
+    };
     for (int i = 0; i < n_layers; ++i) {
         LayerInfo& L = net->layers[i];
-        if (L.d.op != CG_OP_INORM || L.skipped || L.out_t >= n_layers || net->n_consumers[L.out_t] != 1) continue;
-        for (int j = i + 1; j < n_layers; ++j) {
-            const LayerInfo& R = net->layers[j];
-            if (R.skipped) continue;
-            if (R.d.in0 == L.out_t || ((R.d.op == CG_OP_ADD || R.d.op == CG_OP_CONCAT) && R.d.in1 == L.out_t)) {
-                if (R.d.op == CG_OP_RPAD && R.d.in0 == L.out_t && R.d.pad > 0) L.fuse_rpad = j;
+        if (L.skipped || L.out_t >= n_layers) continue;
+        if (L.d.op == CG_OP_INORM && net->n_consumers[L.out_t] == 1) {
+            for (int j = i + 1; j < n_layers; ++j) {
+                const LayerInfo& R = net->layers[j];
+                if (R.skipped || !uses(R, L.out_t)) continue;
+                if (R.d.op == CG_OP_RPAD && R.d.pad > 0) L.fuse_rpad = j;
+                if (R.d.op == CG_OP_ADD && R.d.in0 != R.d.in1) L.fuse_add = j;
                 break;
+            }
+        } else if (L.d.op == CG_OP_ADD) {
+            for (int j = i + 1; j < n_layers; ++j) {
+                const LayerInfo& R = net->layers[j];
+                if (!R.skipped && R.d.op == CG_OP_RPAD && R.d.in0 == L.out_t && R.d.pad > 0) { L.fuse_rpad = j; break; }
             }
         }
     }

@@ -21,9 +21,11 @@ template <typename T> int k_in_apply(const T* x, T* y, const float* stats, const
                                      int act, float slope, int N, int P, int C, cudaStream_t st);
 // bulk-copy pipelined variants (kernels_stream.cu); k_in_stream_ok says whether a (P, C) plane qualifies
 template <typename T> bool k_in_stream_ok(const void* p0, const void* p1, const void* p2, int P, int C);
-// pad > 0: y is the reflection-padded [N][H+2p][W+2p][C] tensor (P = H*W)
-template <typename T> int k_in_apply_stream(const T* x, T* y, const float* stats, const float* gamma, const float* beta,
-                                            int act, float slope, int N, int P, int C, cudaStream_t st, int W = 0, int pad = 0);
+// y (nullable) = act(norm(x)) [+ res]; ypad (nullable, pad > 0) = the same values as the reflection-padded
+// [N][H+2p][W+2p][C] tensor (P = H*W)
+template <typename T> int k_in_apply_stream(const T* x, const T* res, T* y, T* ypad, const float* stats, const float* gamma,
+                                            const float* beta, int act, float slope, int N, int P, int C, int W, int pad,
+                                            cudaStream_t st);
 template <typename T> int k_in_bwd_reduce_stream(const T* x, const T* dy, const float* stats, const float* gamma,
                                                  const float* beta, float* sums, int act, float slope, int N, int P, int C,
                                                  cudaStream_t st);

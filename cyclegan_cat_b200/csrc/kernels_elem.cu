@@ -280,7 +280,8 @@ template <typename T> int k_in_apply(const T* x, T* y, const float* stats, const
                                      int act, float slope, int N, int P, int C, cudaStream_t st) {
     constexpr int VW = VecWidth<T>::value;
     size_t PC = (size_t)P * C;
-    if (k_in_stream_ok<T>(x, y, nullptr, P, C)) return k_in_apply_stream<T>(x, y, stats, gamma, beta, act, slope, N, P, C, st);
+    if (k_in_stream_ok<T>(x, y, nullptr, P, C))
+        return k_in_apply_stream<T>(x, nullptr, y, nullptr, stats, gamma, beta, act, slope, N, P, C, 0, 0, st);
     if (fast_cv_ok(C, VW)) {
         dim3 grid(fast_blocks(P, C, VW, N), N);
         in_apply_fast_kernel<T, VW><<<grid, 256, 0, st>>>(x, y, stats, gamma, beta, act, slope, P, C);

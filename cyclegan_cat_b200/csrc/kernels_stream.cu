@@ -31,6 +31,7 @@ struct StreamArgs {
     const T* x;
     const T* dy;
     T* out;
+    T* out2;
     const float* stats;
     const float* sums_in;
     float* sums_out;
@@ -49,10 +50,13 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 // MODE 0: out = act(x*sc + sh)                     (forward apply; one operand)
 // MODE 1: sums_out += (sum g, sum g*xhat)          (backward reduction; x and dy)
 // MODE 2: out = k*g - c1 - xhat*c2                 (backward apply; x and dy; optional zero-bordered output)
+// MODE 3: out = act(x*sc + sh) + res               (forward apply fused with the residual add; res comes in as `dy`)
+// MODES 0 and 3 write the plain tensor (`out`, nullable) and/or the reflection-padded one (`out2`, pad > 0).
 template <typename T, int VEC, int MODE, bool AFFINE>
 __global__ void __launch_bounds__(ST_THREADS, 2) in_stream_kernel(const StreamArgs<T> a) {
     extern __shared__ __align__(128) uint8_t st_smem[];
     constexpr int NOPS = MODE == 0 ? 1 : 2;
+    constexpr bool FWD = MODE == 0 || MODE == 3;
     const int S = a.stages;
     const uint32_t tiles_u32 = smem_u32(st_smem);
     const uint32_t bars_u32 = tiles_u32 + S * NOPS * ST_TILE;       // full[S], empty[S]
@@ -91,13 +95,13 @@ __global__ void __launch_bounds__(ST_THREADS, 2) in_stream_kernel(const StreamAr
     const int C = a.C, CV = C / VEC;
     const int cv = tid % CV, prow = tid / CV, rows = ST_CONSUMERS / CV;      // a tile holds 2*rows pixels
     float k0[VEC], k1[VEC], k2[MODE == 2 ? VEC : 1], k3[MODE == 2 ? VEC : 1], k4[MODE == 2 ? VEC : 1];
-    float kg[(AFFINE && MODE != 0) ? VEC : 1], ke[(AFFINE && MODE != 0) ? VEC : 1];
+    float kg[(AFFINE && !FWD) ? VEC : 1], ke[(AFFINE && !FWD) ? VEC : 1];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
         const int c = cv * VEC + j;
         const float mean = a.stats[((size_t)n * C + c) * 2], rstd = a.stats[((size_t)n * C + c) * 2 + 1];
         const float ga = AFFINE ? a.gamma[c] : 1.f, be = AFFINE ? a.beta[c] : 0.f;
-        if constexpr (MODE == 0) {
+        if constexpr (FWD) {
             k0[j] = rstd * ga;                     // y = act(v*k0 + k1)
             k1[j] = be - mean * k0[j];
         } else {
@@ -117,9 +121,9 @@ __global__ void __launch_bounds__(ST_THREADS, 2) in_stream_kernel(const StreamAr
         for (int j = 0; j < VEC; ++j) acc_s[j] = acc_ss[j] = 0.f;
     }
     const int Wp = a.W + 2 * a.halo;
-    const size_t out_img = MODE == 2 && a.halo > 0 ? (size_t)(a.P / a.W + 2 * a.halo) * Wp * C
-                           : (MODE == 0 && a.pad > 0 ? (size_t)(a.P / a.W + 2 * a.pad) * (a.W + 2 * a.pad) * C : img_elems);
-    T* outp = MODE == 1 ? nullptr : a.out + (size_t)n * out_img + (size_t)cv * VEC;
+    const size_t out_img = MODE == 2 && a.halo > 0 ? (size_t)(a.P / a.W + 2 * a.halo) * Wp * C : img_elems;
+    T* outp = (MODE == 1 || !a.out) ? nullptr : a.out + (size_t)n * out_img + (size_t)cv * VEC;
+    T* out2p = (FWD && a.pad > 0) ? a.out2 + (size_t)n * (a.P / a.W + 2 * a.pad) * (a.W + 2 * a.pad) * C + (size_t)cv * VEC : nullptr;
 
     int s = 0;
     uint32_t ph = 0;
@@ -138,12 +142,14 @@ __global__ void __launch_bounds__(ST_THREADS, 2) in_stream_kernel(const StreamAr
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int p = t * 2 * rows + u * rows + prow;              // pixel index inside the image
-            if constexpr (MODE == 0) {
+            if constexpr (FWD) {
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) v[u][j] = act_fwd(fmaf(v[u][j], k0[j], k1[j]), a.act, a.slope);
-                if (a.pad == 0) {
-                    store_vec<T, VEC>(outp + (size_t)p * C, v[u]);
-                } else {
+                for (int j = 0; j < VEC; ++j) {
+                    v[u][j] = act_fwd(fmaf(v[u][j], k0[j], k1[j]), a.act, a.slope);
+                    if constexpr (MODE == 3) v[u][j] += g[u][j];
+                }
+                if (outp) store_vec<T, VEC>(outp + (size_t)p * C, v[u]);
+                if (out2p) {
                     // reflection padding (cyclegan/resnet.py:5-23, tf.pad REFLECT): interior pixel (h, w) lands at
                     // (h+p, w+p) and, when it lies within p of an edge (but not on it), at its mirror image(s) too
                     const int pd = a.pad, H = a.P / a.W, Wq = a.W + 2 * pd;
@@ -155,7 +161,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) in_stream_kernel(const StreamAr
                     if (w >= 1 && w <= pd) wr[nw++] = pd - w;
                     if (w >= a.W - 1 - pd && w <= a.W - 2) wr[nw++] = pd + 2 * (a.W - 1) - w;
                     for (int ia = 0; ia < nh; ++ia)
-                        for (int ib = 0; ib < nw; ++ib) store_vec<T, VEC>(outp + ((size_t)hr[ia] * Wq + wr[ib]) * C, v[u]);
+                        for (int ib = 0; ib < nw; ++ib) store_vec<T, VEC>(out2p + ((size_t)hr[ia] * Wq + wr[ib]) * C, v[u]);
                 }
             } else {
                 float o[VEC];
@@ -266,11 +272,13 @@ template <typename T> bool k_in_stream_ok(const void* p0, const void* p1, const 
     return !(((uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2) & 15);
 }
 
-template <typename T> int k_in_apply_stream(const T* x, T* y, const float* stats, const float* gamma, const float* beta,
-                                            int act, float slope, int N, int P, int C, cudaStream_t st, int W, int pad) {
+template <typename T> int k_in_apply_stream(const T* x, const T* res, T* y, T* ypad, const float* stats, const float* gamma,
+                                            const float* beta, int act, float slope, int N, int P, int C, int W, int pad,
+                                            cudaStream_t st) {
     StreamArgs<T> a{};
-    a.x = x; a.out = y; a.stats = stats; a.gamma = gamma; a.beta = beta; a.act = act; a.slope = slope;
-    a.P = P; a.C = C; a.W = pad > 0 ? W : P; a.pad = pad; a.halo = 0; a.invP = 1.f / (float)P;
+    a.x = x; a.dy = res; a.out = y; a.out2 = ypad; a.stats = stats; a.gamma = gamma; a.beta = beta; a.act = act; a.slope = slope;
+    a.P = P; a.C = C; a.W = (ypad && pad > 0) ? W : P; a.pad = ypad ? pad : 0; a.halo = 0; a.invP = 1.f / (float)P;
+    if (res) return gamma ? launch_stream<T, 3, true>(a, N, st) : launch_stream<T, 3, false>(a, N, st);
     return gamma ? launch_stream<T, 0, true>(a, N, st) : launch_stream<T, 0, false>(a, N, st);
 }
 
@@ -294,8 +302,8 @@ template <typename T> int k_in_bwd_apply_stream(const T* x, const T* dy, T* dx, 
 
 #define INSTANTIATE(T)                                                                                                     \
     template bool k_in_stream_ok<T>(const void*, const void*, const void*, int, int);                                      \
-    template int k_in_apply_stream<T>(const T*, T*, const float*, const float*, const float*, int, float, int, int, int,   \
-                                      cudaStream_t, int, int);                                                             \
+    template int k_in_apply_stream<T>(const T*, const T*, T*, T*, const float*, const float*, const float*, int, float,    \
+                                      int, int, int, int, int, cudaStream_t);                                              \
     template int k_in_bwd_reduce_stream<T>(const T*, const T*, const float*, const float*, const float*, float*, int,      \
                                            float, int, int, int, cudaStream_t);                                            \
     template int k_in_bwd_apply_stream<T>(const T*, const T*, T*, const float*, const float*, const float*, const float*,  \

@@ -528,7 +528,7 @@ template <typename T>
 static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
     const cg_net_s* net = c->net;
     const int N = c->N;
-    std::vector<char> stats_done(net->layers.size() + 1, 0), rpad_done(net->layers.size() + 1, 0);
+    std::vector<char> stats_done(net->layers.size() + 1, 0), fused_done(net->layers.size() + 1, 0);
     for (size_t i = 0; i < net->layers.size(); ++i) {
         const LayerInfo& L = net->layers[i];
         if (L.skipped) continue;
@@ -593,14 +593,34 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
                 float* stats = (float*)(c->base + c->stat_off[i]);
                 if (stats_done[i]) CG_TRY(k_in_finalize(stats, N * d.cin, h * w, d.eps, st));
                 else CG_TRY(k_in_stats<T>(x, stats, N, h * w, d.cin, d.eps, st));
+                const float* gam = L.g_off >= 0 ? params + L.g_off : nullptr;
+                const float* bet = L.be_off >= 0 ? params + L.be_off : nullptr;
                 if (L.fuse_rpad >= 0) {
                     const LayerInfo& R = net->layers[L.fuse_rpad];
                     T* yp = (T*)c->act(R.out_t);
                     if (R.d.pad < h && R.d.pad < w && k_in_stream_ok<T>(x, yp, nullptr, h * w, d.cin)) {
-                        CG_TRY(k_in_apply_stream<T>(x, yp, stats, L.g_off >= 0 ? params + L.g_off : nullptr,
-                                                    L.be_off >= 0 ? params + L.be_off : nullptr, L.fused_act, L.fused_slope, N,
-                                                    h * w, d.cin, st, w, R.d.pad));
-                        rpad_done[L.fuse_rpad] = 1;
+                        CG_TRY(k_in_apply_stream<T>(x, nullptr, nullptr, yp, stats, gam, bet, L.fused_act, L.fused_slope, N, h * w,
+                                                    d.cin, w, R.d.pad, st));
+                        fused_done[L.fuse_rpad] = 1;
+                        break;
+                    }
+                }
+                if (L.fuse_add >= 0) {
+                    const LayerInfo& Ad = net->layers[L.fuse_add];
+                    const int other = Ad.d.in0 == tout ? Ad.d.in1 : Ad.d.in0;
+                    const T* res = (const T*)c->act(other);
+                    T* ys = (T*)c->act(Ad.out_t);
+                    T* yp = nullptr;
+                    int pad = 0;
+                    if (Ad.fuse_rpad >= 0 && net->layers[Ad.fuse_rpad].d.pad < h && net->layers[Ad.fuse_rpad].d.pad < w) {
+                        yp = (T*)c->act(net->layers[Ad.fuse_rpad].out_t);
+                        pad = net->layers[Ad.fuse_rpad].d.pad;
+                    }
+                    if (other <= (int)i && k_in_stream_ok<T>(x, res, ys, h * w, d.cin) && !((uintptr_t)yp & 15)) {
+                        CG_TRY(k_in_apply_stream<T>(x, res, ys, yp, stats, gam, bet, L.fused_act, L.fused_slope, N, h * w, d.cin, w,
+                                                    pad, st));
+                        fused_done[L.fuse_add] = 1;
+                        if (yp) fused_done[Ad.fuse_rpad] = 1;
                         break;
                     }
                 }
@@ -613,10 +633,10 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
                 CG_TRY(k_act_fwd<T>(x, y, (size_t)N * c->sample_elems(tin), d.act, d.slope, st));
                 break;
             case CG_OP_RPAD:
-                if (!rpad_done[i]) CG_TRY(k_rpad_fwd<T>(x, y, N, h, w, d.cin, d.pad, st));
+                if (!fused_done[i]) CG_TRY(k_rpad_fwd<T>(x, y, N, h, w, d.cin, d.pad, st));
                 break;
             case CG_OP_ADD:
-                CG_TRY(k_add<T>(x, (const T*)c->act(d.in1), y, (size_t)N * c->sample_elems(tin), st));
+                if (!fused_done[i]) CG_TRY(k_add<T>(x, (const T*)c->act(d.in1), y, (size_t)N * c->sample_elems(tin), st));
                 break;
             case CG_OP_CONCAT: {
                 int ca = net->chan[d.in0], cb = net->chan[d.in1];

@@ -31,7 +31,9 @@ struct LayerInfo {
     int fused_act = CG_ACT_NONE;
     float fused_slope = 0.f;
     int fuse_rpad = -1;            // INORM whose only consumer is a reflection pad: index of that RPAD layer (the norm's
-                                   // forward writes the padded tensor directly when the streaming kernel applies)
+                                   // forward writes the padded tensor directly when the streaming kernel applies);
+                                   // ADD: index of a reflection pad among its consumers (written as a second output)
+    int fuse_add = -1;             // INORM whose only consumer is a residual ADD: index of that ADD layer
     bool feeds_in = false;         // the conv output feeds ONLY an instance norm (statistics fused into the conv epilogue)
     bool bias_grad_zero = false;   // the conv output feeds ONLY an instance norm: d(loss)/d(bias) == 0 exactly
     int tc = 0;             // TC_* kind: which convs run on the tcgen05 kernels in bf16 mode
