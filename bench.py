@@ -269,6 +269,10 @@ def run_gpu(args, wl):
         if agg:
             k, a = max(agg.items(), key=lambda kv: kv[1][0])
             dom = dict(ms=a[0], flops=a[1], n=a[2], geom=f"taps={k[0]} k_chunks={k[1]} n_tile={k[2]}")
+        keep = os.environ.get("CG_KEEP_PROF")             # copy the per-launch CSV somewhere (tools/prof_layers.py reads it)
+        if keep:
+            import shutil
+            shutil.copy(prof_csv, keep)
         os.remove(prof_csv)
     except Exception as e:      # the aggregate below is still reported
         dom["geom"] = f"unavailable ({type(e).__name__})"
