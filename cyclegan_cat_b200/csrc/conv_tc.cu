@@ -160,8 +160,12 @@ static constexpr int TMEM_COLS = 512;
 // ------------------------------------------------------------------------------------------
 // BK16 (the 16-channel-group SWIZZLE_32B mode of the U-Net layers) is a template parameter: as a run-time branch it cost
 // the 64-channel instance 19 % (1216 -> 987 TFLOP/s at the C3 trunk shape, same box, back to back).
-template <bool BK16>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+// DUAL: the variant for N tiles <= 128 columns, two CTAs per SM (6 warps, <= 110 KB of shared memory and 256 TMEM columns
+// each).  With few K steps per tile the single MMA-issuing thread's chain (mbarrier wait -> MMAs -> commit, ~600 cycles
+// per K step; ~2100 cycles per 3-step tile even with loads and epilogue switched off) bounds the SM, not the tensor pipe;
+// two resident CTAs overlap their chains.
+template <bool BK16, bool DUAL>
+__global__ void __launch_bounds__(DUAL ? TC_THREADS : CONV_THREADS, DUAL ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                bf16* __restrict__ out, const float* __restrict__ bias, const TcConvArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -183,10 +187,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         tma_prefetch_desc(&mapA);
         tma_prefetch_desc(&mapB);
         for (int s = 0; s < S; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), DUAL ? 4 : EPI_WARPS); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    constexpr uint32_t ACC_COLS = DUAL ? 128u : 256u;      // TMEM columns per accumulator (two accumulators)
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * ACC_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -227,7 +232,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
                 mbar_wait(tempty(acc), acc_ph ^ 1u);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * ACC_COLS;
                 for (int ks = 0; ks < ksteps; ++ks) {
                     mbar_wait(full(s), ph);
                     tc_fence_after();
@@ -255,7 +260,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
     } else {
         const int q = warp & 3;                   // TMEM lane quarter this warp may read
-        const int half = (warp - 2) >> 2;         // two warps per quarter: even / odd 32-column chunks
+        const int half = (warp - 2) >> 2;         // two warps per quarter: even / odd 32-column chunks (DUAL: one warp, all chunks)
         float* tr = stat_sm + (warp - 2) * (32 * 17);
         int it = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -277,8 +282,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
             mbar_wait(tfull(acc), acc_ph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
-            for (int c0 = half * 32; c0 < a.bn; c0 += 64) {
+            const uint32_t taddr = tmem_base + (uint32_t)acc * ACC_COLS + ((uint32_t)(q * 32) << 16);
+            for (int c0 = half * 32; c0 < a.bn; c0 += (DUAL ? 32 : 64)) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
                 const int cols = BK16 ? min(32, a.bn - c0) : 32;          // 16 when the N tile is not a multiple of 32 (BK16 only)
@@ -347,7 +352,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        tmem_dealloc(tmem_base, 2 * ACC_COLS);
     }
 }
 
@@ -983,23 +988,32 @@ int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, const CUten
         return CG_OK;
     }
     const int stage_b = a.bk16 ? a.groups * (4096 + a.bn * 32) : (A_TILE_BYTES + a.bn * 128);
+    const bool dual = a.bn <= 128 && 2 * stage_b + 1024 + 256 + EPI_SCRATCH / 2 <= 110 * 1024;
     {
-        int sN = (227 * 1024 - 1024 - 256 - EPI_SCRATCH) / stage_b;
+        int sN = ((dual ? 110 : 227) * 1024 - 1024 - 256 - (dual ? EPI_SCRATCH / 2 : EPI_SCRATCH)) / stage_b;
         a.stages = sN > 8 ? 8 : sN;
     }
     a.idesc = make_idesc(128, a.bn, 0, 0);
-    const size_t smem = (size_t)a.stages * stage_b + 1024 + 256 + EPI_SCRATCH;
+    const size_t smem = (size_t)a.stages * stage_b + 1024 + 256 + (dual ? EPI_SCRATCH / 2 : EPI_SCRATCH);
     static bool attr_set = false;
     if (!attr_set) {
-        CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         attr_set = true;
     }
     const int total = a.nb * a.tiles_per_img * a.n_blocks_n;
-    int grid = total < num_sms() ? total : num_sms();
+    const int slots = (dual ? 2 : 1) * num_sms();
+    int grid = total < slots ? total : slots;
     int pi = prof_begin(st);
-    if (a.bk16) conv_tc_kernel<true><<<grid, CONV_THREADS, smem, st>>>(*mapA, *mapB, out, bias, a);
-    else conv_tc_kernel<false><<<grid, CONV_THREADS, smem, st>>>(*mapA, *mapB, out, bias, a);
+    if (dual) {
+        if (a.bk16) conv_tc_kernel<true, true><<<grid, TC_THREADS, smem, st>>>(*mapA, *mapB, out, bias, a);
+        else conv_tc_kernel<false, true><<<grid, TC_THREADS, smem, st>>>(*mapA, *mapB, out, bias, a);
+    } else {
+        if (a.bk16) conv_tc_kernel<true, false><<<grid, CONV_THREADS, smem, st>>>(*mapA, *mapB, out, bias, a);
+        else conv_tc_kernel<false, false><<<grid, CONV_THREADS, smem, st>>>(*mapA, *mapB, out, bias, a);
+    }
     prof_end(pi, st, flops, prof_key(1, a.n_taps, a.cchunks, a.bn, a.tiles_per_img, a.nb));
     CG_LAUNCH_CHECK();
     return CG_OK;
@@ -1008,12 +1022,15 @@ int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, const CUten
 int tc_wgrad_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* dw, TcWgradArgs a, double flops,
                     cudaStream_t st) {
     const int stage = (2 + a.bn / 64) * 8192;
-    int s = (227 * 1024 - 2048) / stage;
+    // N <= 128: a K step is bound by the issue chain (mbarrier wait -> 4 MMAs -> commit, ~600 cycles), not by the tensor
+    // pipe, so two CTAs share an SM (<= 110 KB of shared memory and 256 TMEM columns each) and overlap their chains
+    const int per_sm = a.bn <= 128 ? 2 : 1;
+    int s = ((per_sm == 2 ? 110 : 227) * 1024 - 2048) / stage;
     a.stages = s > 6 ? 6 : s;
     a.idesc = make_idesc(128, a.bn, 1, 1);
     const int units = a.n_taps * a.a_blocks * a.b_blocks;
     const int total_chunks = a.nb * a.chunks_per_img;
-    int splits = num_sms() / units;
+    int splits = per_sm * num_sms() / units;
     if (splits < 1) splits = 1;
     if (splits > total_chunks) splits = total_chunks;
     a.splits = splits;
