@@ -1050,12 +1050,13 @@ int tc_wgrad_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* dw
 int tc_wgrad16_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* dw, TcWgrad16Args a, double flops,
                       cudaStream_t st) {
     const int stage = (8 + a.Cout / 16) * 2048;
-    int s = (227 * 1024 - 2048) / stage;
+    const int per_sm = a.Cout <= 128 ? 2 : 1;              // two resident CTAs overlap their issue chains (see tc_wgrad_launch)
+    int s = ((per_sm == 2 ? 110 : 227) * 1024 - 2048) / stage;
     a.stages = s > 8 ? 8 : s;
     a.idesc = make_idesc(128, a.Cout, 1, 1);
     a.m_blocks = (a.n_taps * a.Cin + 127) / 128;
     const int total_chunks = a.nb * a.chunks_per_img;
-    int splits = (2 * num_sms()) / a.m_blocks;              // ~2 CTAs per SM in total: the units are short
+    int splits = (2 * per_sm * num_sms()) / a.m_blocks;     // ~2 waves of CTAs: the units are short
     if (splits < 1) splits = 1;
     if (splits > total_chunks) splits = total_chunks;
     a.splits = splits;
