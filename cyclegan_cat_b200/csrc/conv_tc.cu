@@ -171,8 +171,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t a_bytes = BK16 ? (uint32_t)a.groups * 4096u : (uint32_t)A_TILE_BYTES;
-    const uint32_t stage_bytes = BK16 ? (uint32_t)a.groups * (4096u + (uint32_t)a.bn * 32u) : A_TILE_BYTES + (uint32_t)a.bn * 128u;
+    // bk16: a K step holds `kg` 16-channel groups = `groups` channel groups of one tap, or (tps > 1) all cin16 groups of tps taps
+    const uint32_t kg = BK16 ? (uint32_t)(a.tps > 1 ? a.tps * a.cin16 : a.groups) : 0u;
+    const uint32_t a_bytes = BK16 ? kg * 4096u : (uint32_t)A_TILE_BYTES;
+    const uint32_t stage_bytes = BK16 ? kg * (4096u + (uint32_t)a.bn * 32u) : A_TILE_BYTES + (uint32_t)a.bn * 128u;
     const int S = a.stages;
     const uint32_t bar0 = smem0 + S * stage_bytes;          // full[S], empty[S], tfull[2], tempty[2], tmem ptr
     auto full = [&](int s) { return bar0 + 8u * s; };
@@ -198,7 +200,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     const int total_tiles = a.nb * a.tiles_per_img * a.n_blocks_n;
-    const int ksteps = a.n_taps * a.cchunks;       // bk16: cchunks = K steps per tap (blocks of `groups` 16-channel groups)
+    // bk16: cchunks = K steps per tap (blocks of `groups` 16-channel groups), or several taps per K step
+    const int ksteps = (BK16 && a.tps > 1) ? (a.n_taps + a.tps - 1) / a.tps : a.n_taps * a.cchunks;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -208,6 +211,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const int img = a.n0 + mt / a.tiles_per_img, ti = mt % a.tiles_per_img;
                 const int w0 = (ti % a.tiles_w) * a.Wb, h0 = (ti / a.tiles_w) * a.Hb;
                 for (int ks = 0; ks < ksteps; ++ks) {
+                    if constexpr (BK16) {
+                        if (a.tps > 1) {        // Cin <= 64: `tps` taps per K step, one A box each, ONE B box of tps*bn weight rows
+                            const int t0 = ks * a.tps, nt = min(a.tps, a.n_taps - t0);
+                            mbar_wait(empty(s), ph ^ 1u);
+                            const uint32_t sa = smem0 + s * stage_bytes;
+                            mbar_expect_tx(full(s), (uint32_t)(nt * a.cin16) * 4096u + kg * (uint32_t)a.bn * 32u);
+                            for (int j = 0; j < nt; ++j)
+                                tma_load_5d(sa + (uint32_t)(j * a.cin16) * 4096u, &mapA, full(s), 0, w0 + a.dw[t0 + j], h0 + a.dh[t0 + j],
+                                            0, img);
+                            tma_load_3d(sa + a_bytes, &mapB, full(s), 0, a.tb[t0] * a.b_rows_per_tap, 0);
+                            if (++s == S) { s = 0; ph ^= 1u; }
+                            continue;
+                        }
+                    }
                     const int tap = ks / a.cchunks, cc = ks - tap * a.cchunks;
                     mbar_wait(empty(s), ph ^ 1u);
                     mbar_expect_tx(full(s), stage_bytes);
@@ -238,6 +255,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     tc_fence_after();
                     const uint32_t sa = smem0 + s * stage_bytes;
                     if constexpr (BK16) {       // one K = 16 MMA per 16-channel group
+                        if (a.tps > 1) {
+                            const int nt = min(a.tps, a.n_taps - ks * a.tps);
+                            for (int j = 0; j < nt; ++j)
+                                for (int cg = 0; cg < a.cin16; ++cg)
+                                    umma_bf16(d_tmem, make_smem_desc32(sa + (uint32_t)(j * a.cin16 + cg) * 4096u),
+                                              make_smem_desc32(sa + a_bytes + (uint32_t)(cg * a.tps + j) * (uint32_t)a.bn * 32u), a.idesc,
+                                              (uint32_t)((ks | j | cg) != 0));
+                            umma_commit(empty(s));
+                            if (++s == S) { s = 0; ph ^= 1u; }
+                            continue;
+                        }
                         const int cc = ks % a.cchunks;
                         const int ng = min(a.groups, a.cin16 - cc * a.groups);
                         for (int gq = 0; gq < ng; ++gq)
@@ -987,7 +1015,7 @@ int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, const CUten
         CG_LAUNCH_CHECK();
         return CG_OK;
     }
-    const int stage_b = a.bk16 ? a.groups * (4096 + a.bn * 32) : (A_TILE_BYTES + a.bn * 128);
+    const int stage_b = a.bk16 ? (a.tps > 1 ? a.tps * a.cin16 : a.groups) * (4096 + a.bn * 32) : (A_TILE_BYTES + a.bn * 128);
     const bool dual = a.bn <= 128 && 2 * stage_b + 1024 + 256 + EPI_SCRATCH / 2 <= 110 * 1024;
     {
         int sN = ((dual ? 110 : 227) * 1024 - 1024 - 256 - (dual ? EPI_SCRATCH / 2 : EPI_SCRATCH)) / stage_b;

@@ -14,6 +14,7 @@ struct TcConvArgs {
     int stages;
     uint32_t idesc;
     int bk16, groups, cin16;                    // 16-channel K groups (SWIZZLE_32B): `groups` per K step, cin16 = Cin/16 in total
+    int tps;                                    // bk16, Cin <= 64: filter taps per K step (each its own A box, ONE B box)
     float* stats;                               // nullable: [N][Cout][2] running (sum, sum of squares) of the outputs
     // per K-loop tap: TMA coordinate offsets into the 5-D activation view (c, w, p, h, n) and the weight row block
     short dc[49], dw[49], dp[49], dh[49], tb[49];

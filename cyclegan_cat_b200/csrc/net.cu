@@ -216,8 +216,17 @@ static int make_conv16(TcConvLaunch& Ln, const void* in, int cin_k, int map_w, i
     a.nb = N; a.out_H = out_h; a.out_W = out_w; a.Cout = n_out; a.out_sy = a.out_sx = 1;
     a.b_rows_per_tap = n_out;
     for (int tp = 0; tp < n_taps; ++tp) { a.tb[tp] = (short)tp; a.dw[tp] = dw[tp]; a.dh[tp] = dh[tp]; }
+    // few input channels: several taps share a K step (fewer barrier round trips and one weight box for all of them);
+    // limits: 8 sixteen-channel groups per step, a weight box of <= 256 rows
+    a.tps = 1;
+    if (a.cchunks == 1) {
+        int tps = 8 / a.cin16;
+        if (tps * n_out > 256) tps = 256 / n_out;
+        if (tps > n_taps) tps = n_taps;
+        if (tps > 1) a.tps = tps;
+    }
     CG_TRY(tc_make_map_act16(&Ln.mapA, in, cin_k, map_w, map_h, N, a.Wb, a.Hb, a.groups));
-    CG_TRY(tc_make_map_w16(&Ln.mapB, wmat, cin_k, n_taps * n_out, n_out, a.groups));
+    CG_TRY(tc_make_map_w16(&Ln.mapB, wmat, cin_k, n_taps * n_out, a.tps * n_out, a.groups));
     Ln.mapB2 = Ln.mapB;
     return CG_OK;
 }
