@@ -26,6 +26,7 @@ template <typename T> bool k_in_stream_ok(const void* p0, const void* p1, const 
 template <typename T> int k_in_apply_stream(const T* x, const T* res, T* y, T* ypad, const float* stats, const float* gamma,
                                             const float* beta, int act, float slope, int N, int P, int C, int W, int pad,
                                             cudaStream_t st);
+template <typename T> int k_in_stats_stream(const T* x, float* sums, int N, int P, int C, cudaStream_t st);
 template <typename T> int k_in_bwd_reduce_stream(const T* x, const T* dy, const float* stats, const float* gamma,
                                                  const float* beta, float* sums, int act, float slope, int N, int P, int C,
                                                  cudaStream_t st);

@@ -129,6 +129,10 @@ int k_in_finalize(float* stats, int NC, int P, float eps, cudaStream_t st) {
 
 template <typename T> int k_in_stats(const T* x, float* stats, int N, int P, int C, float eps, cudaStream_t st) {
     CG_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)N * C, st));
+    if (k_in_stream_ok<T>(x, nullptr, nullptr, P, C)) {
+        CG_TRY(k_in_stats_stream<T>(x, stats, N, P, C, st));
+        return k_in_finalize(stats, N * C, P, eps, st);
+    }
     dim3 grid; int pchunk;
     in_reduce_grid(N, P, C, grid, pchunk);
     in_reduce_kernel<T, 0><<<grid, 256, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, stats, P, C, pchunk, 0, 0.f);

@@ -51,12 +51,14 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 // MODE 1: sums_out += (sum g, sum g*xhat)          (backward reduction; x and dy)
 // MODE 2: out = k*g - c1 - xhat*c2                 (backward apply; x and dy; optional zero-bordered output)
 // MODE 3: out = act(x*sc + sh) + res               (forward apply fused with the residual add; res comes in as `dy`)
+// MODE 4: sums_out += (sum x, sum x^2)             (forward statistics; one operand)
 // MODES 0 and 3 write the plain tensor (`out`, nullable) and/or the reflection-padded one (`out2`, pad > 0).
 template <typename T, int VEC, int MODE, bool AFFINE>
 __global__ void __launch_bounds__(ST_THREADS, 2) in_stream_kernel(const StreamArgs<T> a) {
     extern __shared__ __align__(128) uint8_t st_smem[];
-    constexpr int NOPS = MODE == 0 ? 1 : 2;
+    constexpr int NOPS = (MODE == 0 || MODE == 4) ? 1 : 2;
     constexpr bool FWD = MODE == 0 || MODE == 3;
+    constexpr bool RED = MODE == 1 || MODE == 4;      // reductions: per-thread partial sums, CTA-level combine, atomics
     const int S = a.stages;
     const uint32_t tiles_u32 = smem_u32(st_smem);
     const uint32_t bars_u32 = tiles_u32 + S * NOPS * ST_TILE;       // full[S], empty[S]
@@ -98,6 +100,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) in_stream_kernel(const StreamAr
     float kg[(AFFINE && !FWD) ? VEC : 1], ke[(AFFINE && !FWD) ? VEC : 1];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
+        if constexpr (MODE == 4) { k0[j] = k1[j] = 0.f; continue; }
         const int c = cv * VEC + j;
         const float mean = a.stats[((size_t)n * C + c) * 2], rstd = a.stats[((size_t)n * C + c) * 2 + 1];
         const float ga = AFFINE ? a.gamma[c] : 1.f, be = AFFINE ? a.beta[c] : 0.f;
@@ -115,14 +118,14 @@ __global__ void __launch_bounds__(ST_THREADS, 2) in_stream_kernel(const StreamAr
             }
         }
     }
-    float acc_s[MODE == 1 ? VEC : 1], acc_ss[MODE == 1 ? VEC : 1];
-    if constexpr (MODE == 1) {
+    float acc_s[RED ? VEC : 1], acc_ss[RED ? VEC : 1];
+    if constexpr (RED) {
 #pragma unroll
         for (int j = 0; j < VEC; ++j) acc_s[j] = acc_ss[j] = 0.f;
     }
     const int Wp = a.W + 2 * a.halo;
     const size_t out_img = MODE == 2 && a.halo > 0 ? (size_t)(a.P / a.W + 2 * a.halo) * Wp * C : img_elems;
-    T* outp = (MODE == 1 || !a.out) ? nullptr : a.out + (size_t)n * out_img + (size_t)cv * VEC;
+    T* outp = (RED || !a.out) ? nullptr : a.out + (size_t)n * out_img + (size_t)cv * VEC;
     T* out2p = (FWD && a.pad > 0) ? a.out2 + (size_t)n * (a.P / a.W + 2 * a.pad) * (a.W + 2 * a.pad) * C + (size_t)cv * VEC : nullptr;
 
     int s = 0;
@@ -142,7 +145,13 @@ __global__ void __launch_bounds__(ST_THREADS, 2) in_stream_kernel(const StreamAr
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int p = t * 2 * rows + u * rows + prow;              // pixel index inside the image
-            if constexpr (FWD) {
+            if constexpr (MODE == 4) {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    acc_s[j] += v[u][j];
+                    acc_ss[j] = fmaf(v[u][j], v[u][j], acc_ss[j]);
+                }
+            } else if constexpr (FWD) {
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) {
                     v[u][j] = act_fwd(fmaf(v[u][j], k0[j], k1[j]), a.act, a.slope);
@@ -212,7 +221,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) in_stream_kernel(const StreamAr
         }
     }
 
-    if constexpr (MODE == 1) {                      // CTA-level reduction over the pixel rows, then one atomic per channel
+    if constexpr (RED) {                            // CTA-level reduction over the pixel rows, then one atomic per channel
         consumer_sync();                            // every consumer is past its last tile read: reuse the ring
         float* red = reinterpret_cast<float*>(st_smem);              // [256][2*VEC+1]
         constexpr int RS = 2 * VEC + 1;
@@ -241,11 +250,11 @@ inline bool cv_ok(int C, int VW) {
 template <typename T, int MODE, bool AFFINE>
 int launch_stream(StreamArgs<T>& a, int N, cudaStream_t st) {
     constexpr int VW = VecWidth<T>::value;
-    constexpr int NOPS = MODE == 0 ? 1 : 2;
+    constexpr int NOPS = (MODE == 0 || MODE == 4) ? 1 : 2;
     a.tiles_per_img = (int)(((size_t)a.P * a.C * sizeof(T)) / ST_TILE);
-    a.stages = MODE == 0 ? 8 : 6;
+    a.stages = NOPS == 1 ? 8 : 6;
     size_t smem = (size_t)a.stages * NOPS * ST_TILE + 16 * a.stages;
-    if (MODE == 1) {
+    if (MODE == 1 || MODE == 4) {
         const size_t red = (size_t)ST_CONSUMERS * (2 * VW + 1) * sizeof(float);
         if (smem < red) smem = red;
     }
@@ -282,6 +291,12 @@ template <typename T> int k_in_apply_stream(const T* x, const T* res, T* y, T* y
     return gamma ? launch_stream<T, 0, true>(a, N, st) : launch_stream<T, 0, false>(a, N, st);
 }
 
+template <typename T> int k_in_stats_stream(const T* x, float* sums, int N, int P, int C, cudaStream_t st) {
+    StreamArgs<T> a{};
+    a.x = x; a.sums_out = sums; a.P = P; a.C = C; a.W = P; a.invP = 1.f / (float)P;
+    return launch_stream<T, 4, false>(a, N, st);
+}
+
 template <typename T> int k_in_bwd_reduce_stream(const T* x, const T* dy, const float* stats, const float* gamma,
                                                  const float* beta, float* sums, int act, float slope, int N, int P, int C,
                                                  cudaStream_t st) {
@@ -301,6 +316,7 @@ template <typename T> int k_in_bwd_apply_stream(const T* x, const T* dy, T* dx, 
 }
 
 #define INSTANTIATE(T)                                                                                                     \
+    template int k_in_stats_stream<T>(const T*, float*, int, int, int, cudaStream_t);                                      \
     template bool k_in_stream_ok<T>(const void*, const void*, const void*, int, int);                                      \
     template int k_in_apply_stream<T>(const T*, const T*, T*, T*, const float*, const float*, const float*, int, float,    \
                                       int, int, int, int, int, cudaStream_t);                                              \

@@ -546,7 +546,10 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
         const T* x = (const T*)c->act(tin);
         // a tensor-core conv that feeds only an instance norm accumulates that norm's statistics in its epilogue
         float* fused_stats = nullptr;
-        if (c->tc[i].on && L.feeds_in && L.tc != TC_HEAD && i + 1 < net->layers.size()) {
+        // ... when its main loop is long enough to hide the extra epilogue work (the column sums double the epilogue of a
+        // 32-column chunk); the 3-K-step stem is faster with the separate streaming statistics pass
+        const bool long_k = L.tc != TC_STEM;
+        if (c->tc[i].on && L.feeds_in && L.tc != TC_HEAD && long_k && i + 1 < net->layers.size()) {
             fused_stats = (float*)(c->base + c->stat_off[i + 1]);
             CG_CUDA(cudaMemsetAsync(fused_stats, 0, sizeof(float) * 2 * (size_t)N * d.cout, st));
             stats_done[i + 1] = 1;
