@@ -129,6 +129,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 // column sums of a 32 x 32 tile held one row per lane (v[j] = column j of this lane's row): recursive halving with
 // shuffles -- after the 5 steps lane L holds the sum of column L.  31 shuffles.
+// (a.lo + b.lo, a.hi + b.hi) of two packed bf16 pairs, summed in fp32 and rounded once
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+    const float lo = __uint_as_float(a << 16) + __uint_as_float(b << 16);
+    const float hi = __uint_as_float(a & 0xffff0000u) + __uint_as_float(b & 0xffff0000u);
+    return pack_bf16x2(lo, hi);
+}
+
 __device__ __forceinline__ float warp_colsum32(float (&s)[32], int lane) {
 #pragma unroll
     for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
@@ -302,6 +309,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const bool valid = ow < a.out_wvalid && oh < a.out_hvalid;
             bf16* dst = out + (((size_t)img * a.out_H + (oh * a.out_sy + a.out_oy)) * a.out_W + (ow * a.out_sx + a.out_ox)) * a.Cout +
                         (size_t)nblk * a.bn;
+            if (a.fold_pad > 0) {                 // interior pixel of a reflection-padded grid -> the unpadded gradient
+                const int fp = a.fold_pad, Hi = a.out_H - 2 * fp, Wi = a.out_W - 2 * fp;
+                if (oh >= fp && oh < fp + Hi && ow >= fp && ow < fp + Wi)
+                    dst = reinterpret_cast<bf16*>(reinterpret_cast<unsigned long long>(
+                              a.out2 + (((size_t)img * Hi + (oh - fp)) * Wi + (ow - fp)) * a.Cout + (size_t)nblk * a.bn) |
+                          (unsigned long long)(a.fold_acc != 0));      // bit 0 of the (16-byte aligned) pointer = accumulate
+            }
             bf16* rowptr[4];                      // output rows this lane stores: row (lane/4 + 8i) of the warp's 32, or null
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -337,8 +351,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int r = (lane >> 2) + 8 * i;
-                        const uint4 val = stg[r * 4 + (g ^ ((r >> 1) & 3))];
-                        if (rowptr[i] && g * 8 < cols) *reinterpret_cast<uint4*>(rowptr[i] + c0 + g * 8) = val;
+                        uint4 val = stg[r * 4 + (g ^ ((r >> 1) & 3))];
+                        if (rowptr[i] && g * 8 < cols) {
+                            const unsigned long long pv = reinterpret_cast<unsigned long long>(rowptr[i]);
+                            uint4* gp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(pv & ~1ull) + c0 + g * 8);
+                            if (pv & 1ull) {          // accumulate onto the gradient already there (the skip path wrote it)
+                                const uint4 old = *gp;
+                                val.x = add_bf16x2(val.x, old.x); val.y = add_bf16x2(val.y, old.y);
+                                val.z = add_bf16x2(val.z, old.z); val.w = add_bf16x2(val.w, old.w);
+                            }
+                            *gp = val;
+                        }
                     }
                     __syncwarp();
                 }

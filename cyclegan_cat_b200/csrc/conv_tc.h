@@ -16,6 +16,11 @@ struct TcConvArgs {
     int bk16, groups, cin16;                    // 16-channel K groups (SWIZZLE_32B): `groups` per K step, cin16 = Cin/16 in total
     int tps;                                    // bk16, Cin <= 64: filter taps per K step (each its own A box, ONE B box)
     float* stats;                               // nullable: [N][Cout][2] running (sum, sum of squares) of the outputs
+    // fold mode (data gradient that feeds the adjoint of a reflection pad): output pixels inside the pad border go straight
+    // to the UNPADDED gradient `out2` [nb][out_H-2p][out_W-2p][Cout] (added to its content when fold_acc), only the border
+    // pixels go to `out`; rpad_bwd_border then folds those few pixels
+    bf16* out2;
+    int fold_pad, fold_acc;
     // per K-loop tap: TMA coordinate offsets into the 5-D activation view (c, w, p, h, n) and the weight row block
     short dc[49], dw[49], dp[49], dh[49], tb[49];
 };

@@ -45,6 +45,9 @@ template <typename T> int k_act_bwd(const T* y, const T* dy, T* dx, size_t n, in
 template <typename T> int k_rpad_fwd(const T* x, T* y, int N, int H, int W, int C, int p, cudaStream_t st);
 template <typename T> int k_rpad_bwd(const T* dy, T* dx, int N, int H, int W, int C, int p, int accumulate,
                                      cudaStream_t st);
+// dx already holds the interior term of every pixel (written by the tensor-core data gradient in fold mode): add the
+// mirrored border terms of dy [N][H+2p][W+2p][C]
+template <typename T> int k_rpad_bwd_border(const T* dy, T* dx, int N, int H, int W, int C, int p, cudaStream_t st);
 template <typename T> int k_add(const T* a, const T* b, T* y, size_t n, cudaStream_t st);
 template <typename T> int k_copy_acc(const T* src, T* dst, size_t n, int accumulate, cudaStream_t st);
 template <typename T> int k_slice_copy(const T* src, int Cs, int so, T* dst, int Cd, int doff, int Cc, size_t npix,

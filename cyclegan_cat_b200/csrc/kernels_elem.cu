@@ -554,6 +554,58 @@ __global__ void rpad_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, in
     }
 }
 
+// Border-only adjoint: dx already holds the interior part (padded pixel (h+p, w+p)) of every pixel; add the mirror terms.
+// Only interior pixels within p of an edge (but not on it) have any: rows 1..p and H-1-p..H-2 completely, and of the other
+// rows the columns 1..p and W-1-p..W-2.  One thread = one 16-byte vector of one affected pixel.
+template <typename T, int VEC>
+__global__ void rpad_bwd_border_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int H, int W, int Cv, int p) {
+    const int Ho = H + 2 * p, Wo = W + 2 * p;
+    const int full_rows = 2 * p, side_rows = H - 2 * p;       // affected pixels per image: full_rows*W + side_rows*2p
+    const int per_img = full_rows * W + side_rows * 2 * p;
+    const size_t total = (size_t)N * per_img * Cv;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % Cv);
+        size_t r = i / Cv;
+        int k = (int)(r % per_img);
+        const int n = (int)(r / per_img);
+        int h, w;
+        if (k < full_rows * W) {
+            const int fr = k / W;
+            w = k - fr * W;
+            h = fr < p ? 1 + fr : H - 1 - p + (fr - p);
+        } else {
+            k -= full_rows * W;
+            const int sr = k / (2 * p), j = k - sr * 2 * p;
+            // the side rows are the rows that are not "full" rows: 0, p+1 .. H-2-p, H-1
+            h = sr == 0 ? 0 : (sr == side_rows - 1 ? H - 1 : p + sr);
+            w = j < p ? 1 + j : W - 1 - p + (j - p);
+        }
+        int hs[3], ws[3];
+        const int nh = reflect_sources(h, H, p, hs), nw = reflect_sources(w, W, p, ws);
+        if (nh + nw == 2) continue;
+        float acc[VEC];
+        T* d = dx + ((((size_t)n * H + h) * W + w) * Cv + cv) * VEC;
+        load_vec<T, VEC>(d, acc);
+        for (int a = 0; a < nh; ++a)
+            for (int b = 0; b < nw; ++b) {
+                if (a + b == 0) continue;
+                float v[VEC];
+                load_vec<T, VEC>(dy + (((size_t)n * Ho + hs[a]) * Wo + ws[b]) * Cv * VEC + (size_t)cv * VEC, v);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) acc[j] += v[j];
+            }
+        store_vec<T, VEC>(d, acc);
+    }
+}
+template <typename T> int k_rpad_bwd_border(const T* dy, T* dx, int N, int H, int W, int C, int p, cudaStream_t st) {
+    constexpr int VW = VecWidth<T>::value;
+    if (C % VW || H <= 2 * p + 1 || W <= 2 * p + 1) { cg_set_error("rpad_bwd_border: unsupported shape"); return CG_ERR_INVALID; }
+    const size_t total = (size_t)N * (2 * p * W + (H - 2 * p) * 2 * p) * (C / VW);
+    rpad_bwd_border_kernel<T, VW><<<ew_blocks(total), EW_THREADS, 0, st>>>(dy, dx, N, H, W, C / VW, p);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
 template <typename T> int k_rpad_fwd(const T* x, T* y, int N, int H, int W, int C, int p, cudaStream_t st) {
     constexpr int VW = VecWidth<T>::value;
     size_t total = (size_t)N * (H + 2 * p) * (W + 2 * p) * C;
@@ -802,6 +854,7 @@ int k_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, f
     template int k_act_bwd<T>(const T*, const T*, T*, size_t, int, float, int, cudaStream_t);                   \
     template int k_rpad_fwd<T>(const T*, T*, int, int, int, int, int, cudaStream_t);                            \
     template int k_rpad_bwd<T>(const T*, T*, int, int, int, int, int, int, cudaStream_t);                       \
+    template int k_rpad_bwd_border<T>(const T*, T*, int, int, int, int, int, cudaStream_t);                     \
     template int k_add<T>(const T*, const T*, T*, size_t, cudaStream_t);                                        \
     template int k_copy_acc<T>(const T*, T*, size_t, int, cudaStream_t);                                        \
     template int k_slice_copy<T>(const T*, int, int, T*, int, int, int, size_t, int, cudaStream_t);             \

@@ -680,14 +680,33 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
     if (n0 < 0 || nb <= 0 || n0 + nb > c->N) { cg_set_error("bad sub-batch [%d,%d) of %d", n0, n0 + nb, c->N); return CG_ERR_INVALID; }
     // per-tensor pointers for this sub-batch
     auto A = [&](int t) -> const T* { return (const T*)c->act(t) + (size_t)n0 * c->sample_elems(t); };
+    // galias[t] = u: the gradient of tensor t IS the buffer of tensor u (residual add: d(sum)/d(input) = identity, so the
+    // inputs' gradients start out as the sum's gradient; no copy is made when nothing else can touch the shared buffer first)
+    std::vector<int> galias(nl + 1, -1);
     auto G = [&](int t) -> T* {
+        while (t > 0 && t < nl && galias[t] >= 0) t = galias[t];
         if (t == nl) return const_cast<T*>(dy_out);
         if (t == 0) return dx_in;
         return (T*)(c->arena + c->grad_off[t]);
     };
-    std::vector<char> written(nl + 1, 0);
+    std::vector<char> written(nl + 1, 0), fold_done(nl + 1, 0);
     auto need = [&](int t) -> bool { return dx_in != nullptr || (t != 0 && net->dep_params[t]); };
     float* scratch = (float*)(c->arena + c->scratch_off);
+    // A tensor-core data gradient whose target is a reflection-padded tensor nobody else reads writes the interior of the
+    // padded grid straight into the UNPADDED gradient (accumulating onto the skip path's contribution if that is already
+    // there); the pad's backward then only folds the thin border.  Returns the RPAD layer index or -1.
+    auto find_fold = [&](int i, int tin, int cin) -> int {
+        if (tin < 2 || net->n_consumers[tin] != 1 || cin % 8) return -1;
+        int prod = -1;
+        for (int j = i - 1; j >= 0; --j)
+            if (!net->layers[j].skipped && net->layers[j].out_t == tin) { prod = j; break; }
+        if (prod < 0 || net->layers[prod].d.op != CG_OP_RPAD) return -1;
+        const cg_layer_desc& rd = net->layers[prod].d;
+        if (rd.in0 >= 1 && rd.pad > 0 && need(rd.in0) && c->grad_halo[rd.in0] == 0 && c->th[rd.in0] > 2 * rd.pad + 1 &&
+            c->tw[rd.in0] > 2 * rd.pad + 1)
+            return prod;
+        return -1;
+    };
 
     for (int i = nl - 1; i >= 0; --i) {
         const LayerInfo& L = net->layers[i];
@@ -766,7 +785,18 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                             const TcConvLaunch& tl = c->tc[i].dgrad[0];
                             TcConvArgs a = tl.a;
                             a.nb = nb;
+                            const int fold = find_fold(i, tin, d.cin);
+                            if (fold >= 0) {
+                                const cg_layer_desc& rd = net->layers[fold].d;
+                                a.out2 = (bf16*)G(rd.in0);
+                                a.fold_pad = rd.pad;
+                                a.fold_acc = written[rd.in0] ? 1 : 0;
+                            }
                             CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, (bf16*)dx, nullptr, a, fl, st));
+                            if (fold >= 0) {
+                                written[net->layers[fold].d.in0] = 1;
+                                fold_done[fold] = 1;
+                            }
                         }
                     }
                     break;
@@ -782,12 +812,24 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                         if (L.b_off >= 0 && !L.bias_grad_zero)
                             CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * (oh + 2 * hl) * (ow + 2 * hl), d.cout, st));
                     }
-                    if (want_dx)
+                    if (want_dx) {
+                        const int fold = L.tc == TC_S1_VALID ? find_fold(i, tin, d.cin) : -1;
                         for (const TcConvLaunch& tl : c->tc[i].dgrad) {
                             TcConvArgs a = tl.a;
                             a.nb = nb;
+                            if (fold >= 0) {
+                                const cg_layer_desc& rd = net->layers[fold].d;
+                                a.out2 = (bf16*)G(rd.in0);
+                                a.fold_pad = rd.pad;
+                                a.fold_acc = written[rd.in0] ? 1 : 0;
+                            }
                             CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, (bf16*)dx, nullptr, a, tl.flop_share * fl, st));
                         }
+                        if (fold >= 0) {
+                            written[net->layers[fold].d.in0] = 1;
+                            fold_done[fold] = 1;
+                        }
+                    }
                     break;
                 }
                 if (c->grad_halo[tout]) { cg_set_error("layer %d: zero-bordered dY needs the tensor-core path", i); return CG_ERR_STATE; }
@@ -837,13 +879,37 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                     CG_TRY(k_act_bwd<T>(A(tout), dy, dx, (size_t)nb * c->sample_elems(tin), d.act, d.slope, acc, st));
                 break;
             case CG_OP_RPAD:
-                if (want_dx) CG_TRY(k_rpad_bwd<T>(dy, dx, nb, h, w, d.cin, d.pad, acc, st));
+                if (want_dx && fold_done[i]) CG_TRY(k_rpad_bwd_border<T>(dy, dx, nb, h, w, d.cin, d.pad, st));
+                else if (want_dx) CG_TRY(k_rpad_bwd<T>(dy, dx, nb, h, w, d.cin, d.pad, acc, st));
                 break;
             case CG_OP_ADD: {
                 size_t n = (size_t)nb * c->sample_elems(tin);
-                if (want_dx) CG_TRY(k_copy_acc<T>(dy, dx, n, acc, st));
+                // an input whose gradient has no other contribution yet can share the sum's gradient buffer instead of
+                // receiving a copy.  One input may always do so; both may when no consumer of either input sits between the
+                // other input's producer and this layer (such a consumer would accumulate into the shared buffer before
+                // that producer has read it) -- the case of the ResNet block, resnet.py:26-35
+                auto producer = [&](int t) { for (int j = i - 1; j >= 0; --j) if (!net->layers[j].skipped && net->layers[j].out_t == t) return j; return -1; };
+                auto can_alias = [&](int t) {
+                    if (!(tout != nl && t > 0 && t < nl && !written[t] && need(t) && c->grad_halo[t] == 0 && c->grad_halo[tout] == 0 &&
+                          galias[t] < 0 && d.in0 != d.in1))
+                        return false;
+                    const int pr = producer(t);       // tensor-core layers read their dY through TMA maps bound to its own buffer
+                    return pr >= 0 && !c->tc[pr].on;
+                };
+                auto consumer_between = [&](int t, int lo) {      // a consumer of t with index in (lo, i)
+                    for (int j = lo + 1; j < i; ++j) {
+                        const cg_layer_desc& q = net->layers[j].d;
+                        if (!net->layers[j].skipped && (q.in0 == t || ((q.op == CG_OP_ADD || q.op == CG_OP_CONCAT) && q.in1 == t))) return true;
+                    }
+                    return false;
+                };
+                bool a0 = want_dx && can_alias(tin), a1 = need(d.in1) && can_alias(d.in1);
+                if (a0 && a1 && (consumer_between(tin, producer(d.in1)) || consumer_between(d.in1, producer(tin)))) a0 = false;
+                if (a0) galias[tin] = tout;
+                else if (want_dx) CG_TRY(k_copy_acc<T>(dy, dx, n, acc, st));
                 if (need(d.in1)) {
-                    CG_TRY(k_copy_acc<T>(dy, G(d.in1), n, (int)written[d.in1] || (d.in1 == tin && want_dx), st));
+                    if (a1) galias[d.in1] = tout;
+                    else CG_TRY(k_copy_acc<T>(dy, G(d.in1), n, (int)written[d.in1] || (d.in1 == tin && want_dx), st));
                     written[d.in1] = 1;
                 }
                 break;
