@@ -46,6 +46,10 @@ void prof_end(int idx, cudaStream_t st, double fl, unsigned long long key) {
 
 extern "C" int cg_prof_enable(int enable) {
     std::lock_guard<std::mutex> lk(mu);
+    if (enable < 0) {       // pause: stop recording, keep what has been recorded for cg_prof_read
+        on = false;
+        return CG_OK;
+    }
     on = enable != 0;
     used = 0;
     flops = 0.0;

@@ -163,7 +163,8 @@ int cg_trainer_comm_init(cg_trainer_t tr, const char id[128], int rank, int worl
 
 /* ---- instrumentation for bench.py: CUDA-event timing of one kernel family */
 int cg_prof_enable(int enable);                 /* brackets every tensor-core conv launch with events; 0 = off, 1 = on,
-                                                   n > 1 = on with n event pairs created up front */
+                                                   n > 1 = on with n event pairs created up front,
+                                                   -1 = pause (keep the records for cg_prof_read) */
 int cg_prof_read(double* total_ms, int64_t* launches, double* total_flops);  /* syncs, resets */
 int cg_launch_count(int64_t* launches, int reset);  /* kernels launched by this library */
 
