@@ -16,6 +16,7 @@
 
 #include "kernels.h"
 #include "net.h"
+#include "prof.h"
 
 // ---- NCCL through dlopen (the torch wheel bundles libnccl.so.2; nothing to link at build time) ----
 typedef struct { char internal[128]; } nccl_uid;
@@ -73,6 +74,14 @@ struct cg_trainer_s {
            o_advDA = 0, o_advDB = 0, o_sums = 0, o_arena = 0, o_packed[4] = {0, 0, 0, 0}, o_tcs = 0, total = 0;
     int d_h = 0, d_w = 0, d_c = 0;
     // data parallel
+    // CUDA graph of the gradient step (everything between the input conversion and the metrics copy-out): captured the
+    // second time a (train, stream) pair is seen for the planned shape, replayed afterwards
+    size_t o_metrics = 0;
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};        // [validate, train]
+    cudaStream_t cap_stream = nullptr;                         // capture happens here (the caller's stream may be the legacy
+                                                               // default stream, which cannot be captured); replay on the caller's
+    int graph_seen[2] = {0, 0};
+    long long graph_launches[2] = {0, 0};                      // kernels per replay (for cg_launch_count)
     nccl_comm comm = nullptr; int world = 1, rank = 0;
     cudaStream_t comm_stream = nullptr; cudaEvent_t ev_d = nullptr, ev_g = nullptr, ev_done = nullptr;
 };
@@ -118,6 +127,7 @@ static int trainer_layout(cg_trainer_t tr, int B, int H, int W, bool assign) {
     tr->o_seedDA = take(2 * B * dout); tr->o_seedDB = take(2 * B * dout);
     tr->o_advDA = take(B * dout); tr->o_advDB = take(B * dout);
     tr->o_sums = take(S_COUNT * sizeof(float));
+    tr->o_metrics = take(8 * sizeof(float));
     off = align_up(off, 1024);
     for (int i = 0; i < 4; ++i) tr->o_packed[i] = take(align_up(tr->net[i]->packed_bytes, 1024));
     size_t tcs = 0;
@@ -137,6 +147,10 @@ static int trainer_layout(cg_trainer_t tr, int B, int H, int W, bool assign) {
             cs[i]->packed = tr->ws + tr->o_packed[owner[i]];
             cs[i]->tcs = tr->ws + tr->o_tcs;
             CG_TRY(net_bind(cs[i]));
+        }
+        for (int g = 0; g < 2; ++g) {
+            if (tr->graph_exec[g]) { cudaGraphExecDestroy(tr->graph_exec[g]); tr->graph_exec[g] = nullptr; }
+            tr->graph_seen[g] = 0;
         }
         tr->B = B; tr->H = H; tr->W = W; tr->planned = true;
     }
@@ -165,6 +179,9 @@ extern "C" void cg_trainer_destroy(cg_trainer_t tr) {
     if (tr->ev_d) cudaEventDestroy(tr->ev_d);
     if (tr->ev_g) cudaEventDestroy(tr->ev_g);
     if (tr->ev_done) cudaEventDestroy(tr->ev_done);
+    for (int g = 0; g < 2; ++g)
+        if (tr->graph_exec[g]) cudaGraphExecDestroy(tr->graph_exec[g]);
+    if (tr->cap_stream) cudaStreamDestroy(tr->cap_stream);
     delete tr;
 }
 
@@ -199,11 +216,9 @@ __global__ void metrics_kernel(const float* __restrict__ s, float* __restrict__ 
     out[5] = s[S_OK_B] / (2.f * n_d);
 }
 
+// the part of a step that depends only on the trainer's own buffers (capturable into a CUDA graph)
 template <typename T>
-static int step_T(cg_trainer_t tr, const float* real_a, const float* real_b, int B, int H, int W, float* metrics,
-                  bool train, cudaStream_t st) {
-    if (!tr->ws) { cg_set_error("trainer has no bound buffers (cg_trainer_bind)"); return CG_ERR_STATE; }
-    if (!tr->planned || tr->B != B || tr->H != H || tr->W != W) CG_TRY(trainer_layout(tr, B, H, W, true));
+static int step_body(cg_trainer_t tr, int B, int H, int W, bool train, cudaStream_t st) {
     const cg_train_cfg& cfg = tr->cfg;
     const size_t img = (size_t)H * W * 3;               // elements per image
     const size_t dout = (size_t)tr->d_h * tr->d_w * tr->d_c;
@@ -211,16 +226,11 @@ static int step_T(cg_trainer_t tr, const float* real_a, const float* real_b, int
     const int tDa = tr->net[2]->out_tensor(), tDb = tr->net[3]->out_tensor();
     char* ws = tr->ws;
     float* sums = (float*)(ws + tr->o_sums);
+    float* metrics = (float*)(ws + tr->o_metrics);
     CG_CUDA(cudaMemsetAsync(sums, 0, S_COUNT * sizeof(float), st));
 
     for (int i = 0; i < 4; ++i) CG_TRY(net_pack(tr->net[i], tr->params[i], ws + tr->o_packed[i], st));
-    // ---- inputs: Xab = [a; b], Xba = [b; a] -------------------------------------------------
     T* Xab = (T*)tr->F1.act(0);
-    T* Xba = (T*)tr->F2.act(0);
-    CG_TRY(k_convert_in<T>(real_a, Xab, B * img, st));
-    CG_TRY(k_convert_in<T>(real_b, Xab + B * img, B * img, st));
-    CG_TRY(k_convert_in<T>(real_b, Xba, B * img, st));
-    CG_TRY(k_convert_in<T>(real_a, Xba + B * img, B * img, st));
     const T* ra = Xab;
     const T* rb = Xab + B * img;
 
@@ -304,6 +314,62 @@ static int step_T(cg_trainer_t tr, const float* real_a, const float* real_b, int
         CG_CUDA(cudaEventRecord(tr->ev_done, tr->comm_stream));
         CG_CUDA(cudaStreamWaitEvent(st, tr->ev_done, 0));
     }
+    return CG_OK;
+}
+
+template <typename T>
+static int step_T(cg_trainer_t tr, const float* real_a, const float* real_b, int B, int H, int W, float* metrics,
+                  bool train, cudaStream_t st) {
+    if (!tr->ws) { cg_set_error("trainer has no bound buffers (cg_trainer_bind)"); return CG_ERR_STATE; }
+    if (!tr->planned || tr->B != B || tr->H != H || tr->W != W) CG_TRY(trainer_layout(tr, B, H, W, true));
+    // ---- inputs: Xab = [a; b], Xba = [b; a] (the only part that touches caller pointers) ------
+    const size_t img = (size_t)H * W * 3;
+    T* Xab = (T*)tr->F1.act(0);
+    T* Xba = (T*)tr->F2.act(0);
+    CG_TRY(k_convert_in<T>(real_a, Xab, B * img, st));
+    CG_TRY(k_convert_in<T>(real_b, Xab + B * img, B * img, st));
+    CG_TRY(k_convert_in<T>(real_b, Xba, B * img, st));
+    CG_TRY(k_convert_in<T>(real_a, Xba + B * img, B * img, st));
+
+    // ---- body: replay the captured graph, capture it, or run it eagerly ------------------------
+    static const bool graphs_off = [] { const char* e = getenv("CG_DISABLE_GRAPH"); return e && e[0] == '1'; }();
+    const int gi = train ? 1 : 0;
+    static const bool graphs_nccl = [] { const char* e = getenv("CG_GRAPH_NCCL"); return e && e[0] == '1'; }();
+    const bool graph_ok = !graphs_off && !prof_enabled() && (!tr->comm || graphs_nccl);
+    if (graph_ok && tr->graph_exec[gi]) {
+        CG_CUDA(cudaGraphLaunch(tr->graph_exec[gi], st));
+        g_launches.fetch_add(tr->graph_launches[gi], std::memory_order_relaxed);
+    } else if (graph_ok && tr->graph_seen[gi] >= 1) {
+        // second call for this shape: every lazy one-time initialisation (function attributes, NCCL channels) has happened
+        // in the first, eager one, so the body can be captured
+        if (!tr->cap_stream) CG_CUDA(cudaStreamCreateWithFlags(&tr->cap_stream, cudaStreamNonBlocking));
+        const long long l0 = g_launches.load();
+        cudaGraph_t graph = nullptr;
+        CG_CUDA(cudaStreamBeginCapture(tr->cap_stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = step_body<T>(tr, B, H, W, train, tr->cap_stream);
+        const cudaError_t ce = cudaStreamEndCapture(tr->cap_stream, &graph);
+        bool replayed = false;
+        if (rc == CG_OK && ce == cudaSuccess && graph) {
+            tr->graph_launches[gi] = g_launches.load() - l0;
+            if (cudaGraphInstantiate(&tr->graph_exec[gi], graph, 0) == cudaSuccess) {
+                CG_CUDA(cudaGraphLaunch(tr->graph_exec[gi], st));
+                replayed = true;
+            } else {
+                tr->graph_exec[gi] = nullptr;
+            }
+        }
+        if (graph) cudaGraphDestroy(graph);
+        if (!replayed) {                                // capture is not possible here: stay eager from now on
+            cudaGetLastError();
+            tr->graph_seen[gi] = -1000000;
+            if (rc != CG_OK) return rc;
+            CG_TRY(step_body<T>(tr, B, H, W, train, st));
+        }
+    } else {
+        CG_TRY(step_body<T>(tr, B, H, W, train, st));
+        if (graph_ok) tr->graph_seen[gi] += 1;
+    }
+    CG_CUDA(cudaMemcpyAsync(metrics, tr->ws + tr->o_metrics, 6 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return CG_OK;
 }
 
@@ -395,6 +461,10 @@ extern "C" int cg_trainer_comm_init(cg_trainer_t tr, const char id_in[128], int 
     CG_CUDA(cudaEventCreateWithFlags(&tr->ev_d, cudaEventDisableTiming));
     CG_CUDA(cudaEventCreateWithFlags(&tr->ev_g, cudaEventDisableTiming));
     CG_CUDA(cudaEventCreateWithFlags(&tr->ev_done, cudaEventDisableTiming));
+    for (int g = 0; g < 2; ++g) {          // the step body changes (all-reduces): captured graphs are stale
+        if (tr->graph_exec[g]) { cudaGraphExecDestroy(tr->graph_exec[g]); tr->graph_exec[g] = nullptr; }
+        tr->graph_seen[g] = 0;
+    }
     return CG_OK;
 }
 
