@@ -174,14 +174,14 @@ extern "C" int cg_trainer_create(cg_net_t g_AB, cg_net_t g_BA, cg_net_t d_A, cg_
 
 extern "C" void cg_trainer_destroy(cg_trainer_t tr) {
     if (!tr) return;
+    for (int g = 0; g < 2; ++g)             // graphs first: they may hold NCCL kernels of the communicator
+        if (tr->graph_exec[g]) cudaGraphExecDestroy(tr->graph_exec[g]);
+    if (tr->cap_stream) cudaStreamDestroy(tr->cap_stream);
     if (tr->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(tr->comm);
     if (tr->comm_stream) cudaStreamDestroy(tr->comm_stream);
     if (tr->ev_d) cudaEventDestroy(tr->ev_d);
     if (tr->ev_g) cudaEventDestroy(tr->ev_g);
     if (tr->ev_done) cudaEventDestroy(tr->ev_done);
-    for (int g = 0; g < 2; ++g)
-        if (tr->graph_exec[g]) cudaGraphExecDestroy(tr->graph_exec[g]);
-    if (tr->cap_stream) cudaStreamDestroy(tr->cap_stream);
     delete tr;
 }
 
