@@ -19,17 +19,19 @@ static inline int blocks_for(size_t n) {
 }
 
 // dst[n][r][q][(j*k + kw)*Cs + c] = src[n][r + sign*j][q + sign*kw][c]  for j < 3 (0 outside the source), 64 channels,
-// channels >= 3*k*Cs are zero.  grid = (N*Hd rows, 32-pixel blocks of a row).  A block first copies the three source row
-// windows it needs ((32 + k - 1) pixels each, zero outside the source) into shared memory with coalesced loads, then one
-// thread = one 16-byte vector of one destination pixel gathers its 8 values from there; the channel -> (j, kw, c) decode
-// (two integer divisions) is done once per block.
-constexpr int UNF_MAXW = (32 + 15) * 4;                   // window elements per row: k <= 16, Cs <= 4
+// channels >= 3*k*Cs are zero.  grid = (N*Hd rows, row segments of UNF_SEG pixels).  A block first copies the three source
+// row windows it needs ((UNF_SEG + k - 1) pixels each, zero outside the source) into shared memory with coalesced loads,
+// then walks its segment 32 pixels at a time: one thread = one 16-byte vector of one destination pixel, gathering its 8
+// values from the windows; the channel -> (j, kw, c) decode (two integer divisions) is done once per block.
+constexpr int UNF_SEG = 256;                              // destination pixels per block
+constexpr int UNF_MAXW = (UNF_SEG + 15) * 4;              // window elements per row: k <= 16, Cs <= 4
 __global__ void __launch_bounds__(256) unfold_w_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int Hs, int Ws,
                                                        int Cs, int Hd, int Wd, int k, int sign) {
     __shared__ int lut[64];                              // offset into the window: j*winE + kw'*Cs + c, or -1 (zero channel)
     __shared__ bf16 win[3 * UNF_MAXW];
-    const int row = blockIdx.x, n = row / Hd, r = row - n * Hd, q0 = blockIdx.y * 32;
-    const int winP = 32 + k - 1, winE = winP * Cs;       // window: source columns [c0, c0 + winP)
+    const int row = blockIdx.x, n = row / Hd, r = row - n * Hd, q0 = blockIdx.y * UNF_SEG;
+    const int seg = min(UNF_SEG, Wd - q0);
+    const int winP = seg + k - 1, winE = winP * Cs;      // window: source columns [c0, c0 + winP)
     const int c0 = sign > 0 ? q0 : q0 - (k - 1);
     if (threadIdx.x < 64) {
         const int ch = threadIdx.x, row_live = k * Cs;
@@ -41,24 +43,30 @@ __global__ void __launch_bounds__(256) unfold_w_kernel(const bf16* __restrict__ 
         lut[ch] = e;
     }
     const bf16 zero = __float2bfloat16(0.f);
-    for (int i = threadIdx.x; i < 3 * winE; i += 256) {
-        const int j = i / winE, rem = i - j * winE, px = rem / Cs, c = rem - px * Cs;
-        const int hs = r + sign * j, ws = c0 + px;
-        win[i] = (hs >= 0 && hs < Hs && ws >= 0 && ws < Ws) ? src[(((size_t)n * Hs + hs) * Ws + ws) * Cs + c] : zero;
+    for (int j = 0; j < 3; ++j) {                        // a window row is one contiguous run of the source row
+        const int hs = r + sign * j;
+        const bool row_ok = hs >= 0 && hs < Hs;
+        const bf16* srow = src + ((size_t)n * Hs + (row_ok ? hs : 0)) * Ws * Cs;
+        for (int i = threadIdx.x; i < winE; i += 256) {
+            const int e = c0 * Cs + i;                   // element index inside the source row
+            win[j * winE + i] = (row_ok && e >= 0 && e < Ws * Cs) ? srow[e] : zero;
+        }
     }
     __syncthreads();
-    const int v = threadIdx.x & 7, ql = threadIdx.x >> 3, q = q0 + ql;
-    if (q >= Wd) return;
-    Pack<bf16, 8> pk;
+    const int v = threadIdx.x & 7;
+    int d[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int d = lut[v * 8 + e];
-        pk.v[e] = d >= 0 ? win[d + ql * Cs] : zero;
+    for (int e = 0; e < 8; ++e) d[e] = lut[v * 8 + e];
+    uint4* drow = reinterpret_cast<uint4*>(dst) + (size_t)row * Wd * 8;
+    for (int ql = threadIdx.x >> 3; ql < seg; ql += 32) {
+        Pack<bf16, 8> pk;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pk.v[e] = d[e] >= 0 ? win[d[e] + ql * Cs] : zero;
+        drow[(size_t)(q0 + ql) * 8 + v] = *reinterpret_cast<uint4*>(&pk);
     }
-    reinterpret_cast<uint4*>(dst)[((size_t)row * Wd + q) * 8 + v] = *reinterpret_cast<uint4*>(&pk);
 }
 int sp_unfold_w(const bf16* src, bf16* dst, int N, int Hs, int Ws, int Cs, int Hd, int Wd, int k, int sign, cudaStream_t st) {
-    unfold_w_kernel<<<dim3(N * Hd, (Wd + 31) / 32), 256, 0, st>>>(src, dst, Hs, Ws, Cs, Hd, Wd, k, sign);
+    unfold_w_kernel<<<dim3(N * Hd, (Wd + UNF_SEG - 1) / UNF_SEG), 256, 0, st>>>(src, dst, Hs, Ws, Cs, Hd, Wd, k, sign);
     CG_LAUNCH_CHECK();
     return CG_OK;
 }

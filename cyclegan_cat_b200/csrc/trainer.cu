@@ -332,7 +332,8 @@ static int step_T(cg_trainer_t tr, const float* real_a, const float* real_b, int
     CG_TRY(k_convert_in<T>(real_a, Xba + B * img, B * img, st));
 
     // ---- body: replay the captured graph, capture it, or run it eagerly ------------------------
-    static const bool graphs_off = [] { const char* e = getenv("CG_DISABLE_GRAPH"); return e && e[0] == '1'; }();
+    const char* goff = getenv("CG_DISABLE_GRAPH");      // read per call: tests switch it between trainers
+    const bool graphs_off = goff && goff[0] == '1';
     const int gi = train ? 1 : 0;
     static const bool graphs_nccl = [] { const char* e = getenv("CG_GRAPH_NCCL"); return e && e[0] == '1'; }();
     const bool graph_ok = !graphs_off && !prof_enabled() && (!tr->comm || graphs_nccl);

@@ -64,6 +64,46 @@ def test_epoch_loop_checkpoint_and_resume():
         shutil.rmtree(folder, ignore_errors=True)
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_cuda_graph_replay_matches_eager_steps(mode):
+    """The gradient step is captured into a CUDA graph at its second call and replayed afterwards (trainer.cu); a
+    trainer with CG_DISABLE_GRAPH=1 launches every kernel eagerly.  Same seeds, same batches -> same metrics at every
+    step and the same weights after 5 steps (up to the summation order of the atomics)."""
+    folder = tempfile.mkdtemp(prefix="cg_b200_")
+    try:
+        data = _dataset(4, size=64, seed=3)
+        a, b = np.stack([t[0] for t in data[:2]]), np.stack([t[1] for t in data[:2]])
+        a2, b2 = np.stack([t[0] for t in data[2:]]), np.stack([t[1] for t in data[2:]])
+        runs = []
+        for disable in ("0", "1"):
+            os.environ["CG_DISABLE_GRAPH"] = disable
+            try:
+                gan = _gan(folder, mode=mode)
+                for i, n in enumerate((gan.g_AB, gan.g_BA, gan.d_A, gan.d_B)):
+                    n.initialize(7 + i)
+                ms = []
+                for k in range(5):      # eager, capture, replay, replay (other batch: inputs are outside the graph), replay
+                    m = gan.train_step(*((a2, b2) if k == 3 else (a, b)))
+                    ms.append({key: float(v) for key, v in m.items()})
+                vm = {key: float(v) for key, v in gan.validate_step(a, b).items()}
+                runs.append((ms, vm, [w.copy() for w in gan.g_AB.get_weights()] + [w.copy() for w in gan.d_B.get_weights()]))
+            finally:
+                os.environ.pop("CG_DISABLE_GRAPH", None)
+        for k, (m1, m2) in enumerate(zip(runs[0][0] + [runs[0][1]], runs[1][0] + [runs[1][1]])):
+            # the first replay (k = 2) must agree tightly; later steps drift apart through Adam (the first updates are
+            # ~ lr * sign(g), and the summation order of the atomics differs from run to run)
+            tol = (2e-4 if k <= 2 else 2e-3) if mode == "fp32" else 2e-2
+            for key in m1:
+                assert abs(m1[key] - m2[key]) <= tol * max(1.0, abs(m2[key])), (k, key, m1[key], m2[key])
+        for w1, w2 in zip(runs[0][2], runs[1][2]):
+            if w1.ndim == 4:
+                # 5 Adam steps of ~lr each on N(0, 0.02) weights: entries whose tiny gradient changes sign between the runs
+                # differ by up to 2*lr per step
+                assert C.rel_l2(w1, w2) <= (2e-2 if mode == "fp32" else 5e-2), C.rel_l2(w1, w2)
+    finally:
+        shutil.rmtree(folder, ignore_errors=True)
+
+
 def test_predict_path_like_predict_py():
     """predict.py:20-39: uint8 image -> normalize -> model(x)[0] -> (y+1)*127.5 -> uint8."""
     g = create_model(C.FIX_RESNET, mode="bf16")
