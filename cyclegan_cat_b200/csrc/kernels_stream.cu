@@ -19,6 +19,7 @@
 
 #include "common.h"
 #include "kernels.h"
+#include "prof.h"
 #include "ptx_async.h"
 
 namespace {
@@ -128,6 +129,16 @@ __global__ void __launch_bounds__(ST_THREADS, 2) in_stream_kernel(const StreamAr
     T* outp = (RED || !a.out) ? nullptr : a.out + (size_t)n * out_img + (size_t)cv * VEC;
     T* out2p = (FWD && a.pad > 0) ? a.out2 + (size_t)n * (a.P / a.W + 2 * a.pad) * (a.W + 2 * a.pad) * C + (size_t)cv * VEC : nullptr;
 
+    // zero-bordered output (MODE 2): row / first column of the current tile, advanced incrementally (valid when W is a
+    // multiple of the tile) -- no division per pixel (backward apply 43.8 -> 39.2 us at the trunk shape)
+    const int tpix = 2 * rows;
+    const bool row_tiles = MODE == 2 && a.halo > 0 && (a.W % tpix) == 0;
+    int th = 0, tw0 = 0, dth = 0, dtw = 0;
+    if (row_tiles) {
+        const int p0 = blockIdx.x * tpix, dp = G * tpix;
+        th = p0 / a.W; tw0 = p0 - th * a.W;
+        dth = dp / a.W; dtw = dp - dth * a.W;
+    }
     int s = 0;
     uint32_t ph = 0;
     for (int t = blockIdx.x; t < TI; t += G) {
@@ -190,13 +201,16 @@ __global__ void __launch_bounds__(ST_THREADS, 2) in_stream_kernel(const StreamAr
                 if constexpr (MODE == 2) {
                     size_t po = p;
                     if (a.halo > 0) {
-                        const int h = p / a.W, w = p - h * a.W;
+                        int h, w;
+                        if (row_tiles) { h = th; w = tw0 + u * rows + prow; }
+                        else { h = p / a.W; w = p - h * a.W; }
                         po = (size_t)(h + a.halo) * Wp + (w + a.halo);
                     }
                     store_vec<T, VEC>(outp + po * C, o);
                 }
             }
         }
+        if (row_tiles) { th += dth; tw0 += dtw; if (tw0 >= a.W) { tw0 -= a.W; ++th; } }
     }
 
     if constexpr (MODE == 2) if (a.halo > 0) {      // zero border of the [H+2h][W+2h] output
@@ -267,7 +281,13 @@ int launch_stream(StreamArgs<T>& a, int N, cudaStream_t st) {
     int G = (2 * 148) / N;                           // all CTAs resident at once (2 per SM), no second wave
     if (G > a.tiles_per_img) G = a.tiles_per_img;
     if (G < 1) G = 1;
+    static const bool prof_stream = [] { const char* e = getenv("CG_PROF_STREAM"); return e && e[0] == '1'; }();
+    const int pi = prof_stream ? prof_begin(st) : -1;      // diagnostic: in-step timing of the streaming kernels (CSV kinds 8+MODE)
     kern<<<dim3(G, N), ST_THREADS, smem, st>>>(a);
+    if (pi >= 0) {
+        const double bytes = (double)N * a.P * a.C * sizeof(T) * (MODE == 4 ? 1 : (MODE == 0 || MODE == 1) ? 2 : 3);
+        prof_end(pi, st, bytes, prof_key(8 + MODE, MODE, 0, a.C, a.tiles_per_img, N));
+    }
     CG_LAUNCH_CHECK();
     return CG_OK;
 }

@@ -38,7 +38,7 @@ void prof_end(int idx, cudaStream_t st, double fl, unsigned long long key) {
     if (idx < 0) return;
     std::lock_guard<std::mutex> lk(mu);
     cudaEventRecord(pool[idx].b, st);
-    flops += fl;
+    if ((key >> 60) < 8) flops += fl;
     if (rec_flops.size() <= (size_t)idx) { rec_flops.resize(idx + 1); rec_key.resize(idx + 1); }
     rec_flops[idx] = fl;
     rec_key[idx] = key;
@@ -71,7 +71,8 @@ extern "C" int cg_prof_read(double* total_ms, int64_t* launches, double* total_f
     if (f) fprintf(f, "kind,taps,cchunks,bn,tiles,nb,flops,ms\n");
     for (size_t i = 0; i < used; ++i) {
         float t = 0.f;
-        if (cudaEventElapsedTime(&t, pool[i].a, pool[i].b) == cudaSuccess) ms += t;
+        const bool tc = i >= rec_key.size() || (rec_key[i] >> 60) < 8;     // kinds >= 8: streaming kernels (CG_PROF_STREAM=1),
+        if (cudaEventElapsedTime(&t, pool[i].a, pool[i].b) == cudaSuccess && tc) ms += t;      // listed in the CSV only
         if (f && i < rec_key.size()) {
             const unsigned long long k = rec_key[i];
             fprintf(f, "%llu,%llu,%llu,%llu,%llu,%llu,%.0f,%.5f\n", k >> 60, (k >> 52) & 0xff, (k >> 44) & 0xff, (k >> 32) & 0xfff,
