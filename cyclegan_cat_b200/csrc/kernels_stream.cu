@@ -55,7 +55,7 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 // MODE 4: sums_out += (sum x, sum x^2)             (forward statistics; one operand)
 // MODES 0 and 3 write the plain tensor (`out`, nullable) and/or the reflection-padded one (`out2`, pad > 0).
 template <typename T, int VEC, int MODE, bool AFFINE>
-__global__ void __launch_bounds__(ST_THREADS, 2) in_stream_kernel(const StreamArgs<T> a) {
+__global__ void __launch_bounds__(ST_THREADS, (MODE == 0 || MODE == 4) ? 3 : 2) in_stream_kernel(const StreamArgs<T> a) {
     extern __shared__ __align__(128) uint8_t st_smem[];
     constexpr int NOPS = (MODE == 0 || MODE == 4) ? 1 : 2;
     constexpr bool FWD = MODE == 0 || MODE == 3;
@@ -163,10 +163,21 @@ __global__ void __launch_bounds__(ST_THREADS, 2) in_stream_kernel(const StreamAr
                     acc_ss[j] = fmaf(v[u][j], v[u][j], acc_ss[j]);
                 }
             } else if constexpr (FWD) {
+                // the activation switch is taken once per vector, not once per element (the forward kernels are
+                // instruction-bound: ~170 warp instructions per 16-byte vector before this)
+                if (a.act == CG_ACT_RELU) {
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    v[u][j] = act_fwd(fmaf(v[u][j], k0[j], k1[j]), a.act, a.slope);
-                    if constexpr (MODE == 3) v[u][j] += g[u][j];
+                    for (int j = 0; j < VEC; ++j) v[u][j] = fmaxf(fmaf(v[u][j], k0[j], k1[j]), 0.f);
+                } else if (a.act == CG_ACT_NONE) {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) v[u][j] = fmaf(v[u][j], k0[j], k1[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) v[u][j] = act_fwd(fmaf(v[u][j], k0[j], k1[j]), a.act, a.slope);
+                }
+                if constexpr (MODE == 3) {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) v[u][j] += g[u][j];
                 }
                 if (outp) store_vec<T, VEC>(outp + (size_t)p * C, v[u]);
                 if (out2p) {
@@ -278,7 +289,8 @@ int launch_stream(StreamArgs<T>& a, int N, cudaStream_t st) {
         CG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(6 * 2 * ST_TILE + 1024)));
         attr_done = true;
     }
-    int G = (2 * 148) / N;                           // all CTAs resident at once (2 per SM), no second wave
+    const int per_sm = (MODE == 0 || MODE == 4) ? 3 : 2;      // one-operand modes: 64 KB of ring and <= 75 registers -> 3 CTAs per SM
+    int G = (per_sm * 148) / N;                      // all CTAs resident at once, no second wave
     if (G > a.tiles_per_img) G = a.tiles_per_img;
     if (G < 1) G = 1;
     static const bool prof_stream = [] { const char* e = getenv("CG_PROF_STREAM"); return e && e[0] == '1'; }();
