@@ -335,7 +335,9 @@ static int step_T(cg_trainer_t tr, const float* real_a, const float* real_b, int
     const char* goff = getenv("CG_DISABLE_GRAPH");      // read per call: tests switch it between trainers
     const bool graphs_off = goff && goff[0] == '1';
     const int gi = train ? 1 : 0;
-    static const bool graphs_nccl = [] { const char* e = getenv("CG_GRAPH_NCCL"); return e && e[0] == '1'; }();
+    // with a communicator attached the all-reduces (side stream, fork/join by events) become graph nodes too; opt out
+    // with CG_GRAPH_NCCL=0
+    static const bool graphs_nccl = [] { const char* e = getenv("CG_GRAPH_NCCL"); return !(e && e[0] == '0'); }();
     const bool graph_ok = !graphs_off && !prof_enabled() && (!tr->comm || graphs_nccl);
     if (graph_ok && tr->graph_exec[gi]) {
         CG_CUDA(cudaGraphLaunch(tr->graph_exec[gi], st));
