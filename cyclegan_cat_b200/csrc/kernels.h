@@ -15,7 +15,8 @@ template <typename T> int k_conv_wgrad(const T* x, const T* dy, float* dw, ConvG
 template <typename T> int k_colsum(const T* dy, float* db, size_t rows, int C, cudaStream_t st);
 
 // ---- instance norm ----
-template <typename T> int k_in_stats(const T* x, float* stats, int N, int P, int C, float eps, cudaStream_t st);
+template <typename T> int k_in_stats(const T* x, float* stats, int N, int P, int C, float eps, cudaStream_t st,
+                                     bool zeroed = false);      // zeroed: the caller has already cleared `stats`
 int k_in_finalize(float* stats, int NC, int P, float eps, cudaStream_t st);
 template <typename T> int k_in_apply(const T* x, T* y, const float* stats, const float* gamma, const float* beta,
                                      int act, float slope, int N, int P, int C, cudaStream_t st);
@@ -36,7 +37,7 @@ template <typename T> int k_in_bwd_apply_stream(const T* x, const T* dy, T* dx, 
 template <typename T> int k_in_bwd(const T* x, const T* dy, T* dx, const float* stats, const float* gamma,
                                    const float* beta, float* dgamma, float* dbeta, float* scratch, int act,
                                    float slope, int N, int P, int C, int accumulate, cudaStream_t st,
-                                   int halo = 0, int W = 0);
+                                   int halo = 0, int W = 0, bool zeroed = false);   // zeroed: `scratch` is already cleared
 
 // ---- elementwise / data movement ----
 template <typename T> int k_act_fwd(const T* x, T* y, size_t n, int act, float slope, cudaStream_t st);

@@ -93,6 +93,7 @@ int net_plan(const cg_net_s* net, int N, int H, int W, bool bwd, CallCtx* ctx) {
         off += align_up((size_t)N * ctx->sample_elems((int)t) * es, 256);
     }
     ctx->stat_off.assign(nl, 0);
+    ctx->stat_begin = off;
     size_t max_nc = 1;
     for (size_t i = 0; i < nl; ++i) {
         const cg_layer_desc& d = net->layers[i].d;
@@ -152,7 +153,15 @@ int net_plan(const cg_net_s* net, int N, int H, int W, bool bwd, CallCtx* ctx) {
             goff += align_up((size_t)N * (ctx->th[t] + 2 * hl) * (ctx->tw[t] + 2 * hl) * net->chan[t] * es, 256);
         }
         ctx->scratch_off = goff;
-        goff += align_up(max_nc * 2 * sizeof(float), 256);
+        ctx->sums_off.assign(nl, 0);
+        for (size_t i = 0; i < nl; ++i) {
+            const cg_layer_desc& d = net->layers[i].d;
+            if (d.op != CG_OP_INORM) continue;
+            ctx->sums_off[i] = goff;
+            goff += align_up((size_t)N * d.cin * 2 * sizeof(float), 256);
+        }
+        ctx->sums_bytes = goff - ctx->scratch_off;
+        (void)max_nc;
     }
     ctx->grad_bytes = goff;
     return CG_OK;
@@ -538,6 +547,8 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
     const cg_net_s* net = c->net;
     const int N = c->N;
     std::vector<char> stats_done(net->layers.size() + 1, 0), fused_done(net->layers.size() + 1, 0);
+    // every statistics table of this call is zeroed by ONE memset (they are accumulated into by atomics)
+    if (c->act_bytes > c->stat_begin) CG_CUDA(cudaMemsetAsync(c->base + c->stat_begin, 0, c->act_bytes - c->stat_begin, st));
     for (size_t i = 0; i < net->layers.size(); ++i) {
         const LayerInfo& L = net->layers[i];
         if (L.skipped) continue;
@@ -551,7 +562,6 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
         const bool long_k = L.tc != TC_STEM;
         if (c->tc[i].on && L.feeds_in && L.tc != TC_HEAD && long_k && i + 1 < net->layers.size()) {
             fused_stats = (float*)(c->base + c->stat_off[i + 1]);
-            CG_CUDA(cudaMemsetAsync(fused_stats, 0, sizeof(float) * 2 * (size_t)N * d.cout, st));
             stats_done[i + 1] = 1;
         }
         T* y = (T*)c->act(tout);
@@ -604,7 +614,7 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
             case CG_OP_INORM: {
                 float* stats = (float*)(c->base + c->stat_off[i]);
                 if (stats_done[i]) CG_TRY(k_in_finalize(stats, N * d.cin, h * w, d.eps, st));
-                else CG_TRY(k_in_stats<T>(x, stats, N, h * w, d.cin, d.eps, st));
+                else CG_TRY(k_in_stats<T>(x, stats, N, h * w, d.cin, d.eps, st, /*zeroed=*/true));
                 const float* gam = L.g_off >= 0 ? params + L.g_off : nullptr;
                 const float* bet = L.be_off >= 0 ? params + L.be_off : nullptr;
                 if (L.fuse_rpad >= 0) {
@@ -691,7 +701,8 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
     };
     std::vector<char> written(nl + 1, 0), fold_done(nl + 1, 0);
     auto need = [&](int t) -> bool { return dx_in != nullptr || (t != 0 && net->dep_params[t]); };
-    float* scratch = (float*)(c->arena + c->scratch_off);
+    // the backward sums of every instance norm of this call are cleared by ONE memset (sub-batch relative tables)
+    if (c->sums_bytes) CG_CUDA(cudaMemsetAsync(c->arena + c->scratch_off, 0, c->sums_bytes, st));
     // A tensor-core data gradient whose target is a reflection-padded tensor nobody else reads writes the interior of the
     // padded grid straight into the UNPADDED gradient (accumulating onto the skip path's contribution if that is already
     // there); the pad's backward then only folds the thin border.  Returns the RPAD layer index or -1.
@@ -870,8 +881,8 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                 bool pg = grads && L.g_off >= 0;
                 CG_TRY(k_in_bwd<T>(A(tin), dy, dx, stats, L.g_off >= 0 ? params + L.g_off : nullptr,
                                    L.be_off >= 0 ? params + L.be_off : nullptr, pg ? grads + L.g_off : nullptr,
-                                   pg ? grads + L.be_off : nullptr, scratch, L.fused_act, L.fused_slope, nb, h * w,
-                                   d.cin, acc, st, c->grad_halo[tin], w));
+                                   pg ? grads + L.be_off : nullptr, (float*)(c->arena + c->sums_off[i]), L.fused_act,
+                                   L.fused_slope, nb, h * w, d.cin, acc, st, c->grad_halo[tin], w, /*zeroed=*/true));
                 break;
             }
             case CG_OP_ACT:

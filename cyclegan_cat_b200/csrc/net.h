@@ -63,9 +63,12 @@ struct CallCtx {
     std::vector<size_t> act_off;        // byte offsets into `base` (activations)
     std::vector<size_t> stat_off;       // per layer: INORM statistics [N][C][2] float
     size_t act_bytes = 0;
+    size_t stat_begin = 0;              // the INORM statistics tables are one contiguous region [stat_begin, act_bytes)
     std::vector<size_t> grad_off;       // byte offsets into the shared gradient arena
     size_t grad_bytes = 0;              // includes the IN-backward scratch at scratch_off
-    size_t scratch_off = 0;
+    size_t scratch_off = 0;             // IN-backward sums: one [N][C][2] float table per INORM layer from here on,
+    std::vector<size_t> sums_off;       // per layer (offset into the arena); the region is zeroed once per backward
+    size_t sums_bytes = 0;
     char* base = nullptr;               // activations workspace
     char* arena = nullptr;              // gradient arena (may be shared between calls)
     void* ext_input = nullptr;          // if set, tensor 0 lives here instead of at act_off[0]
