@@ -57,8 +57,15 @@ def build(verbose=False, force=False):
         else:
             with open(stamp, "w") as fh:
                 fh.write(dig)
-    with open(os.path.join(LIBDIR, "build.log"), "a" if not force else "w") as fh:
-        fh.write("\n".join(logs))
+    # one log per source (overwritten when that source is recompiled); build.log is their concatenation, so it always
+    # holds exactly the ptxas output (registers / spills, -Xptxas -v) of the objects that are in the library
+    for src, stamp, dig, p in procs:
+        with open(os.path.join(OBJDIR, src + ".log"), "w") as fh:
+            fh.write(next(l for l in logs if l.startswith(f"== {src}\n")))
+    with open(os.path.join(LIBDIR, "build.log"), "w") as fh:
+        for f in sorted(os.listdir(OBJDIR)):
+            if f.endswith(".log"):
+                fh.write(open(os.path.join(OBJDIR, f)).read() + "\n")
     if failed:
         raise RuntimeError("nvcc compilation failed (see above)")
     if procs or not os.path.exists(LIB):
