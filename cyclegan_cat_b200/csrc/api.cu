@@ -198,6 +198,9 @@ extern "C" int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode
                 kind = TC_CONV_S2;
             else if (d.op == CG_OP_CONVT && d.stride == 2 && (d.k == 3 || d.k == 4) && chan_ok(d.cout, d.cin))
                 kind = TC_CONVT_S2;
+            else if (d.op == CG_OP_CONV && d.stride == 2 && d.same && d.cin <= 4 && d.k * d.k * d.cin <= 64 && d.k <= 8 &&
+                     d.cout % 64 == 0 && d.cout <= 256)
+                kind = TC_IM2COL;       // discriminator input layer (resnet.py:96, Conv k4 s2 on the image): full im2col into 64 channels
             else if (d.op == CG_OP_CONV && d.stride == 1 && !d.same && d.k >= 3 && d.cin <= 4 && d.k * d.cin <= 21 && d.k <= 12 &&
                      d.cout % 64 == 0 && d.cout <= 256)
                 kind = TC_STEM;         // c7s1-f stem (resnet.py:39-40): horizontal taps unfolded into channels
@@ -207,7 +210,11 @@ extern "C" int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode
             else if (d.op == CG_OP_CONV && d.stride == 1 && (d.same || d.k == 1) && d.k <= 7 && d.cin % 16 == 0 &&
                      d.cout % 16 == 0 && d.cout <= 256 && d.cin <= 256 * 8)
                 kind = TC_S1_16;        // U-Net double_conv layers (unet.py:25): channel counts are multiples of 16 only
-            if (kind == TC_STEM) {
+            if (kind == TC_IM2COL) {
+                L.tc = kind;
+                L.pk_f = (long long)pk; pk += align_up((size_t)d.cout * 64 * 2, 1024);
+                L.pk_d = (long long)pk; pk += align_up((size_t)64 * d.cout * 2, 1024);
+            } else if (kind == TC_STEM) {
                 L.tc = kind;
                 L.pk_f = (long long)pk; pk += align_up((size_t)d.k * d.cout * 64 * 2, 1024);
                 L.pk_d = (long long)pk; pk += align_up((size_t)d.k * 32 * d.cout * 2, 1024);

@@ -175,3 +175,109 @@ int sp_unpack_dw(const float* t, float* dw, int k, int Cin, int Cout, int head, 
     CG_LAUNCH_CHECK();
     return CG_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Thin-input strided conv (the discriminators' first layer, resnet.py:96: Conv k4 s2 'same' on a 3-channel image):
+// k*k*Cin <= 64, so the whole receptive field of an output pixel is unfolded into ONE dense 64-channel chunk
+//   U[n][oh][ow][(kh*k+kw)*Cin+ci] = x[n][oh*s + kh - pt][ow*s + kw - pl][ci]   (0 outside the image, 0 for the unused channels)
+// and the conv is a 1x1 tensor-core GEMM over U (forward), a tap-stacked weight gradient with U as the X operand, and for
+// the data gradient a 1x1 GEMM dU = dY . W^T followed by the adjoint of the unfolding (col2im).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) im2col_kernel(const bf16* __restrict__ x, bf16* __restrict__ U, int N, int H, int W, int Cin,
+                                                     int Ho, int Wo, int k, int s, int pt, int pl) {
+    __shared__ int lut[64];                              // (kh << 16) | (kw << 8) | ci, or -1 for an unused channel
+    if (threadIdx.x < 64) {
+        const int ch = threadIdx.x;
+        int e = -1;
+        if (ch < k * k * Cin) { const int tap = ch / Cin, ci = ch - tap * Cin, kh = tap / k, kw = tap - kh * k; e = (kh << 16) | (kw << 8) | ci; }
+        lut[ch] = e;
+    }
+    __syncthreads();
+    const size_t total = (size_t)N * Ho * Wo * 8;
+    const bf16 zero = __float2bfloat16(0.f);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int v = (int)(i & 7);
+        size_t px = i >> 3;
+        const int ow = (int)(px % Wo);
+        px /= Wo;
+        const int oh = (int)(px % Ho), n = (int)(px / Ho);
+        const bf16* img = x + (size_t)n * H * W * Cin;
+        Pack<bf16, 8> pk;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int d = lut[v * 8 + e];
+            bf16 val = zero;
+            if (d >= 0) {
+                const int ih = oh * s + (d >> 16) - pt, iw = ow * s + ((d >> 8) & 0xff) - pl;
+                if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = img[((size_t)ih * W + iw) * Cin + (d & 0xff)];
+            }
+            pk.v[e] = val;
+        }
+        reinterpret_cast<uint4*>(U)[i] = *reinterpret_cast<uint4*>(&pk);
+    }
+}
+int sp_im2col(const bf16* x, bf16* U, int N, int H, int W, int Cin, int Ho, int Wo, int k, int s, int pt, int pl, cudaStream_t st) {
+    im2col_kernel<<<blocks_for((size_t)N * Ho * Wo * 8), 256, 0, st>>>(x, U, N, H, W, Cin, Ho, Wo, k, s, pt, pl);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+// dx[n][ih][iw][ci] = sum over the taps (kh, kw) with (ih + pt - kh) and (iw + pl - kw) divisible by s and the quotient inside
+// the output grid of dU[n][(ih+pt-kh)/s][(iw+pl-kw)/s][(kh*k+kw)*Cin+ci]
+__global__ void col2im_kernel(const bf16* __restrict__ dU, bf16* __restrict__ dx, int N, int H, int W, int Cin, int Ho, int Wo,
+                              int k, int s, int pt, int pl) {
+    const size_t total = (size_t)N * H * W;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int iw = (int)(i % W);
+        size_t r = i / W;
+        const int ih = (int)(r % H), n = (int)(r / H);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int kh = 0; kh < k; ++kh) {
+            const int th = ih + pt - kh;
+            if (th < 0 || th % s) continue;
+            const int oh = th / s;
+            if (oh >= Ho) continue;
+            for (int kw = 0; kw < k; ++kw) {
+                const int tw = iw + pl - kw;
+                if (tw < 0 || tw % s) continue;
+                const int ow = tw / s;
+                if (ow >= Wo) continue;
+                const bf16* p = dU + (((size_t)n * Ho + oh) * Wo + ow) * 64 + (kh * k + kw) * Cin;
+                for (int c = 0; c < Cin; ++c) acc[c] += __bfloat162float(p[c]);
+            }
+        }
+        for (int c = 0; c < Cin; ++c) dx[i * Cin + c] = __float2bfloat16(acc[c]);
+    }
+}
+int sp_col2im(const bf16* dU, bf16* dx, int N, int H, int W, int Cin, int Ho, int Wo, int k, int s, int pt, int pl, cudaStream_t st) {
+    col2im_kernel<<<blocks_for((size_t)N * H * W), 256, 0, st>>>(dU, dx, N, H, W, Cin, Ho, Wo, k, s, pt, pl);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+// weights w[kh][kw][ci][co] (fp32 HWIO) -> wf[co][j] (64 columns, forward B operand) and wd[j][co] (64 rows, data-gradient
+// B operand), j = (kh*k+kw)*Cin+ci, zero padded
+__global__ void pack_im2col_kernel(const float* __restrict__ w, bf16* __restrict__ wf, bf16* __restrict__ wd, int k, int Cin, int Cout) {
+    const int total = 64 * Cout, live = k * k * Cin;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int co = i % Cout, j = i / Cout;
+        const bf16 v = __float2bfloat16(j < live ? w[(size_t)j * Cout + co] : 0.f);
+        wd[(size_t)j * Cout + co] = v;
+        wf[(size_t)co * 64 + j] = v;
+    }
+}
+int sp_pack_im2col(const float* w, bf16* wf, bf16* wd, int k, int Cin, int Cout, cudaStream_t st) {
+    pack_im2col_kernel<<<blocks_for((size_t)64 * Cout), 256, 0, st>>>(w, wf, wd, k, Cin, Cout);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+// dw[j][co] += t[j][co] for the live rows j < k*k*Cin (t: the first 64 rows of the tap-stacked weight-gradient result)
+__global__ void unpack_im2col_kernel(const float* __restrict__ t, float* __restrict__ dw, int live, int Cout) {
+    const int total = live * Cout;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) dw[i] += t[i];
+}
+int sp_unpack_im2col(const float* t, float* dw, int k, int Cin, int Cout, cudaStream_t st) {
+    unpack_im2col_kernel<<<blocks_for((size_t)k * k * Cin * Cout), 256, 0, st>>>(t, dw, k * k * Cin, Cout);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}

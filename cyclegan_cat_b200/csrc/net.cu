@@ -126,12 +126,20 @@ int net_plan(const cg_net_s* net, int N, int H, int W, bool bwd, CallCtx* ctx) {
         }
         else if (kind == TC_S1_16) {
             ok = boxable(wo, ho, 128) && d.cin <= 256;      // dgrad N tile = Cin
+        } else if (kind == TC_IM2COL) {
+            ok = boxable(wo, ho, 128) && boxable(wo, ho, 64);
         } else if (kind == TC_STEM) {
             ok = boxable(wo, ho, 128) && boxable(wo, ho, 64);
         } else if (kind == TC_HEAD) {
             ok = (size_t)hi * wi < (1u << 30) && 6 * wi < 32767;
         }
         ctx->tc[i].on = ok;
+        if (ok && kind == TC_IM2COL) {       // scratch: the unfolded tensor / its gradient [N][ho][wo][64], then the fp32 dW staging
+            const size_t big = (size_t)N * ho * wo * 64 * 2, tmp = (size_t)2 * 64 * d.cout * 4;
+            ctx->tc[i].sc_tmp = align_up(big, 1024);
+            const size_t need = ctx->tc[i].sc_tmp + align_up(tmp, 1024);
+            if (need > ctx->tcs_bytes) ctx->tcs_bytes = need;
+        }
         if (ok && (kind == TC_STEM || kind == TC_HEAD)) {
             // scratch: the unfolded tensor (64 channels; S of the head forward is smaller) then the fp32 dW staging
             // ([vertical taps rounded up to pairs][64][C])
@@ -178,6 +186,11 @@ int net_pack(const cg_net_s* net, const float* params, void* packed, cudaStream_
         if (L.tc == TC_STEM) {
             CG_TRY(sp_pack_stem(params + L.w_off, (bf16*)((char*)packed + L.pk_f), L.d.k, L.d.cin, L.d.cout, st));
             CG_TRY(sp_pack_stem_d(params + L.w_off, (bf16*)((char*)packed + L.pk_d), L.d.k, L.d.cin, L.d.cout, st));
+            continue;
+        }
+        if (L.tc == TC_IM2COL) {
+            CG_TRY(sp_pack_im2col(params + L.w_off, (bf16*)((char*)packed + L.pk_f), (bf16*)((char*)packed + L.pk_d), L.d.k,
+                                  L.d.cin, L.d.cout, st));
             continue;
         }
         if (L.tc == TC_HEAD) {
@@ -424,6 +437,46 @@ int net_bind(CallCtx* c) {
                 CG_TRY(tc_make_map_act16(&t.mapDYw, dy, d.cout, wo, ho, c->N, a.Wk, a.Hk, d.cout / 16));
                 t.wg16 = true;
             }
+        } else if (L.tc == TC_IM2COL) {
+            if (!c->tcs) { cg_set_error("net_bind: no scratch for the unfolded input"); return CG_ERR_STATE; }
+            const void* U = c->tcs;                         // [N][ho][wo][64]: the receptive field of every output pixel
+            t.fwd.assign(1, TcConvLaunch());
+            {
+                TcConvArgs& a = t.fwd[0].a;
+                memset(&a, 0, sizeof(a));
+                set_tiles(a, wo, ho);
+                a.n_taps = 1; a.cchunks = 1; a.bn = d.cout; a.n_blocks_n = 1;
+                a.nb = c->N; a.out_H = ho; a.out_W = wo; a.Cout = d.cout; a.out_sy = a.out_sx = 1;
+                a.b_rows_per_tap = d.cout;
+                CG_TRY(tc_make_map_act(&t.fwd[0].mapA, U, 64, wo, ho, c->N, 0, a.Wb, a.Hb));
+                CG_TRY(tc_make_map_2d(&t.fwd[0].mapB, wf, 64, d.cout, a.bn));
+                CG_TRY(tc_make_map_2d(&t.fwd[0].mapB2, wf, 64, d.cout, (a.bn) / 2 >= 8 ? (a.bn) / 2 : 8));
+            }
+            if (!c->bwd) continue;
+            {   // dW[j][co] = sum_pixels U[p][j] * dy[p][co]: one unit, the second 64 MMA rows are out of bounds (zero)
+                TcWgradArgs& a = t.wa;
+                memset(&a, 0, sizeof(a));
+                a.Wk = wo % 64 == 0 ? 64 : wo; a.Hk = 64 / a.Wk;
+                a.n_taps = 1; a.stack2 = 1; a.transposed = 0; a.a_blocks = 1; a.bn = d.cout; a.b_blocks = 1;
+                a.chunks_w = wo / a.Wk; a.chunks_per_img = a.chunks_w * (ho / a.Hk);
+                a.Cin = 128; a.Cout = d.cout;
+                a.dh[0] = 0; a.dh[1] = 20000;
+                a.x_grouped = 0; a.y_grouped = 1;
+                CG_TRY(tc_make_map_act(&t.mapXw, U, 64, wo, ho, c->N, 0, a.Wk, a.Hk));
+                CG_TRY(tc_make_map_act_grouped(&t.mapDYw, dy, d.cout, wo, ho, c->N, a.Wk, a.Hk, d.cout / 64));
+            }
+            t.dgrad.assign(1, TcConvLaunch());
+            {   // dU[p][j] = sum_co dy[p][co] * W[j][co]   (written to the scratch, then folded back by col2im)
+                TcConvArgs& a = t.dgrad[0].a;
+                memset(&a, 0, sizeof(a));
+                set_tiles(a, wo, ho);
+                a.n_taps = 1; a.cchunks = d.cout / 64; a.bn = 64; a.n_blocks_n = 1;
+                a.nb = c->N; a.out_H = ho; a.out_W = wo; a.Cout = 64; a.out_sy = a.out_sx = 1;
+                a.b_rows_per_tap = 64;
+                CG_TRY(tc_make_map_act(&t.dgrad[0].mapA, dy, d.cout, wo, ho, c->N, 0, a.Wb, a.Hb));
+                CG_TRY(tc_make_map_2d(&t.dgrad[0].mapB, wd, d.cout, 64, 64));
+                CG_TRY(tc_make_map_2d(&t.dgrad[0].mapB2, wd, d.cout, 64, 32));
+            }
         } else if (L.tc == TC_STEM) {
             if (!c->tcs) { cg_set_error("net_bind: no scratch for the unfolded stem input"); return CG_ERR_STATE; }
             const void* U = c->tcs;                         // [N][hi][wo][64]: U[r][ow][(j*k+kw)*cin+ci] = x[r+j][ow+kw][ci], j < 3
@@ -559,7 +612,7 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
         float* fused_stats = nullptr;
         // ... when its main loop is long enough to hide the extra epilogue work (the column sums double the epilogue of a
         // 32-column chunk); the 3-K-step stem is faster with the separate streaming statistics pass
-        const bool long_k = L.tc != TC_STEM;
+        const bool long_k = L.tc != TC_STEM && L.tc != TC_IM2COL;
         if (c->tc[i].on && L.feeds_in && L.tc != TC_HEAD && long_k && i + 1 < net->layers.size()) {
             fused_stats = (float*)(c->base + c->stat_off[i + 1]);
             stats_done[i + 1] = 1;
@@ -571,7 +624,13 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
                 ConvGeom g = conv_geom(d, N, h, w, oh, ow);
                 const float* bias = L.b_off >= 0 ? params + L.b_off : nullptr;
                 const double fl = 2.0 * N * oh * ow * (double)d.cout * d.k * d.k * d.cin;
-                if (c->tc[i].on && L.tc == TC_STEM) {
+                if (c->tc[i].on && L.tc == TC_IM2COL) {
+                    const TcConvLaunch& tl = c->tc[i].fwd[0];
+                    CG_TRY(sp_im2col((const bf16*)x, (bf16*)c->tcs, N, h, w, d.cin, oh, ow, d.k, d.stride, g.pt, g.pl, st));
+                    TcConvArgs a = tl.a;
+                    a.nb = N;
+                    CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, (bf16*)y, bias, a, fl, st));
+                } else if (c->tc[i].on && L.tc == TC_STEM) {
                     const TcConvLaunch& tl = c->tc[i].fwd[0];
                     CG_TRY(sp_unfold_w((const bf16*)x, (bf16*)c->tcs, N, h, w, d.cin, h, ow, d.k, +1, st));
                     TcConvArgs a = tl.a;
@@ -757,6 +816,28 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                             CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, (bf16*)dx, nullptr, a,
                                                   2.0 * nb * oh * ow * (double)d.cout * d.k * d.k * d.cin, st));
                         }
+                    }
+                    break;
+                }
+                if (c->tc[i].on && !acc && L.tc == TC_IM2COL) {
+                    const double fl = 2.0 * nb * oh * ow * (double)d.cout * d.k * d.k * d.cin;
+                    float* tmp = (float*)(c->tcs + c->tc[i].sc_tmp);
+                    bf16* big = (bf16*)c->tcs;
+                    if (grads) {
+                        CG_TRY(sp_im2col((const bf16*)A(tin), big, nb, h, w, d.cin, oh, ow, d.k, d.stride, g.pt, g.pl, st));
+                        CG_CUDA(cudaMemsetAsync(tmp, 0, (size_t)2 * 64 * d.cout * sizeof(float), st));
+                        TcWgradArgs a = c->tc[i].wa;
+                        a.n0 = 0; a.nb = nb;
+                        CG_TRY(tc_wgrad_launch(&c->tc[i].mapXw, &c->tc[i].mapDYw, tmp, a, fl, st));
+                        CG_TRY(sp_unpack_im2col(tmp, grads + L.w_off, d.k, d.cin, d.cout, st));
+                        if (L.b_off >= 0 && !L.bias_grad_zero) CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
+                    }
+                    if (want_dx) {
+                        const TcConvLaunch& tl = c->tc[i].dgrad[0];
+                        TcConvArgs a = tl.a;
+                        a.nb = nb;
+                        CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, big, nullptr, a, fl, st));
+                        CG_TRY(sp_col2im(big, (bf16*)dx, nb, h, w, d.cin, oh, ow, d.k, d.stride, g.pt, g.pl, st));
                     }
                     break;
                 }

@@ -21,7 +21,7 @@ struct TcLayer {
     int wg_x_is_dy = 0;                 // Conv2DTranspose: the "X" operand of the weight gradient is dY
     size_t sc_tmp = 0;                  // TC_STEM / TC_HEAD: offset of the fp32 weight-gradient staging buffer in the scratch
 };
-enum { TC_NONE = 0, TC_S1_VALID = 1, TC_CONV_S2 = 2, TC_CONVT_S2 = 3, TC_STEM = 4, TC_HEAD = 5, TC_S1_16 = 6 };
+enum { TC_NONE = 0, TC_S1_VALID = 1, TC_CONV_S2 = 2, TC_CONVT_S2 = 3, TC_STEM = 4, TC_HEAD = 5, TC_S1_16 = 6, TC_IM2COL = 7 };
 
 struct LayerInfo {
     cg_layer_desc d;

@@ -175,6 +175,33 @@ def test_tc_wgrad16_matches_cuda_core(cin, cout, k, h, w, n):
     assert C.rel_l2(ga[0], gb[0]) <= 1e-2, C.rel_l2(ga[0], gb[0])
 
 
+@pytest.mark.parametrize("cin,cout,k,h,w,n", [(3, 64, 4, 64, 64, 2), (3, 64, 4, 256, 256, 1), (3, 128, 3, 32, 64, 3), (4, 64, 4, 128, 32, 2)])
+def test_tc_im2col_input_layer_matches_cuda_core(cin, cout, k, h, w, n):
+    """The discriminators' input layer (resnet.py:96, Conv k s2 'same' on the image): receptive fields unfolded into one dense
+    64-channel chunk, 1x1 tensor-core GEMM forward, tap-stacked weight gradient, GEMM + col2im data gradient."""
+    g = ir.Graph(channels=[cin])
+    x_ = g.conv(g.input, cout, k, stride=2, padding='same')
+    x_ = g.instance_norm(x_, affine=False)
+    x_ = g.act(x_, ir.ACT_LEAKY, 0.2)
+    x_ = g.conv(x_, 2 * cout, 4, stride=2, padding='same')
+    x_ = g.instance_norm(x_, affine=False)
+    a, b = _make(g, True), _make(g, False)
+    rng = np.random.RandomState(9)
+    ws = [_bf16_round(v + (rng.normal(0, 0.05, v.shape) if v.ndim == 1 else 0)) for v in a.get_weights()]
+    a.set_weights(ws)
+    b.set_weights(ws)
+    x = _bf16_round(rng.uniform(-1, 1, (n, h, w, cin)))
+    dy = _bf16_round(rng.normal(0, 1, (n, h // 4, w // 4, 2 * cout)))
+    ya, dxa, ga = _net_grads(a, x, dy)
+    yb, dxb, gb = _net_grads(b, x, dy)
+    assert C.rel_l2(ya, yb) <= 4e-3, C.rel_l2(ya, yb)
+    assert C.rel_l2(dxa, dxb) <= 3e-2, C.rel_l2(dxa, dxb)
+    scale = max(np.linalg.norm(v) for v in gb)
+    for i, (u, v) in enumerate(zip(ga, gb)):
+        e = np.linalg.norm(u - v) / max(np.linalg.norm(v), 0.02 * scale)
+        assert e <= 3e-2, (i, u.shape, e)
+
+
 @pytest.mark.parametrize("f,h,w,n", [(64, 64, 64, 2), (64, 32, 128, 3), (128, 256, 256, 1)])
 def test_tc_stem_and_head_match_cuda_core(f, h, w, n):
     g = _stem_head_net(f)
