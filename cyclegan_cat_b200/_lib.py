@@ -20,9 +20,19 @@ SIGNATURES = {
     "cg_init": (c_int, [c_int]),
     "cg_last_error": (ctypes.c_char_p, []),
     "cg_version": (c_int, []),
+    "cg_abi_sizeof": (c_int, [c_int]),
     "cg_net_create": (c_int, [ctypes.POINTER(LayerDesc), c_int, c_int, ctypes.POINTER(c_void_p)]),
     "cg_net_destroy": (None, [c_void_p]),
     "cg_net_param_floats": (c_int, [c_void_p, ctypes.POINTER(c_i64)]),
+    "cg_net_state_floats": (c_int, [c_void_p, ctypes.POINTER(c_i64)]),
+    "cg_net_bind_state": (c_int, [c_void_p, c_void_p]),
+    "cg_net_set_training": (c_int, [c_void_p, c_int]),
+    "cg_net_set_seed": (c_int, [c_void_p, ctypes.c_uint64]),
+    "cg_normalize_u8": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cg_postprocess_u8": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cg_resize_bilinear": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "cg_resize_crop_flip": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     "cg_net_var_count": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
     "cg_net_var_info": (c_int, [c_void_p, c_int, ctypes.POINTER(VarInfo)]),
     "cg_net_out_shape": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_int * 4)]),
@@ -73,6 +83,11 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    from .ir import AdamCfg
+    for which, mirror in enumerate((LayerDesc, VarInfo, TrainCfg, AdamCfg)):
+        if lib.cg_abi_sizeof(which) != ctypes.sizeof(mirror):
+            raise NativeError(f"{LIB_PATH} is stale: sizeof({mirror.__name__}) is {lib.cg_abi_sizeof(which)} in the "
+                              f"library, {ctypes.sizeof(mirror)} in the binding -- rebuild it")
     _lib = lib
     return lib
 

@@ -19,7 +19,16 @@ void cg_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* cg_last_error(void) { return g_err; }
-extern "C" int cg_version(void) { return 100; }
+extern "C" int cg_version(void) { return 110; }
+extern "C" int cg_abi_sizeof(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(cg_layer_desc);
+        case 1: return (int)sizeof(cg_var_info);
+        case 2: return (int)sizeof(cg_train_cfg);
+        case 3: return (int)sizeof(cg_adam_cfg);
+        default: return -1;
+    }
+}
 
 extern "C" int cg_init(int device) {
     int n = 0;
@@ -67,7 +76,8 @@ extern "C" int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode
     for (int i = 0; i < n_layers; ++i)
         if (layers[i].in0 == 0) { net->chan[0] = layers[i].cin; break; }
     if (net->chan[0] <= 0) return fail("tensor 0 is never consumed", 0);
-    long long off = 0;
+    long long off = 0, soff = 0;
+    int n_drop = 0;
     for (int i = 0; i < n_layers; ++i) {
         LayerInfo& L = net->layers[i];
         L.d = layers[i];
@@ -105,6 +115,23 @@ extern "C" int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode
                 net->chan[i + 1] = d.cin;
                 if (d.affine) { L.g_off = add_var(2, 1, d.cin, 0, 0, 0); L.be_off = add_var(3, 1, d.cin, 0, 0, 0); }
                 break;
+            case CG_OP_BNORM:
+                // BatchNormalization runs on the instance-norm kernels with its statistics tables pooled over the samples
+                // of a call; from here on the layer is an INORM with `batch` set.  Trainable: [gamma, beta] when affine
+                // (Keras center/scale); non-trainable: [moving_mean, moving_variance].
+                if (!(d.momentum >= 0.f && d.momentum < 1.f)) return fail("BatchNormalization momentum must be in [0, 1)", i);
+                L.d.op = CG_OP_INORM;
+                L.batch = true;
+                net->chan[i + 1] = d.cin;
+                if (d.affine) { L.g_off = add_var(2, 1, d.cin, 0, 0, 0); L.be_off = add_var(3, 1, d.cin, 0, 0, 0); }
+                L.mm_off = soff; soff += d.cin;
+                L.mv_off = soff; soff += d.cin;
+                break;
+            case CG_OP_DROPOUT:
+                if (!(d.rate >= 0.f && d.rate < 1.f)) return fail("Dropout rate must be in [0, 1)", i);
+                net->chan[i + 1] = d.cin;
+                L.drop_index = n_drop++;
+                break;
             case CG_OP_ACT:
                 if (d.act < CG_ACT_RELU || d.act > CG_ACT_SIGMOID) return fail("unknown activation", i);
                 net->chan[i + 1] = d.cin;
@@ -128,6 +155,7 @@ extern "C" int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode
         net->dep_params[i + 1] = params_here || net->dep_params[d.in0] || (two && net->dep_params[d.in1]);
     }
     net->n_params = off;
+    net->n_state = soff;
     // fold ReLU / LeakyReLU into the instance norm that feeds only them
     for (int i = 0; i + 1 < n_layers; ++i) {
         LayerInfo& L = net->layers[i];
@@ -250,6 +278,27 @@ extern "C" int cg_net_param_floats(cg_net_t net, int64_t* n) {
     *n = net->n_params;
     return CG_OK;
 }
+extern "C" int cg_net_state_floats(cg_net_t net, int64_t* n) {
+    if (!net || !n) { cg_set_error("null argument"); return CG_ERR_INVALID; }
+    *n = net->n_state;
+    return CG_OK;
+}
+extern "C" int cg_net_bind_state(cg_net_t net, float* state_dev) {
+    if (!net || (!state_dev && net->n_state)) { cg_set_error("cg_net_bind_state: null argument"); return CG_ERR_INVALID; }
+    net->state = state_dev;
+    return CG_OK;
+}
+extern "C" int cg_net_set_training(cg_net_t net, int training) {
+    if (!net) { cg_set_error("null argument"); return CG_ERR_INVALID; }
+    net->training = training != 0;
+    return CG_OK;
+}
+extern "C" int cg_net_set_seed(cg_net_t net, uint64_t seed) {
+    if (!net) { cg_set_error("null argument"); return CG_ERR_INVALID; }
+    net->seed = seed;
+    net->calls = 0;
+    return CG_OK;
+}
 extern "C" int cg_net_var_count(cg_net_t net, int* n) {
     if (!net || !n) { cg_set_error("null argument"); return CG_ERR_INVALID; }
     *n = (int)net->vars.size();
@@ -318,6 +367,13 @@ extern "C" int cg_net_forward(cg_net_t net, const float* params, const float* x,
     sc->ctx.ext_input = nullptr;
     sc->ctx.packed = (char*)ws + sc->lay.packed;
     sc->ctx.tcs = (char*)ws + sc->lay.tcs;
+    sc->ctx.bn_group = 0;                       // one Keras call
+    sc->ctx.training = net->training != 0;
+    sc->ctx.defer_moving = false;
+    sc->ctx.drop_ctr_dev = nullptr;
+    sc->ctx.drop_ctr_host = net->calls;
+    sc->ctx.call_id[0] = 0;
+    if (net->training) net->calls += 1;
     CG_TRY(net_bind(&sc->ctx));
     CG_TRY(net_pack(net, params, sc->ctx.packed, st));
     const int tout = net->out_tensor();

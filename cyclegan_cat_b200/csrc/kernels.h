@@ -37,7 +37,8 @@ template <typename T> int k_in_bwd_apply_stream(const T* x, const T* dy, T* dx, 
 template <typename T> int k_in_bwd(const T* x, const T* dy, T* dx, const float* stats, const float* gamma,
                                    const float* beta, float* dgamma, float* dbeta, float* scratch, int act,
                                    float slope, int N, int P, int C, int accumulate, cudaStream_t st,
-                                   int halo = 0, int W = 0, bool zeroed = false);   // zeroed: `scratch` is already cleared
+                                   int halo = 0, int W = 0, bool zeroed = false,    // zeroed: `scratch` is already cleared
+                                   int bn_group = 0);   // > 0: BatchNormalization, statistics pooled over bn_group samples
 
 // ---- elementwise / data movement ----
 template <typename T> int k_act_fwd(const T* x, T* y, size_t n, int act, float slope, cudaStream_t st);
@@ -67,3 +68,26 @@ template <typename T> int k_l1_loss(const T* real, const T* gen, size_t n, float
                                     float* sum_out, cudaStream_t st);
 int k_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float b1, float b2, float eps,
            float grad_scale, cudaStream_t st);
+
+// ---- optional config paths and input pipeline (kernels_extra.cu) ----
+// coefficients of one optimizer step, computed on the host in double (trainer.cu)
+struct OptCoef { float lr, b1, b2, eps, c_m, c_v, r_t, gscale; int rect; };
+int k_opt_step(int kind, float* p, const float* g, float* m, float* v, size_t n, const OptCoef& c, cudaStream_t st);
+// BatchNormalization on the instance-norm tables: `group` consecutive samples form one Keras call
+template <typename T> int k_in_stats_raw(const T* x, float* stats, int N, int P, int C, cudaStream_t st, bool zeroed);
+int k_bn_finalize(float* stats, float* bstat, int N, int C, int group, int P, float eps, cudaStream_t st);
+int k_bn_fill(float* stats, const float* moving_mean, const float* moving_var, int N, int C, float eps, cudaStream_t st);
+int k_bn_update_moving(float* moving_mean, float* moving_var, const float* bstat, int C, float momentum, cudaStream_t st);
+int k_bn_pool_sums(float* sums, int N, int C, int group, cudaStream_t st);
+// Dropout: the mask of element e of group g is a hash of (seed, counter, call_id[g], layer, e)
+struct DropKey {
+    unsigned long long seed, ctr_host;
+    const unsigned long long* ctr_dev;      // when non-null the counter is read on the device (CUDA-graph replays)
+    int call_id[4];
+    int layer;
+};
+template <typename T> int k_dropout_fwd(const T* x, T* y, size_t group_elems, int groups, float rate, const DropKey& key,
+                                        int training, cudaStream_t st);
+template <typename T> int k_dropout_bwd(const T* dy, T* dx, size_t group_elems, int groups, float rate, const DropKey& key,
+                                        int training, int accumulate, cudaStream_t st);
+int k_set_counter(unsigned long long* ctr_dev, unsigned long long value, cudaStream_t st);

@@ -127,16 +127,18 @@ int k_in_finalize(float* stats, int NC, int P, float eps, cudaStream_t st) {
     return CG_OK;
 }
 
-template <typename T> int k_in_stats(const T* x, float* stats, int N, int P, int C, float eps, cudaStream_t st, bool zeroed) {
+// raw (sum x, sum x^2) per (sample, channel); k_in_stats turns them into (mean, rstd), k_bn_finalize pools them first
+template <typename T> int k_in_stats_raw(const T* x, float* stats, int N, int P, int C, cudaStream_t st, bool zeroed) {
     if (!zeroed) CG_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)N * C, st));
-    if (k_in_stream_ok<T>(x, nullptr, nullptr, P, C)) {
-        CG_TRY(k_in_stats_stream<T>(x, stats, N, P, C, st));
-        return k_in_finalize(stats, N * C, P, eps, st);
-    }
+    if (k_in_stream_ok<T>(x, nullptr, nullptr, P, C)) return k_in_stats_stream<T>(x, stats, N, P, C, st);
     dim3 grid; int pchunk;
     in_reduce_grid(N, P, C, grid, pchunk);
     in_reduce_kernel<T, 0><<<grid, 256, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, stats, P, C, pchunk, 0, 0.f);
     CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+template <typename T> int k_in_stats(const T* x, float* stats, int N, int P, int C, float eps, cudaStream_t st, bool zeroed) {
+    CG_TRY(k_in_stats_raw<T>(x, stats, N, P, C, st, zeroed));
     return k_in_finalize(stats, N * C, P, eps, st);
 }
 
@@ -382,7 +384,7 @@ __global__ void in_param_grad_kernel(const float* __restrict__ sums, float* __re
 template <typename T> int k_in_bwd(const T* x, const T* dy, T* dx, const float* stats, const float* gamma,
                                    const float* beta, float* dgamma, float* dbeta, float* scratch, int act,
                                    float slope, int N, int P, int C, int accumulate, cudaStream_t st, int halo, int W,
-                                   bool zeroed) {
+                                   bool zeroed, int bn_group) {
     if (!zeroed) CG_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * 2 * (size_t)N * C, st));
     // (a register-resident, 16-byte-vector variant of this reduction was measured slower -- 51 us vs 43 us per trunk
     // launch -- than the lanes-over-channels kernel with its 6 resident blocks per SM, so the simple kernel stays)
@@ -395,6 +397,7 @@ template <typename T> int k_in_bwd(const T* x, const T* dy, T* dx, const float* 
         in_reduce_kernel<T, 1><<<grid, 256, 0, st>>>(x, dy, stats, gamma, beta, scratch, P, C, pchunk, act, slope);
         CG_LAUNCH_CHECK();
     }
+    if (bn_group > 0) CG_TRY(k_bn_pool_sums(scratch, N, C, bn_group, st));
     if (dgamma) {
         in_param_grad_kernel<<<cdiv(C, 128), 128, 0, st>>>(scratch, dgamma, dbeta, N, C);
         CG_LAUNCH_CHECK();
@@ -847,10 +850,11 @@ int k_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, f
     template int k_convert_in<T>(const float*, T*, size_t, cudaStream_t);                                       \
     template int k_convert_out<T>(const T*, float*, size_t, cudaStream_t);                                      \
     template int k_in_stats<T>(const T*, float*, int, int, int, float, cudaStream_t, bool);                     \
+    template int k_in_stats_raw<T>(const T*, float*, int, int, int, cudaStream_t, bool);                        \
     template int k_in_apply<T>(const T*, T*, const float*, const float*, const float*, int, float, int, int, int, \
                                cudaStream_t);                                                                   \
     template int k_in_bwd<T>(const T*, const T*, T*, const float*, const float*, const float*, float*, float*,  \
-                             float*, int, float, int, int, int, int, cudaStream_t, int, int, bool);             \
+                             float*, int, float, int, int, int, int, cudaStream_t, int, int, bool, int);        \
     template int k_act_fwd<T>(const T*, T*, size_t, int, float, cudaStream_t);                                  \
     template int k_act_bwd<T>(const T*, const T*, T*, size_t, int, float, int, cudaStream_t);                   \
     template int k_rpad_fwd<T>(const T*, T*, int, int, int, int, int, cudaStream_t);                            \

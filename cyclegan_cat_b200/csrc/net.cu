@@ -93,6 +93,7 @@ int net_plan(const cg_net_s* net, int N, int H, int W, bool bwd, CallCtx* ctx) {
         off += align_up((size_t)N * ctx->sample_elems((int)t) * es, 256);
     }
     ctx->stat_off.assign(nl, 0);
+    ctx->bstat_off.assign(nl, 0);
     ctx->stat_begin = off;
     size_t max_nc = 1;
     for (size_t i = 0; i < nl; ++i) {
@@ -101,6 +102,10 @@ int net_plan(const cg_net_s* net, int N, int H, int W, bool bwd, CallCtx* ctx) {
             ctx->stat_off[i] = off;
             off += align_up((size_t)N * d.cin * 2 * sizeof(float), 256);
             if ((size_t)N * d.cin > max_nc) max_nc = (size_t)N * d.cin;
+            if (net->layers[i].batch) {      // per-group batch statistics (at most N groups)
+                ctx->bstat_off[i] = off;
+                off += align_up((size_t)N * d.cin * 2 * sizeof(float), 256);
+            }
         }
     }
     ctx->act_bytes = off;
@@ -595,6 +600,26 @@ int net_bind(CallCtx* c) {
 }
 
 // ------------------------------------------------------------------------------------------
+static DropKey drop_key(const CallCtx* c, const LayerInfo& L) {
+    DropKey k;
+    k.seed = c->net->seed; k.ctr_host = c->drop_ctr_host; k.ctr_dev = c->drop_ctr_dev;
+    for (int g = 0; g < 4; ++g) k.call_id[g] = c->call_id[g];
+    k.layer = L.drop_index;
+    return k;
+}
+
+int net_update_moving(CallCtx* c, int g, cudaStream_t st) {
+    const cg_net_s* net = c->net;
+    for (size_t i = 0; i < net->layers.size(); ++i) {
+        const LayerInfo& L = net->layers[i];
+        if (!L.batch) continue;
+        if (!net->state) { cg_set_error("BatchNormalization without bound state"); return CG_ERR_STATE; }
+        const float* bstat = (const float*)(c->base + c->bstat_off[i]) + (size_t)g * L.d.cin * 2;
+        CG_TRY(k_bn_update_moving(net->state + L.mm_off, net->state + L.mv_off, bstat, L.d.cin, L.d.momentum, st));
+    }
+    return CG_OK;
+}
+
 template <typename T>
 static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
     const cg_net_s* net = c->net;
@@ -613,7 +638,8 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
         // ... when its main loop is long enough to hide the extra epilogue work (the column sums double the epilogue of a
         // 32-column chunk); the 3-K-step stem is faster with the separate streaming statistics pass
         const bool long_k = L.tc != TC_STEM && L.tc != TC_IM2COL;
-        if (c->tc[i].on && L.feeds_in && L.tc != TC_HEAD && long_k && i + 1 < net->layers.size()) {
+        const bool bn_infer = i + 1 < net->layers.size() && net->layers[i + 1].batch && !c->training;
+        if (c->tc[i].on && L.feeds_in && L.tc != TC_HEAD && long_k && i + 1 < net->layers.size() && !bn_infer) {
             fused_stats = (float*)(c->base + c->stat_off[i + 1]);
             stats_done[i + 1] = 1;
         }
@@ -672,7 +698,23 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
             }
             case CG_OP_INORM: {
                 float* stats = (float*)(c->base + c->stat_off[i]);
-                if (stats_done[i]) CG_TRY(k_in_finalize(stats, N * d.cin, h * w, d.eps, st));
+                if (L.batch) {
+                    if (!net->state) { cg_set_error("layer %d: BatchNormalization without bound state (cg_net_bind_state)", (int)i); return CG_ERR_STATE; }
+                    float* mm = net->state + L.mm_off;
+                    float* mv = net->state + L.mv_off;
+                    if (c->training) {
+                        const int grp = c->bn_group > 0 ? c->bn_group : N;
+                        if (N % grp) { cg_set_error("batch %d is not a multiple of the call size %d", N, grp); return CG_ERR_INVALID; }
+                        if (!stats_done[i]) CG_TRY(k_in_stats_raw<T>(x, stats, N, h * w, d.cin, st, /*zeroed=*/true));
+                        float* bstat = (float*)(c->base + c->bstat_off[i]);
+                        CG_TRY(k_bn_finalize(stats, bstat, N, d.cin, grp, h * w, d.eps, st));
+                        if (!c->defer_moving)
+                            for (int g = 0; g < N / grp; ++g)
+                                CG_TRY(k_bn_update_moving(mm, mv, bstat + (size_t)g * d.cin * 2, d.cin, d.momentum, st));
+                    } else {
+                        CG_TRY(k_bn_fill(stats, mm, mv, N, d.cin, d.eps, st));
+                    }
+                } else if (stats_done[i]) CG_TRY(k_in_finalize(stats, N * d.cin, h * w, d.eps, st));
                 else CG_TRY(k_in_stats<T>(x, stats, N, h * w, d.cin, d.eps, st, /*zeroed=*/true));
                 const float* gam = L.g_off >= 0 ? params + L.g_off : nullptr;
                 const float* bet = L.be_off >= 0 ? params + L.be_off : nullptr;
@@ -728,6 +770,12 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
             }
             case CG_OP_AVGPOOL: CG_TRY(k_avgpool_fwd<T>(x, y, N, h, w, d.cin, st)); break;
             case CG_OP_UPSAMPLE: CG_TRY(k_upsample_fwd<T>(x, y, N, h, w, d.cin, st)); break;
+            case CG_OP_DROPOUT: {
+                const int grp = c->bn_group > 0 ? c->bn_group : N;
+                if (N % grp || N / grp > 4) { cg_set_error("dropout: batch %d / call size %d", N, grp); return CG_ERR_INVALID; }
+                CG_TRY(k_dropout_fwd<T>(x, y, (size_t)grp * c->sample_elems(tin), N / grp, d.rate, drop_key(c, L), c->training ? 1 : 0, st));
+                break;
+            }
             default: cg_set_error("unknown op %d", d.op); return CG_ERR_INVALID;
         }
     }
@@ -960,10 +1008,16 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
             case CG_OP_INORM: {
                 const float* stats = (const float*)(c->base + c->stat_off[i]) + (size_t)n0 * d.cin * 2;
                 bool pg = grads && L.g_off >= 0;
+                int grp = 0;
+                if (L.batch) {
+                    if (!c->training) { cg_set_error("layer %d: backward through an inference-mode BatchNormalization", i); return CG_ERR_STATE; }
+                    grp = c->bn_group > 0 ? c->bn_group : c->N;
+                    if (n0 % grp || nb % grp) { cg_set_error("sub-batch [%d,%d) splits a BatchNormalization call of %d", n0, n0 + nb, grp); return CG_ERR_INVALID; }
+                }
                 CG_TRY(k_in_bwd<T>(A(tin), dy, dx, stats, L.g_off >= 0 ? params + L.g_off : nullptr,
                                    L.be_off >= 0 ? params + L.be_off : nullptr, pg ? grads + L.g_off : nullptr,
                                    pg ? grads + L.be_off : nullptr, (float*)(c->arena + c->sums_off[i]), L.fused_act,
-                                   L.fused_slope, nb, h * w, d.cin, acc, st, c->grad_halo[tin], w, /*zeroed=*/true));
+                                   L.fused_slope, nb, h * w, d.cin, acc, st, c->grad_halo[tin], w, /*zeroed=*/true, grp));
                 break;
             }
             case CG_OP_ACT:
@@ -1022,6 +1076,15 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                 break;
             case CG_OP_UPSAMPLE:
                 if (want_dx) CG_TRY(k_upsample_bwd<T>(dy, dx, nb, h, w, d.cin, acc, st));
+                break;
+            case CG_OP_DROPOUT:
+                if (want_dx) {
+                    const int grp = c->bn_group > 0 ? c->bn_group : c->N;
+                    if (n0 % grp || nb % grp) { cg_set_error("sub-batch [%d,%d) splits a dropout call of %d", n0, n0 + nb, grp); return CG_ERR_INVALID; }
+                    DropKey key = drop_key(c, L);
+                    for (int g = 0; g < 4; ++g) key.call_id[g] = c->call_id[(n0 / grp + g) & 3];
+                    CG_TRY(k_dropout_bwd<T>(dy, dx, (size_t)grp * c->sample_elems(tin), nb / grp, d.rate, key, c->training ? 1 : 0, acc, st));
+                }
                 break;
             default: cg_set_error("unknown op %d", d.op); return CG_ERR_INVALID;
         }

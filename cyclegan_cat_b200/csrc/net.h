@@ -36,6 +36,9 @@ struct LayerInfo {
     int fuse_add = -1;             // INORM whose only consumer is a residual ADD: index of that ADD layer
     bool feeds_in = false;         // the conv output feeds ONLY an instance norm (statistics fused into the conv epilogue)
     bool bias_grad_zero = false;   // the conv output feeds ONLY an instance norm: d(loss)/d(bias) == 0 exactly
+    bool batch = false;            // INORM that is a BatchNormalization: statistics pooled over the samples of one call
+    long long mm_off = -1, mv_off = -1;   // BatchNormalization: offsets (floats) of moving_mean / moving_variance in the state
+    int drop_index = -1;           // DROPOUT: ordinal among the net's dropout layers (part of the mask key)
     int tc = 0;             // TC_* kind: which convs run on the tcgen05 kernels in bf16 mode
     long long pk_f = 0, pk_d = 0;   // byte offsets of the packed bf16 weights ([tap][Cout][Cin] / [tap][Cin][Cout])
 };
@@ -49,6 +52,11 @@ struct cg_net_s {
     std::vector<char> dep_params;       // tensor depends on some trainable variable
     std::vector<cg_var_info> vars;
     long long n_params = 0;
+    long long n_state = 0;              // non-trainable floats (BatchNormalization moving statistics)
+    float* state = nullptr;             // caller-owned device buffer of n_state floats (cg_net_bind_state)
+    int training = 0;                   // Keras `training=` of the next single-net forward (cg_net_set_training)
+    unsigned long long seed = 0;        // dropout stream (cg_net_set_seed)
+    unsigned long long calls = 0;       // training-mode single-net forwards so far (dropout counter)
     size_t packed_bytes = 0;            // bf16 weight copies for the tensor-core layers
     int out_tensor() const { return (int)layers.size(); }
     size_t elem_size() const { return mode == CG_MODE_BF16 ? 2 : 4; }
@@ -77,6 +85,15 @@ struct CallCtx {
     char* tcs = nullptr;                // scratch for the unfolded tensors of the 7x7 stem / head (conv_special.cu)
     size_t tcs_bytes = 0;
     std::vector<TcLayer> tc;            // per layer
+    // BatchNormalization / Dropout: the batch of this call is `N / bn_group` Keras calls of bn_group samples each
+    int bn_group = 0;                   // 0 = the whole batch is one call
+    bool training = false;              // batch statistics + moving-average update, active dropout
+    bool defer_moving = false;          // the caller applies the moving-average updates itself (net_update_moving), in the
+                                        // reference's call order
+    std::vector<size_t> bstat_off;      // per layer: (mean, unbiased variance) per group of a BatchNormalization [G][C][2]
+    unsigned long long drop_ctr_host = 0;
+    const unsigned long long* drop_ctr_dev = nullptr;
+    int call_id[4] = {0, 1, 2, 3};      // dropout: id of each group's Keras call within the step
     std::vector<int> grad_halo;         // per tensor: zero border of the gradient buffer (tensor-core layers)
 
     size_t sample_elems(int t) const { return (size_t)th[t] * tw[t] * net->chan[t]; }
@@ -94,3 +111,5 @@ int net_forward(CallCtx* ctx, const float* params, cudaStream_t st);
 // dx (nullable) receives dLoss/d(input); parameter gradients are ACCUMULATED into grads when non-null.
 int net_backward(CallCtx* ctx, const float* params, const void* dy, void* dx, float* grads, int n0, int nb,
                  cudaStream_t st);
+// BatchNormalization: fold group g's batch statistics of the last training forward into the moving averages
+int net_update_moving(CallCtx* ctx, int g, cudaStream_t st);

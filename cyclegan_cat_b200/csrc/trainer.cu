@@ -66,6 +66,8 @@ struct cg_trainer_s {
     float* params[4] = {}; float* grads[4] = {}; float* m[4] = {}; float* v[4] = {};
     char* ws = nullptr; size_t ws_bytes = 0;
     long long iters[4] = {0, 0, 0, 0};
+    unsigned long long train_calls = 0;         // training-mode steps so far: the dropout counter of the next one
+    size_t o_ctr = 0;                           // device copy of that counter (read by the dropout kernels, also in graph replays)
     // planned shape
     int B = 0, H = 0, W = 0; bool planned = false;
     CallCtx F1, F2, C1, C2, DA, DB;
@@ -128,6 +130,7 @@ static int trainer_layout(cg_trainer_t tr, int B, int H, int W, bool assign) {
     tr->o_advDA = take(B * dout); tr->o_advDB = take(B * dout);
     tr->o_sums = take(S_COUNT * sizeof(float));
     tr->o_metrics = take(8 * sizeof(float));
+    tr->o_ctr = take(sizeof(unsigned long long));
     off = align_up(off, 1024);
     for (int i = 0; i < 4; ++i) tr->o_packed[i] = take(align_up(tr->net[i]->packed_bytes, 1024));
     size_t tcs = 0;
@@ -139,6 +142,16 @@ static int trainer_layout(cg_trainer_t tr, int B, int H, int W, bool assign) {
         size_t bases[6] = {oF1, oF2, oC1, oC2, oDA, oDB};
         CallCtx* cs[6] = {&tr->F1, &tr->F2, &tr->C1, &tr->C2, &tr->DA, &tr->DB};
         for (int i = 0; i < 6; ++i) { cs[i]->base = tr->ws + bases[i]; cs[i]->arena = tr->ws + tr->o_arena; cs[i]->ext_input = nullptr; }
+        // BatchNormalization / Dropout see the Keras calls of model.py:93-106, not the concatenated batches: B samples per
+        // call; call ids = the order in which validate_step calls each model (g_AB: real_a, fake_a, real_b; g_BA: fake_b,
+        // real_b, real_a; d_A: real_a, fake_a; d_B: real_b, fake_b)
+        const int ids[6][2] = {{0, 2}, {1, 2}, {0, 0}, {1, 1}, {0, 1}, {0, 1}};
+        for (int i = 0; i < 6; ++i) {
+            cs[i]->bn_group = B;
+            cs[i]->defer_moving = true;
+            cs[i]->drop_ctr_dev = (const unsigned long long*)(tr->ws + tr->o_ctr);
+            cs[i]->call_id[0] = ids[i][0]; cs[i]->call_id[1] = ids[i][1];
+        }
         // cycle calls read the first half (the fakes) of F1 / F2's output in place
         tr->C1.ext_input = tr->F1.act(tr->net[0]->out_tensor());
         tr->C2.ext_input = tr->F2.act(tr->net[1]->out_tensor());
@@ -165,6 +178,11 @@ extern "C" int cg_trainer_create(cg_net_t g_AB, cg_net_t g_BA, cg_net_t d_A, cg_
         return CG_ERR_INVALID;
     }
     if (cfg->loss < CG_LOSS_MSE || cfg->loss > CG_LOSS_BCE) { cg_set_error("unknown loss %d", cfg->loss); return CG_ERR_INVALID; }
+    for (int i = 0; i < 4; ++i)
+        if (cfg->adam[i].kind < CG_OPT_ADAM || cfg->adam[i].kind > CG_OPT_ADABELIEF) {
+            cg_set_error("unknown optimizer kind %d for net %d", cfg->adam[i].kind, i);
+            return CG_ERR_INVALID;
+        }
     cg_trainer_s* tr = new cg_trainer_s();
     tr->net[0] = g_AB; tr->net[1] = g_BA; tr->net[2] = d_A; tr->net[3] = d_B;
     tr->cfg = *cfg;
@@ -235,6 +253,7 @@ static int step_body(cg_trainer_t tr, int B, int H, int W, bool train, cudaStrea
     const T* rb = Xab + B * img;
 
     // ---- forward --------------------------------------------------------------------------
+    for (CallCtx* c : {&tr->F1, &tr->F2, &tr->C1, &tr->C2, &tr->DA, &tr->DB}) c->training = train;   // model.py:138-141 / :221
     CG_TRY(net_forward(&tr->F1, tr->params[0], st));
     CG_TRY(net_forward(&tr->F2, tr->params[1], st));
     CG_TRY(net_forward(&tr->C1, tr->params[1], st));    // g_BA(fake_b)
@@ -253,6 +272,12 @@ static int step_body(cg_trainer_t tr, int B, int H, int W, bool train, cudaStrea
     CG_TRY(net_forward(&tr->DB, tr->params[3], st));
     const T* dA = (const T*)tr->DA.act(tDa);            // [disc_real_a ; disc_fake_a]
     const T* dB = (const T*)tr->DB.act(tDb);
+    if (train) {    // BatchNormalization moving averages, one update per Keras call in the order of model.py:93-106
+        if (tr->net[0]->n_state) { CG_TRY(net_update_moving(&tr->F1, 0, st)); CG_TRY(net_update_moving(&tr->C2, 0, st)); CG_TRY(net_update_moving(&tr->F1, 1, st)); }
+        if (tr->net[1]->n_state) { CG_TRY(net_update_moving(&tr->C1, 0, st)); CG_TRY(net_update_moving(&tr->F2, 0, st)); CG_TRY(net_update_moving(&tr->F2, 1, st)); }
+        if (tr->net[2]->n_state) { CG_TRY(net_update_moving(&tr->DA, 0, st)); CG_TRY(net_update_moving(&tr->DA, 1, st)); }
+        if (tr->net[3]->n_state) { CG_TRY(net_update_moving(&tr->DB, 0, st)); CG_TRY(net_update_moving(&tr->DB, 1, st)); }
+    }
 
     // ---- losses (+ gradient seeds when training) ---------------------------------------------
     const size_t n_d = (size_t)B * dout, n_img = (size_t)B * img;
@@ -330,6 +355,13 @@ static int step_T(cg_trainer_t tr, const float* real_a, const float* real_b, int
     CG_TRY(k_convert_in<T>(real_b, Xab + B * img, B * img, st));
     CG_TRY(k_convert_in<T>(real_b, Xba, B * img, st));
     CG_TRY(k_convert_in<T>(real_a, Xba + B * img, B * img, st));
+    if (train) {
+        bool any_drop = false;
+        for (int i = 0; i < 4; ++i)
+            for (const LayerInfo& L : tr->net[i]->layers) any_drop |= L.drop_index >= 0;
+        if (any_drop) CG_TRY(k_set_counter((unsigned long long*)(tr->ws + tr->o_ctr), tr->train_calls, st));
+        tr->train_calls += 1;
+    }
 
     // ---- body: replay the captured graph, capture it, or run it eagerly ------------------------
     const char* goff = getenv("CG_DISABLE_GRAPH");      // read per call: tests switch it between trainers
@@ -401,9 +433,25 @@ extern "C" int cg_trainer_apply_gradients(cg_trainer_t tr, void* stream) {
     for (int i = 0; i < 4; ++i) {
         const cg_adam_cfg& a = tr->cfg.adam[i];
         const double t = (double)(tr->iters[i] + 1);
-        const double lr_t = (double)a.learning_rate * sqrt(1.0 - pow((double)a.beta_2, t)) / (1.0 - pow((double)a.beta_1, t));
-        CG_TRY(k_adam(tr->params[i], tr->grads[i], tr->m[i], tr->v[i], (size_t)tr->net[i]->n_params, (float)lr_t,
-                      a.beta_1, a.beta_2, a.epsilon, gscale, st));
+        const size_t n = (size_t)tr->net[i]->n_params;
+        if (a.kind == CG_OPT_ADAM) {
+            const double lr_t = (double)a.learning_rate * sqrt(1.0 - pow((double)a.beta_2, t)) / (1.0 - pow((double)a.beta_1, t));
+            CG_TRY(k_adam(tr->params[i], tr->grads[i], tr->m[i], tr->v[i], n, (float)lr_t, a.beta_1, a.beta_2, a.epsilon, gscale, st));
+        } else {
+            OptCoef c;
+            memset(&c, 0, sizeof(c));
+            c.lr = a.learning_rate; c.b1 = a.beta_1; c.b2 = a.beta_2; c.eps = a.epsilon; c.gscale = gscale;
+            if (a.kind == CG_OPT_ADABELIEF) {       // adabelief_tf: bias corrections and the RAdam rectification term
+                const double b1p = pow((double)a.beta_1, t), b2p = pow((double)a.beta_2, t);
+                const double sma_inf = 2.0 / (1.0 - (double)a.beta_2) - 1.0;
+                const double sma_t = sma_inf - 2.0 * t * b2p / (1.0 - b2p);
+                c.c_m = (float)(1.0 / (1.0 - b1p));
+                c.c_v = (float)(1.0 / (1.0 - b2p));
+                c.rect = sma_t >= 5.0 ? 1 : 0;      // sma_threshold default
+                c.r_t = c.rect ? (float)sqrt((sma_t - 4.0) / (sma_inf - 4.0) * (sma_t - 2.0) / (sma_inf - 2.0) * sma_inf / sma_t) : 0.f;
+            }
+            CG_TRY(k_opt_step(a.kind, tr->params[i], tr->grads[i], tr->m[i], tr->v[i], n, c, st));
+        }
         tr->iters[i] += 1;
     }
     return CG_OK;

@@ -133,7 +133,7 @@ class CycleGan:
             cfg.w_cycle, cfg.w_identity = w["cycle"], w["identity"]
             cfg.w_generator, cfg.w_discriminator = w["generator"], w["discriminator"]
             for i, o in enumerate(self._opts()):
-                cfg.adam[i] = ir.AdamCfg(o.learning_rate, o.beta_1, o.beta_2, o.epsilon)
+                cfg.adam[i] = ir.AdamCfg(o.learning_rate, o.beta_1, o.beta_2, o.epsilon, o.kind)
                 o._binding = (self, i)
             h = ctypes.c_void_p()
             nets = self._nets()
@@ -184,7 +184,12 @@ class CycleGan:
 
     # -- reference surface ---------------------------------------------------------------
     def validate_step(self, real_a, real_b, training: bool = False) -> Dict:
-        """model.py:91-134.  Instance norm behaves identically for training=True/False."""
+        """model.py:91-134 as the reference calls it outside the tape (model.py:221: training=False): moving
+        statistics for BatchNormalization, no dropout.  Instance norm is identical for training=True/False; with
+        BatchNormalization / Dropout nets, training=True (a forward that also moves the moving averages but
+        takes no gradient) is what `compute_gradients` runs, so it is served from there."""
+        if training and any(n.n_state or n.graph.has_dropout() for n in self._nets()):
+            return self._run("cg_trainer_compute_gradients", real_a, real_b)
         return self._run("cg_validate_step", real_a, real_b)
 
     def train_step(self, real_a, real_b) -> Dict:
@@ -248,22 +253,32 @@ class CycleGan:
         _lib.check(_lib.load().cg_trainer_get_iterations(self._trainer, ctypes.byref(it)), "get_iterations")
         return int(it[i])
 
+    def _slot_buffers(self, i):
+        """Device buffers behind the Keras slots of optimizer i, in slot creation order: Adam / AdaBelief (m, v);
+        RMSprop keeps `rms` in the v buffer; SGD has none."""
+        slots = self._opts()[i].slots
+        return [self._v[i]] if slots == ("rms",) else [self._m[i], self._v[i]][:len(slots)]
+
     def _optimizer_get_weights(self, i):
         net = self._nets()[i]
-        m, v = self._m[i].cpu().numpy(), self._v[i].cpu().numpy()
         sl = lambda f: [f[x.offset:x.offset + x.size].reshape(x.shape).copy() for x in net.trainable_variables]
-        return [np.int64(self._get_iterations(i))] + sl(m) + sl(v)
+        out = [np.int64(self._get_iterations(i))]
+        for buf in self._slot_buffers(i):
+            out += sl(buf.cpu().numpy())
+        return out
 
     def _optimizer_set_weights(self, i, weights):
         torch = _require_cuda()
         net = self._nets()[i]
         n = len(net.trainable_variables)
-        assert len(weights) == 1 + 2 * n
+        bufs = self._slot_buffers(i)
+        assert len(weights) == 1 + len(bufs) * n, (len(weights), len(bufs), n)
         it = (ctypes.c_int64 * 4)()
         _lib.check(_lib.load().cg_trainer_get_iterations(self._trainer, ctypes.byref(it)), "get_iterations")
         it[i] = int(weights[0])
         _lib.check(_lib.load().cg_trainer_set_iterations(self._trainer, ctypes.byref(it)), "set_iterations")
-        for dst, part in ((self._m[i], weights[1:1 + n]), (self._v[i], weights[1 + n:])):
+        for j, dst in enumerate(bufs):
+            part = weights[1 + j * n:1 + (j + 1) * n]
             flat = np.concatenate([np.asarray(a, np.float32).ravel() for a in part]) if n else np.zeros(0, np.float32)
             dst.copy_(torch.from_numpy(flat))
 

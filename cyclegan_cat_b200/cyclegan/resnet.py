@@ -91,8 +91,7 @@ def simple_discriminator(config: Dict, mode: str = "bf16") -> Model:
         if norm_type == 'instancenorm':
             x = g.instance_norm(x, affine=False)
         else:
-            raise NotImplementedError("BatchNormalization(center=False, scale=False) (resnet.py:100) is not "
-                                      "built for B200 (SURVEY 8f rank 4)")
+            x = g.batch_norm(x, affine=False)           # resnet.py:100 BatchNormalization(center=False, scale=False)
         x = g.act(x, ir.ACT_LEAKY, slope=0.2)
     x = g.conv(x, 1, 1, stride=1, padding='same')
     return Model(g, name="simple_discriminator", mode=mode)

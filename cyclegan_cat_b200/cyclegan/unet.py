@@ -13,21 +13,25 @@ from ..runtime import Model
 
 
 def _norm(g: ir.Graph, x, norm_type: str):
+    """strided_unet's choice (unet.py:55-58,69-72): 'instancenorm' or, for anything else, BatchNormalization()."""
     if norm_type == 'instancenorm':
         return g.instance_norm(x, affine=True)          # TFA default center=scale=True, eps 1e-3
-    raise NotImplementedError(
-        f"normalization={norm_type!r}: only 'instancenorm' is built for B200 (batchnorm is SURVEY 8f rank 4)")
+    return g.batch_norm(x, affine=True)                 # keras defaults: momentum .99, eps 1e-3, center=scale=True
 
 
 def double_conv(g: ir.Graph, x, filter: int, kernel_size: int,
                 norm_type: str = 'instancenorm', apply_dropout: bool = False):
-    """Two (Conv k s1 SAME no-bias -> norm -> ReLU) stages, unet.py:20-36."""
-    if apply_dropout:
-        raise NotImplementedError("dropout=True is not built for B200 (needs TF's RNG stream; SURVEY 8f rank 4)")
+    """Two (Conv k s1 SAME no-bias -> norm -> ReLU [-> Dropout(0.5)]) stages, unet.py:20-36.  As in the reference a
+    normalization string that is neither 'batchnorm' nor 'instancenorm' (case-insensitive) adds no norm layer."""
     for _ in range(2):
         x = g.conv(x, filter, kernel_size, stride=1, padding='same', use_bias=False)
-        x = _norm(g, x, norm_type.lower())
+        if norm_type.lower() == 'batchnorm':
+            x = g.batch_norm(x, affine=True)
+        elif norm_type.lower() == 'instancenorm':
+            x = g.instance_norm(x, affine=True)
         x = g.act(x, ir.ACT_RELU)
+        if apply_dropout:
+            x = g.dropout(x, 0.5)
     return x
 
 

@@ -11,7 +11,8 @@ from dataclasses import dataclass, field
 from typing import List
 
 # cg_op
-OP_CONV, OP_CONVT, OP_INORM, OP_ACT, OP_RPAD, OP_ADD, OP_CONCAT, OP_AVGPOOL, OP_UPSAMPLE = range(1, 10)
+(OP_CONV, OP_CONVT, OP_INORM, OP_ACT, OP_RPAD, OP_ADD, OP_CONCAT, OP_AVGPOOL, OP_UPSAMPLE, OP_BNORM,
+ OP_DROPOUT) = range(1, 12)
 # cg_act
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH, ACT_SIGMOID = range(5)
 ACT_BY_NAME = {None: ACT_NONE, "linear": ACT_NONE, "relu": ACT_RELU, "tanh": ACT_TANH, "sigmoid": ACT_SIGMOID}
@@ -20,6 +21,8 @@ LOSS_BY_NAME = {"mse": 0, "mae": 1, "bce": 2}
 # cg_mode
 MODE_BF16, MODE_FP32_CHECK = 0, 1
 MODE_BY_NAME = {"bf16": MODE_BF16, "fp32": MODE_FP32_CHECK}
+# cg_opt
+OPT_ADAM, OPT_SGD, OPT_RMSPROP, OPT_ADABELIEF = range(4)
 
 
 class LayerDesc(ctypes.Structure):
@@ -28,7 +31,8 @@ class LayerDesc(ctypes.Structure):
                 ("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("k", ctypes.c_int32),
                 ("stride", ctypes.c_int32), ("same", ctypes.c_int32), ("has_bias", ctypes.c_int32),
                 ("act", ctypes.c_int32), ("affine", ctypes.c_int32), ("pad", ctypes.c_int32),
-                ("eps", ctypes.c_float), ("slope", ctypes.c_float)]
+                ("eps", ctypes.c_float), ("slope", ctypes.c_float), ("momentum", ctypes.c_float),
+                ("rate", ctypes.c_float)]
 
 
 class VarInfo(ctypes.Structure):
@@ -39,7 +43,7 @@ class VarInfo(ctypes.Structure):
 
 class AdamCfg(ctypes.Structure):
     _fields_ = [("learning_rate", ctypes.c_float), ("beta_1", ctypes.c_float),
-                ("beta_2", ctypes.c_float), ("epsilon", ctypes.c_float)]
+                ("beta_2", ctypes.c_float), ("epsilon", ctypes.c_float), ("kind", ctypes.c_int32)]
 
 
 class TrainCfg(ctypes.Structure):
@@ -64,11 +68,14 @@ class Layer:
     pad: int = 0
     eps: float = 1e-3
     slope: float = 0.2
+    momentum: float = 0.99
+    rate: float = 0.0
     init: str = "normal"          # host-side only: kernel initializer kind
 
     def to_c(self) -> LayerDesc:
         return LayerDesc(self.op, self.in0, self.in1, self.cin, self.cout, self.k, self.stride, self.same,
-                         self.has_bias, self.act, self.affine, self.pad, self.eps, self.slope)
+                         self.has_bias, self.act, self.affine, self.pad, self.eps, self.slope, self.momentum,
+                         self.rate)
 
 
 @dataclass
@@ -103,6 +110,15 @@ class Graph:
     def instance_norm(self, x, affine=True, eps=1e-3):
         c = self.channels[x]
         return self._emit(Layer(OP_INORM, x, cin=c, cout=c, affine=int(affine), eps=eps), c)
+
+    def batch_norm(self, x, affine=True, eps=1e-3, momentum=0.99):
+        """keras BatchNormalization(): momentum 0.99, epsilon 1e-3; center/scale = `affine`."""
+        c = self.channels[x]
+        return self._emit(Layer(OP_BNORM, x, cin=c, cout=c, affine=int(affine), eps=eps, momentum=momentum), c)
+
+    def dropout(self, x, rate=0.5):
+        c = self.channels[x]
+        return self._emit(Layer(OP_DROPOUT, x, cin=c, cout=c, rate=rate), c)
 
     def act(self, x, kind, slope=0.2):
         c = self.channels[x]
@@ -144,10 +160,23 @@ class Graph:
                 specs.append(((L.k, L.k, L.cout, L.cin), L.init))
                 if L.has_bias:
                     specs.append(((L.cout,), "zeros"))
-            elif L.op == OP_INORM and L.affine:
+            elif L.op in (OP_INORM, OP_BNORM) and L.affine:
                 specs.append(((L.cin,), "ones"))
                 specs.append(((L.cin,), "zeros"))
         return specs
+
+    def state_specs(self):
+        """[(shape, init kind)] of the non-trainable variables in Keras order: per BatchNormalization
+        [moving_mean (zeros), moving_variance (ones)]."""
+        specs = []
+        for L in self.layers:
+            if L.op == OP_BNORM:
+                specs.append(((L.cin,), "zeros"))
+                specs.append(((L.cin,), "ones"))
+        return specs
+
+    def has_dropout(self) -> bool:
+        return any(L.op == OP_DROPOUT for L in self.layers)
 
     def to_c_array(self):
         arr = (LayerDesc * len(self.layers))()

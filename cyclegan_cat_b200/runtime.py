@@ -63,14 +63,17 @@ class DeviceTensor:
 
 
 class Variable:
-    """One entry of `model.trainable_variables` (a view into the flat parameter buffer)."""
+    """One entry of `model.trainable_variables` (a view into the flat parameter buffer) or, with
+    `state=True`, of `model.non_trainable_variables` (BatchNormalization moving statistics)."""
 
-    def __init__(self, model, index, shape, offset, role):
+    def __init__(self, model, index, shape, offset, role, state=False):
         self._model, self.index, self.shape, self.offset, self.role = model, index, tuple(shape), offset, role
         self.size = int(np.prod(shape))
+        self.state = state
 
     def numpy(self):
-        return self._model._flat_host()[self.offset:self.offset + self.size].reshape(self.shape).copy()
+        flat = self._model._state_flat_host() if self.state else self._model._flat_host()
+        return flat[self.offset:self.offset + self.size].reshape(self.shape).copy()
 
     def assign(self, value):
         self._model._assign(self, np.asarray(value, np.float32))
@@ -109,12 +112,24 @@ class Model:
         for L in graph.layers:
             if L.op in (ir.OP_CONV, ir.OP_CONVT):
                 roles += [0] + ([1] if L.has_bias else [])
-            elif L.op == ir.OP_INORM and L.affine:
+            elif L.op in (ir.OP_INORM, ir.OP_BNORM) and L.affine:
                 roles += [2, 3]
         self.trainable_variables: List[Variable] = [
             Variable(self, i, s, o, r) for i, ((s, _), o, r) in enumerate(zip(specs, offs, roles))]
         self._host = np.zeros(self.n_params, np.float32)
         self._dev = None            # flat float32 cuda tensor (master weights)
+        # non-trainable state: BatchNormalization [moving_mean (0), moving_variance (1)] per layer, Keras order
+        self.non_trainable_variables: List[Variable] = []
+        soff = 0
+        for i, (shape, _) in enumerate(graph.state_specs()):
+            self.non_trainable_variables.append(Variable(self, i, shape, soff, 4 + (i & 1), state=True))
+            soff += int(np.prod(shape))
+        self.n_state = soff
+        self._state_host = np.concatenate(
+            [(np.zeros if kind == "zeros" else np.ones)(shape, np.float32).ravel()
+             for shape, kind in graph.state_specs()]) if soff else np.zeros(0, np.float32)
+        self._state_dev = None
+        self._drop_seed = 0
         self._handle = None
         self._ws = {}
         self.owner = None           # set by CycleGan when a native trainer shares the buffer
@@ -151,25 +166,53 @@ class Model:
             self._host = self._dev.detach().cpu().numpy()
         return self._host
 
+    def _state_flat_host(self):
+        if self._state_dev is not None:
+            self._state_host = self._state_dev.detach().cpu().numpy()
+        return self._state_host
+
     def _assign(self, var: Variable, value):
         assert value.shape == var.shape, (value.shape, var.shape)
-        self._flat_host()[var.offset:var.offset + var.size] = value.ravel()
-        if self._dev is not None:
+        flat, dev = (self._state_flat_host(), self._state_dev) if var.state else (self._flat_host(), self._dev)
+        flat[var.offset:var.offset + var.size] = value.ravel()
+        if dev is not None:
             torch = _torch()
-            self._dev[var.offset:var.offset + var.size].copy_(torch.from_numpy(value.ravel().copy()))
+            dev[var.offset:var.offset + var.size].copy_(torch.from_numpy(value.ravel().copy()))
+
+    @property
+    def weights(self):
+        """keras `Model.weights`: the trainable variables, then the non-trainable ones."""
+        return self.trainable_variables + self.non_trainable_variables
 
     def get_weights(self):
-        return [v.numpy() for v in self.trainable_variables]
+        return [v.numpy() for v in self.weights]
 
     def set_weights(self, arrays: Sequence[np.ndarray]):
-        assert len(arrays) == len(self.trainable_variables)
+        """keras `Model.set_weights`; a list holding only the trainable variables is accepted too."""
+        nt = len(self.trainable_variables)
+        assert len(arrays) in (nt, nt + len(self.non_trainable_variables)), len(arrays)
         flat = self._flat_host()
-        for v, a in zip(self.trainable_variables, arrays):
+        for v, a in zip(self.trainable_variables, arrays[:nt]):
             a = np.asarray(a, np.float32)
             assert a.shape == v.shape, (a.shape, v.shape)
             flat[v.offset:v.offset + v.size] = a.ravel()
         self._host = flat
         self._push()
+        if len(arrays) > nt:
+            st = self._state_flat_host()
+            for v, a in zip(self.non_trainable_variables, arrays[nt:]):
+                a = np.asarray(a, np.float32)
+                assert a.shape == v.shape, (a.shape, v.shape)
+                st[v.offset:v.offset + v.size] = a.ravel()
+            self._state_host = st
+            if self._state_dev is not None:
+                self._state_dev.copy_(_torch().from_numpy(st))
+
+    def set_dropout_seed(self, seed: int):
+        """Seed of the counter-based dropout masks (also restarts the call counter)."""
+        self._drop_seed = int(seed) & (2 ** 64 - 1)
+        if self._handle is not None:
+            _lib.check(_lib.load().cg_net_set_seed(self._handle, ctypes.c_uint64(self._drop_seed)), "cg_net_set_seed")
 
     # -- native handle ---------------------------------------------------------------
     def handle(self):
@@ -184,6 +227,10 @@ class Model:
             _lib.check(lib.cg_net_param_floats(h, ctypes.byref(n)), "cg_net_param_floats")
             if n.value != self.n_params:
                 raise _lib.NativeError(f"parameter count mismatch host {self.n_params} vs native {n.value}")
+            _lib.check(lib.cg_net_state_floats(h, ctypes.byref(n)), "cg_net_state_floats")
+            if n.value != self.n_state:
+                raise _lib.NativeError(f"state size mismatch host {self.n_state} vs native {n.value}")
+            _lib.check(lib.cg_net_set_seed(h, ctypes.c_uint64(self._drop_seed)), "cg_net_set_seed")
             self._handle = h
         return self._handle
 
@@ -191,7 +238,16 @@ class Model:
         torch = _require_cuda()
         if self._dev is None:
             self._dev = torch.from_numpy(self._host).cuda()
+        self.device_state()
         return self._dev
+
+    def device_state(self):
+        """The moving statistics live in a caller-owned device buffer bound to the handle (cg_net_bind_state)."""
+        if self.n_state and self._state_dev is None:
+            torch = _require_cuda()
+            self._state_dev = torch.from_numpy(self._state_host).cuda()
+            _lib.check(_lib.load().cg_net_bind_state(self.handle(), _ptr(self._state_dev)), "cg_net_bind_state")
+        return self._state_dev
 
     def out_shape(self, N, H, W):
         out = (ctypes.c_int * 4)()
@@ -220,6 +276,7 @@ class Model:
             ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device="cuda")
             self._ws[key] = ws
         y = torch.empty(self.out_shape(N, H, W), dtype=torch.float32, device="cuda")
+        _lib.check(lib.cg_net_set_training(self.handle(), int(bool(training))), "cg_net_set_training")
         _lib.check(lib.cg_net_forward(self.handle(), _ptr(self.device_params()), _ptr(xd), _ptr(y), _ptr(ws),
                                       ws.numel(), N, H, W, 0, _stream_ptr(torch)), "cg_net_forward")
         return DeviceTensor(y)

@@ -53,7 +53,9 @@ typedef enum cg_op {
     CG_OP_ADD = 6,       /* Add               resnet.py:35                                       */
     CG_OP_CONCAT = 7,    /* Concatenate [in0, in1] on channels  unet.py:68,118                   */
     CG_OP_AVGPOOL = 8,   /* AveragePooling2D() 2x2/2   unet.py:101                               */
-    CG_OP_UPSAMPLE = 9   /* UpSampling2D() nearest x2  unet.py:109                               */
+    CG_OP_UPSAMPLE = 9,  /* UpSampling2D() nearest x2  unet.py:109                               */
+    CG_OP_BNORM = 10,    /* BatchNormalization  unet.py:27-28,57-58,71-72  resnet.py:99-100      */
+    CG_OP_DROPOUT = 11   /* Dropout(0.5)      unet.py:33-34                                      */
 } cg_op;
 
 typedef enum cg_act {
@@ -85,8 +87,10 @@ typedef struct cg_layer_desc {
     int32_t act;       /* cg_act (ACT layers)                                        */
     int32_t affine;    /* INORM: center=scale=True -> [gamma, beta] variables        */
     int32_t pad;       /* RPAD amount (same on H and W)                              */
-    float eps;         /* INORM epsilon (TFA default 1e-3)                           */
+    float eps;         /* INORM / BNORM epsilon (TFA and Keras default 1e-3)         */
     float slope;       /* LeakyReLU alpha                                            */
+    float momentum;    /* BNORM moving-average momentum (Keras default 0.99)         */
+    float rate;        /* DROPOUT rate (unet.py:34: 0.5)                             */
 } cg_layer_desc;
 
 typedef struct cg_var_info {
@@ -97,8 +101,17 @@ typedef struct cg_var_info {
     int64_t offset;    /* in floats, into the flat parameter buffer */
 } cg_var_info;
 
-typedef struct cg_adam_cfg {    /* Keras Adam, optimizers.py:14-15 (beta_2, epsilon = Keras defaults) */
+typedef enum cg_opt {           /* get_optimizer, optimizers.py:14-21 */
+    CG_OPT_ADAM = 0,            /* Adam(learning_rate, beta_1); beta_2 0.999, epsilon 1e-7 (Keras defaults)      */
+    CG_OPT_SGD = 1,             /* SGD(learning_rate): p -= lr*g (momentum 0)                                     */
+    CG_OPT_RMSPROP = 2,         /* RMSprop(learning_rate): rho = beta_2 (0.9), epsilon 1e-7, no momentum/centering */
+    CG_OPT_ADABELIEF = 3        /* adabelief_tf AdaBeliefOptimizer(learning_rate): betas .9/.999, eps 1e-14, rectified */
+} cg_opt;
+
+typedef struct cg_adam_cfg {    /* one optimizer of optimizers.py:5-24; the slots are the trainer's m / v buffers:
+                                   Adam, AdaBelief use both, RMSprop keeps its `rms` slot in v, SGD has none */
     float learning_rate, beta_1, beta_2, epsilon;
+    int32_t kind;               /* cg_opt */
 } cg_adam_cfg;
 
 typedef struct cg_train_cfg {   /* configs/cycle.yaml:36-41 + training_config.yaml:4-11 */
@@ -114,6 +127,8 @@ typedef struct cg_trainer_s* cg_trainer_t;
 int cg_init(int device);                 /* replaces train.py:36-43 (device selection); checks sm_100 */
 const char* cg_last_error(void);
 int cg_version(void);
+int cg_abi_sizeof(int which);            /* sizeof of 0 cg_layer_desc, 1 cg_var_info, 2 cg_train_cfg, 3 cg_adam_cfg: lets a
+                                            binding check its struct mirrors before the first real call */
 
 /* ---- model builder: replaces keras.Model(inputs, outputs) at unet.py:78,123 / resnet.py:85,105 */
 int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode, cg_net_t* out);
@@ -123,6 +138,16 @@ int cg_net_var_count(cg_net_t net, int* n_vars);                   /* len(model.
 int cg_net_var_info(cg_net_t net, int i, cg_var_info* out);
 int cg_net_out_shape(cg_net_t net, int N, int H, int W, int out_nhwc[4]);
 int cg_net_workspace_bytes(cg_net_t net, int N, int H, int W, int need_backward, size_t* bytes);
+/* Non-trainable state = the BatchNormalization moving statistics (Keras `non_trainable_variables` order: per BNORM
+ * layer [moving_mean[C], moving_variance[C]]); 0 floats for instance-norm nets.  The buffer is caller-owned. */
+int cg_net_state_floats(cg_net_t net, int64_t* n_floats);
+int cg_net_bind_state(cg_net_t net, float* state_dev);
+/* Keras `model(x, training=...)`: selects batch statistics + moving-average update (BNORM) and active DROPOUT for the
+ * following cg_net_forward calls on this handle; default 0 (inference), like Keras.  Ignored by instance norm. */
+int cg_net_set_training(cg_net_t net, int training);
+/* DROPOUT masks are a counter-based hash of (seed, call counter, layer, element): reproducible, and restated bit for
+ * bit by the oracle (TensorFlow's own random stream cannot be reproduced). */
+int cg_net_set_seed(cg_net_t net, uint64_t seed);
 
 /* model(x) -- Keras Model.__call__ (predict.py:32,35; model.py:93-106; unittests/test_*.py) */
 int cg_net_forward(cg_net_t net, const float* params_dev, const float* x_dev, float* y_dev,
@@ -156,6 +181,19 @@ int cg_trainer_get_iterations(cg_trainer_t tr, int64_t iters[4]);   /* optimizer
 int cg_trainer_set_iterations(cg_trainer_t tr, const int64_t iters[4]);
 /* pointer to an image the last step produced, for tests: 0 fake_b 1 same_b 2 fake_a 3 same_a 4 cycled_a 5 cycled_b */
 int cg_trainer_fetch_image(cg_trainer_t tr, int which, float* out_dev, void* stream);
+
+/* ---- input pipeline (transform/data_load.py:20-34, predict.py:20-27), all HBM-bound streaming kernels ---------- */
+/* normalize (data_load.py:31-34): dst = float32(src) / 127.5 - 1 */
+int cg_normalize_u8(const uint8_t* src_dev, float* dst_dev, size_t n, void* stream);
+/* postprocess_prediction (predict.py:26-27): dst = uint8((src + 1) * 127.5), truncating, clamped to [0, 255] */
+int cg_postprocess_u8(const float* src_dev, uint8_t* dst_dev, size_t n, void* stream);
+/* tf.image.resize(x, [Ho, Wo]) (data_load.py:23,41): bilinear, half-pixel centres, no antialiasing; float32 NHWC */
+int cg_resize_bilinear(const float* src_dev, int N, int H, int W, int C, float* dst_dev, int Ho, int Wo, void* stream);
+/* random_jitter (data_load.py:21-27) as ONE kernel: resize to [Hr, Wr] (bilinear, as above), crop [Ho, Wo] at
+ * (oy[n], ox[n]) and mirror horizontally where flip[n] != 0, without materialising the resized image.  The caller
+ * draws the random offsets / flips (tf.image.random_crop / random_flip_left_right cannot be reproduced bit for bit). */
+int cg_resize_crop_flip(const float* src_dev, int N, int H, int W, int C, int Hr, int Wr, float* dst_dev, int Ho, int Wo,
+                        const int32_t* oy_dev, const int32_t* ox_dev, const int32_t* flip_dev, void* stream);
 
 /* ---- data parallel (new functionality; the reference is single-device, train.py:36-43) */
 int cg_comm_unique_id(char id_out[128]);

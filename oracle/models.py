@@ -22,6 +22,11 @@ class OracleModel:
         self.variables: List[torch.Tensor] = []
         self.var_specs = []          # (shape, init kind) in creation order
         self._program = []           # list of callables built by the builder
+        # keras non_trainable_variables: [moving_mean, moving_variance] per BatchNormalization
+        self.state: List[torch.Tensor] = []
+        self.training = False        # the `training=` argument of the current call
+        self.n_dropout = 0           # dropout layers created so far (their ordinal keys the mask)
+        self.drop_seed, self.drop_counter, self.call_id = 0, 0, 0
 
     # -- variable creation ---------------------------------------------------
     def _var(self, shape, init):
@@ -43,7 +48,13 @@ class OracleModel:
 
     def __call__(self, x, training=False):
         x = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(self.dtype)
-        return self.forward(x)
+        self.training = bool(training)
+        try:
+            return self.forward(x)
+        finally:
+            if training:
+                self.drop_counter += 1          # standalone calls: one dropout counter tick per training call
+            self.training = False
 
 
 def init_variables(var_specs, seed):
@@ -90,25 +101,38 @@ def _inorm(m: OracleModel, c, affine):
     return lambda x: T.instance_norm(x)
 
 
-def _require_instancenorm(norm_type):
-    if str(norm_type).lower() != "instancenorm":
-        raise NotImplementedError("oracle restates normalization='instancenorm' only (batchnorm: SURVEY 8f rank 4)")
+def _bnorm(m: OracleModel, c, affine):
+    """keras BatchNormalization(): trainable [gamma, beta] when center/scale, state [moving_mean 0, moving_variance 1]."""
+    gi = m._var((c,), "ones") if affine else None
+    bi = m._var((c,), "zeros") if affine else None
+    si = len(m.state)
+    m.state += [torch.zeros(c, dtype=m.dtype), torch.ones(c, dtype=m.dtype)]
+    return lambda x: T.batch_norm(x, m.state[si:si + 2], None if gi is None else m.variables[gi],
+                                  None if bi is None else m.variables[bi], training=m.training)
+
+
+def _dropout(m: OracleModel, rate):
+    li = m.n_dropout
+    m.n_dropout += 1
+    return lambda x: T.dropout(x, rate, m.training, m.drop_seed, m.drop_counter, m.call_id, li)
 
 
 # ---------------------------------------------------------------------------
 # unet.py
 # ---------------------------------------------------------------------------
 def _double_conv(m, cin, f, k, norm_type, apply_dropout):
-    """unet.py:20-36."""
-    _require_instancenorm(norm_type)
-    if apply_dropout:
-        raise NotImplementedError("dropout=True needs TF's RNG stream: parity unpinned, not restated")
+    """unet.py:20-36 (a normalization string that is neither 'batchnorm' nor 'instancenorm' adds no norm layer)."""
     ops = []
     c = cin
     for _ in range(2):
         ops.append(_conv(m, c, f, k, 1, "same", use_bias=False))
-        ops.append(_inorm(m, f, affine=True))
+        if norm_type.lower() == 'batchnorm':
+            ops.append(_bnorm(m, f, affine=True))
+        elif norm_type.lower() == 'instancenorm':
+            ops.append(_inorm(m, f, affine=True))
         ops.append(torch.relu)
+        if apply_dropout:
+            ops.append(_dropout(m, 0.5))
         c = f
 
     def run(x):
@@ -125,13 +149,13 @@ def strided_unet(config: Dict, dtype=torch.float32) -> OracleModel:
     norm_type = config['normalization']
     output_channels = config['output_channels']
     final_activation = config['final_activation']
-    _require_instancenorm(norm_type)
+    norm = (lambda c: _inorm(m, c, True)) if norm_type == 'instancenorm' else (lambda c: _bnorm(m, c, True))   # unet.py:55-58
 
     m = OracleModel(dtype)
     up_filters = filters[::-1][:-1]
     down, c = [], 3
     for f, k in list(zip(filters, kernel_sizes))[:-1]:
-        down.append((_conv(m, c, f, k, 2, "same"), _inorm(m, f, True)))
+        down.append((_conv(m, c, f, k, 2, "same"), norm(f)))
         c = f
     skip_ch = [f for f in filters[:-1]][::-1]
     bottom = _conv(m, c, filters[-1], kernel_sizes[-1], 2, "same")
@@ -139,7 +163,7 @@ def strided_unet(config: Dict, dtype=torch.float32) -> OracleModel:
     ups = []
     for f, sc, k in zip(up_filters, skip_ch, kernel_sizes[:0:-1]):
         ct = _convT(m, c, f, k, 2)
-        nrm = _inorm(m, sc + f, True)
+        nrm = norm(sc + f)
         ups.append((ct, nrm))
         c = sc + f
     last = _convT(m, c, output_channels, 4, 2)
@@ -237,17 +261,18 @@ def simple_discriminator(config: Dict, dtype=torch.float32) -> OracleModel:
     down_filters = config['filters']
     kernel_size = config['kernels']
     norm_type = config['normalization']
-    _require_instancenorm(norm_type)
     m = OracleModel(dtype)
     convs, c = [], 3
     for k, f in zip(kernel_size, down_filters):
-        convs.append(_conv(m, c, f, k, 2, "same"))
+        cv = _conv(m, c, f, k, 2, "same")
+        nrm = _inorm(m, f, False) if norm_type == 'instancenorm' else _bnorm(m, f, False)      # resnet.py:97-100
+        convs.append((cv, nrm))
         c = f
     head = _conv(m, c, 1, 1, 1, "same")
 
     def forward(x):
-        for cv in convs:
-            x = T.leaky_relu(T.instance_norm(cv(x)), 0.2)
+        for cv, nrm in convs:
+            x = T.leaky_relu(nrm(cv(x)), 0.2)
         return head(x)
     m.forward = forward
     return m

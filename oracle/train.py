@@ -31,10 +31,11 @@ class OracleCycleGan:
         self.loss_weights = loss_weights or dict(cycle=2.0, identity=0.5, generator=1.0, discriminator=0.5)
         g_opt = g_opt or dict(name="adam", learning_rate=2e-4, beta_1=0.5)
         d_opt = d_opt or dict(name="adam", learning_rate=2e-4, beta_1=0.5)
-        # model.py:68-71 (optimizers.py:14-15: Adam only)
-        mk = lambda c: T.KerasAdam(c["learning_rate"], c["beta_1"])
+        # model.py:68-71 (optimizers.py:5-24)
+        mk = T.get_optimizer
         self.g_AB_optimizer, self.g_BA_optimizer = mk(g_opt), mk(g_opt)
         self.d_A_optimizer, self.d_B_optimizer = mk(d_opt), mk(d_opt)
+        self.train_calls = 0         # training-mode steps so far = the dropout counter of the next one
 
     def nets(self):
         return dict(g_AB=self.g_AB, g_BA=self.g_BA, d_A=self.d_A, d_B=self.d_B)
@@ -42,20 +43,34 @@ class OracleCycleGan:
     def _to(self, x):
         return torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(self.dtype)
 
-    def forward_all(self, real_a, real_b):
-        """model.py:93-106."""
+    def forward_all(self, real_a, real_b, training=False):
+        """model.py:93-106.  Each model call is one Keras call: its own batch statistics / moving-average update
+        (BatchNormalization) and its own dropout mask, keyed by the order of the calls on that model."""
         real_a, real_b = self._to(real_a), self._to(real_b)
+        calls = {}
+
+        def run(net, x):
+            net.training = training
+            net.call_id = calls.get(id(net), 0)
+            net.drop_counter = self.train_calls
+            calls[id(net)] = net.call_id + 1
+            try:
+                return net.forward(x)
+            finally:
+                net.training = False
         o = {}
-        o["fake_b"] = self.g_AB.forward(real_a)
-        o["cycled_a"] = self.g_BA.forward(o["fake_b"])
-        o["fake_a"] = self.g_BA.forward(real_b)
-        o["cycled_b"] = self.g_AB.forward(o["fake_a"])
-        o["same_a"] = self.g_BA.forward(real_a)
-        o["same_b"] = self.g_AB.forward(real_b)
-        o["disc_real_a"] = self.d_A.forward(real_a)
-        o["disc_real_b"] = self.d_B.forward(real_b)
-        o["disc_fake_a"] = self.d_A.forward(o["fake_a"])
-        o["disc_fake_b"] = self.d_B.forward(o["fake_b"])
+        o["fake_b"] = run(self.g_AB, real_a)
+        o["cycled_a"] = run(self.g_BA, o["fake_b"])
+        o["fake_a"] = run(self.g_BA, real_b)
+        o["cycled_b"] = run(self.g_AB, o["fake_a"])
+        o["same_a"] = run(self.g_BA, real_a)
+        o["same_b"] = run(self.g_AB, real_b)
+        o["disc_real_a"] = run(self.d_A, real_a)
+        o["disc_real_b"] = run(self.d_B, real_b)
+        o["disc_fake_a"] = run(self.d_A, o["fake_a"])
+        o["disc_fake_b"] = run(self.d_B, o["fake_b"])
+        if training:
+            self.train_calls += 1
         return real_a, real_b, o
 
     def _metrics(self, real_a, real_b, o):
@@ -75,12 +90,12 @@ class OracleCycleGan:
 
     def validate_step(self, real_a, real_b, training=False):
         with torch.no_grad():
-            ra, rb, o = self.forward_all(real_a, real_b)
+            ra, rb, o = self.forward_all(real_a, real_b, training)
             return {k: float(v) for k, v in self._metrics(ra, rb, o).items()}
 
     def gradients(self, real_a, real_b):
         """model.py:138-147: returns (metrics, grads dict) without applying them."""
-        ra, rb, o = self.forward_all(real_a, real_b)
+        ra, rb, o = self.forward_all(real_a, real_b, training=True)
         metrics = self._metrics(ra, rb, o)
         grads = {}
         for loss_name, net_name in (("gAB_loss", "g_AB"), ("gBA_loss", "g_BA"),

@@ -24,6 +24,14 @@ SMALL_UNET_D = dict(type="unet_generator", filters=[8, 8], kernels=[7, 3], outpu
                     expansion="upsample", normalization="instancenorm", dropout=False, final_activation="sigmoid")
 SMALL_SIMPLE = dict(type="simple_discriminator", filters=[8, 16], kernels=[4, 4], normalization="instancenorm")
 
+# optional config paths: BatchNormalization / Dropout variants of the small nets
+BN_STRIDED = dict(SMALL_STRIDED, normalization="batchnorm")
+BN_UNET = dict(SMALL_UNET, normalization="batchnorm")
+BN_SIMPLE = dict(SMALL_SIMPLE, normalization="batchnorm")
+DROP_UNET = dict(SMALL_UNET, dropout=True)
+BN_DROP_UNET = dict(SMALL_UNET, normalization="batchnorm", dropout=True)
+NONORM_UNET = dict(SMALL_UNET, normalization="none")        # unet.py:27-30: neither branch -> no norm layer
+
 LOSS_WEIGHTS = dict(cycle=2.0, identity=0.5, generator=1.0, discriminator=0.5)   # cycle.yaml:36-41
 ADAM = dict(name="adam", learning_rate=2e-4, beta_1=0.5)                         # training_config.yaml:4-11
 
@@ -40,7 +48,7 @@ def model_config(gen, disc, loss="mse"):
                  discriminator=dict(disc), loss=loss, loss_weights=dict(LOSS_WEIGHTS))
 
 
-def train_config(batch_size=1):
+def train_config(batch_size=1, g_opt=None, d_opt=None):
     from cyclegan_cat_b200.model_processing.load_model import Bunch
-    return Bunch(epochs=1, batch_size=batch_size, image_size=128, g_opt=dict(ADAM), d_opt=dict(ADAM),
+    return Bunch(epochs=1, batch_size=batch_size, image_size=128, g_opt=dict(g_opt or ADAM), d_opt=dict(d_opt or ADAM),
                  summary=dict(samples=1, images=5, model=20))

@@ -55,14 +55,37 @@ def test_create_model_dispatch_and_unknown_type():
         simple_discriminator(dict(filters=[8], kernels=[4]))
 
 
-@pytest.mark.parametrize("cfg", [C.UNET_G, C.UNET_D, C.SIMPLE_D4, C.RESNET64, C.FIX_UNET, C.SMALL_STRIDED])
+@pytest.mark.parametrize("cfg", [C.UNET_G, C.UNET_D, C.SIMPLE_D4, C.RESNET64, C.FIX_UNET, C.SMALL_STRIDED,
+                                 C.BN_STRIDED, C.BN_UNET, C.BN_SIMPLE, C.BN_DROP_UNET, C.NONORM_UNET])
 def test_variable_lists_match_oracle(cfg):
-    """Keras trainable_variables order/shape/initializer agree between the IR builders and the oracle."""
+    """Keras trainable_variables order/shape/initializer agree between the IR builders and the oracle; so do the
+    non-trainable ones (BatchNormalization moving statistics)."""
     m = create_model(cfg)
     o = om.create_model(cfg)
     assert m.graph.var_specs() == o.var_specs
     assert [v.shape for v in m.trainable_variables] == [tuple(v.shape) for v in o.variables]
     assert m.n_params == sum(v.numel() for v in o.variables)
+    assert [v.shape for v in m.non_trainable_variables] == [tuple(s.shape) for s in o.state]
+    assert [v.numpy().tolist() for v in m.non_trainable_variables] == [s.tolist() for s in o.state]     # zeros / ones
+    assert m.graph.has_dropout() == (o.n_dropout > 0)
+    assert len(m.get_weights()) == len(o.variables) + len(o.state)
+
+
+def test_optional_paths_plan_natively(built_lib):
+    """BatchNormalization / Dropout graphs pass the native planner (pure host code) and report their state size."""
+    for cfg, n_bn in ((C.BN_STRIDED, 4), (C.BN_SIMPLE, 2), (C.BN_DROP_UNET, 10), (C.DROP_UNET, 0)):
+        m = create_model(cfg)
+        n = ctypes.c_int64()
+        assert built_lib.cg_net_state_floats(m.handle(), ctypes.byref(n)) == 0
+        assert n.value == m.n_state == sum(v.size for v in m.non_trainable_variables)
+        assert len(m.non_trainable_variables) == 2 * n_bn
+        nbytes = ctypes.c_size_t()
+        assert built_lib.cg_net_workspace_bytes(m.handle(), 2, 32, 32, 1, ctypes.byref(nbytes)) == 0 and nbytes.value > 0
+    h = ctypes.c_void_p()
+    bad = (ir.LayerDesc * 1)(ir.LayerDesc(ir.OP_DROPOUT, 0, -1, 3, 3, 0, 1, 0, 0, 0, 0, 0, 1e-3, 0.2, 0.99, 1.0))   # rate 1
+    assert built_lib.cg_net_create(bad, 1, 0, ctypes.byref(h)) == -1 and b"rate" in built_lib.cg_last_error()
+    bad = (ir.LayerDesc * 1)(ir.LayerDesc(ir.OP_BNORM, 0, -1, 3, 3, 0, 1, 0, 0, 0, 1, 0, 1e-3, 0.2, 1.5, 0.0))    # momentum
+    assert built_lib.cg_net_create(bad, 1, 0, ctypes.byref(h)) == -1 and b"momentum" in built_lib.cg_last_error()
 
 
 def test_flops_match_survey_tables():
@@ -77,6 +100,12 @@ def test_optimizer_and_loss_factories():
     """optimizers.py:5-24, losses.py:67-81."""
     o = get_optimizer(dict(name="adam", learning_rate=2e-4, beta_1=0.5))
     assert (o.learning_rate, o.beta_1, o.beta_2, o.epsilon) == (2e-4, 0.5, 0.999, 1e-7)
+    r = get_optimizer(dict(name="rmsprop", learning_rate=1e-3))
+    assert (r.kind, r.rho, r.beta_2, r.epsilon, r.slots) == (ir.OPT_RMSPROP, 0.9, 0.9, 1e-7, ("rms",))
+    s = get_optimizer(dict(name="sgd", learning_rate=1e-2))
+    assert (s.kind, s.learning_rate, s.slots) == (ir.OPT_SGD, 1e-2, ())
+    a = get_optimizer(dict(name="adabelief", learning_rate=1e-3))
+    assert (a.kind, a.beta_1, a.beta_2, a.epsilon, a.slots) == (ir.OPT_ADABELIEF, 0.9, 0.999, 1e-14, ("m", "v"))
     with pytest.raises(ValueError):
         get_optimizer(dict(name="nadam", learning_rate=1e-3))
     with pytest.raises(KeyError):
@@ -104,9 +133,12 @@ def test_library_exports_every_declared_symbol(built_lib):
 
 
 def test_struct_layouts_match_header(built_lib):
-    assert ctypes.sizeof(ir.LayerDesc) == 14 * 4
+    assert ctypes.sizeof(ir.LayerDesc) == 16 * 4
     assert ctypes.sizeof(ir.VarInfo) == 40
-    assert ctypes.sizeof(ir.TrainCfg) == 5 * 4 + 4 * 16
+    assert ctypes.sizeof(ir.TrainCfg) == 5 * 4 + 4 * 20
+    lib = _lib.load()
+    for which, mirror in enumerate((ir.LayerDesc, ir.VarInfo, ir.TrainCfg, ir.AdamCfg)):
+        assert lib.cg_abi_sizeof(which) == ctypes.sizeof(mirror), mirror
 
 
 def test_native_planner_agrees_with_host(built_lib):

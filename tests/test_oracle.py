@@ -1,5 +1,6 @@
 """CPU tests of the oracle itself: the reference's only known-answer vector, the reference's shape
 tests, self-consistency of the TF semantics restated in oracle/tf_ops.py, and the frozen fixtures."""
+import math
 import os
 
 import numpy as np
@@ -127,3 +128,127 @@ def test_frozen_fixture_train_step():
         for k, v in m.items():
             assert abs(v - float(z[f"step{step}_{k}"])) <= 2e-5 * max(1.0, abs(v)), (step, k)
     assert C.rel_l2(o.g_AB.variables[0].detach().numpy(), z["g_AB_var0"]) < 1e-5
+
+
+# ---- optional config paths and input pipeline (rank 3): oracle pinned against independent forms ----
+def test_batch_norm_against_torch_batch_norm():
+    """Appendix A.4: training output uses the biased batch variance, the moving variance the Bessel-corrected one
+    (torch's F.batch_norm has the same convention, momentum_torch = 1 - momentum_keras)."""
+    from oracle import tf_ops as T
+    rng = np.random.RandomState(0)
+    x = torch.from_numpy(rng.normal(0.3, 2.0, (3, 5, 4, 6))).double()
+    g, b = torch.from_numpy(rng.normal(1, .1, 6)), torch.from_numpy(rng.normal(0, .1, 6))
+    state = [torch.zeros(6).double(), torch.ones(6).double()]
+    rm, rv = torch.zeros(6).double(), torch.ones(6).double()
+    y = T.batch_norm(x, state, g, b, training=True)
+    ref = torch.nn.functional.batch_norm(x.permute(0, 3, 1, 2), rm, rv, g, b, True, 0.01, 1e-3).permute(0, 2, 3, 1)
+    assert torch.allclose(y, ref, atol=1e-12)
+    assert torch.allclose(state[0], rm, atol=1e-12) and torch.allclose(state[1], rv, atol=1e-12)
+    y2 = T.batch_norm(x, state, g, b, training=False)
+    ref2 = torch.nn.functional.batch_norm(x.permute(0, 3, 1, 2), rm, rv, g, b, False, 0.01, 1e-3).permute(0, 2, 3, 1)
+    assert torch.allclose(y2, ref2, atol=1e-12)
+
+
+def test_dropout_mask_hash_against_python_ints():
+    """The numpy (wrapping uint64) restatement of the kernel's splitmix64 mask against arbitrary-precision ints."""
+    from oracle import tf_ops as T
+    M = (1 << 64) - 1
+
+    def sm(z):
+        z = (z + 0x9E3779B97F4A7C15) & M
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+        return z ^ (z >> 31)
+    seed, ctr, call, layer, rate = 0xDEADBEEFCAFE, 7, 2, 3, 0.5
+    key = sm(seed ^ ((ctr * 0xD1342543DE82EF95) & M))
+    key = sm(key ^ ((call << 32) | layer))
+    want = [1.0 if (sm((key + e * 0x9E3779B97F4A7C15) & M) >> 40) / 16777216.0 >= rate else 0.0 for e in range(257)]
+    got = T.dropout_mask(seed, ctr, call, layer, 257, rate)
+    assert got.tolist() == want
+    big = T.dropout_mask(1, 0, 0, 0, 1 << 16, 0.5)
+    assert abs(big.mean() - 0.5) < 0.01
+    assert not np.array_equal(big, T.dropout_mask(1, 1, 0, 0, 1 << 16, 0.5))      # another step, another mask
+    assert not np.array_equal(big, T.dropout_mask(1, 0, 1, 0, 1 << 16, 0.5))      # another call
+    assert not np.array_equal(big, T.dropout_mask(1, 0, 0, 1, 1 << 16, 0.5))      # another layer
+
+
+def test_keras_sgd_rmsprop_and_adabelief_formulas():
+    """Appendix A.9 + adabelief_tf's published rule, against a scalar float64 re-derivation."""
+    from oracle import tf_ops as T
+    g_seq = [0.5, -0.25, 0.125, 0.3, -0.7, 0.2, 0.2]
+    # SGD
+    p = torch.tensor([1.0], dtype=torch.float64)
+    o = T.KerasSGD(0.1)
+    for g in g_seq[:2]:
+        o.apply_gradients([torch.tensor([g], dtype=torch.float64)], [p])
+    assert abs(float(p) - (1.0 - 0.1 * 0.5 + 0.1 * 0.25)) < 1e-15 and o.get_weights() == [2]
+    # RMSprop
+    p = torch.tensor([1.0], dtype=torch.float64)
+    o = T.KerasRMSprop(0.01)
+    ref, rms = 1.0, 0.0
+    for g in g_seq:
+        o.apply_gradients([torch.tensor([g], dtype=torch.float64)], [p])
+        rms = 0.9 * rms + 0.1 * g * g
+        ref -= 0.01 * g / (math.sqrt(rms) + 1e-7)
+    assert abs(float(p) - ref) < 1e-14 and len(o.get_weights()) == 2
+    # AdaBelief: steps 1..5 are unrectified (sma_t < 5), later ones rectified
+    p = torch.tensor([1.0], dtype=torch.float64)
+    o = T.AdaBelief(0.01)
+    ref, m, v = 1.0, 0.0, 0.0
+    b1, b2, eps = 0.9, 0.999, 1e-14
+    rectified = []
+    for t, g in enumerate(g_seq, 1):
+        o.apply_gradients([torch.tensor([g], dtype=torch.float64)], [p])
+        m = b1 * m + (1 - b1) * g
+        v = b2 * v + (1 - b2) * (g - m) ** 2 + eps
+        sma_inf = 2 / (1 - b2) - 1
+        sma = sma_inf - 2 * t * b2 ** t / (1 - b2 ** t)
+        mc = m / (1 - b1 ** t)
+        if sma >= 5:
+            r = math.sqrt((sma - 4) / (sma_inf - 4) * (sma - 2) / (sma_inf - 2) * sma_inf / sma)
+            ref -= 0.01 * r * mc / (math.sqrt(v / (1 - b2 ** t)) + eps)
+        else:
+            ref -= 0.01 * mc
+        rectified.append(sma >= 5)
+        assert abs(float(p) - ref) < 1e-13, t
+    assert rectified[0] is False and rectified[-1] is True
+    assert len(o.get_weights()) == 3
+
+
+def test_resize_bilinear_against_torch_interpolate():
+    """tf.image.resize bilinear / half-pixel centres == torch's align_corners=False bilinear (no antialias), up and down."""
+    from oracle import tf_ops as T
+    rng = np.random.RandomState(3)
+    x = rng.uniform(0, 255, (2, 13, 17, 3)).astype(np.float32)
+    for oh, ow in ((26, 34), (7, 9), (50, 20), (13, 17)):
+        ref = torch.nn.functional.interpolate(torch.from_numpy(x).permute(0, 3, 1, 2), size=(oh, ow), mode="bilinear",
+                                              align_corners=False).permute(0, 2, 3, 1).numpy()
+        assert np.abs(T.resize_bilinear(x, oh, ow) - ref).max() <= 1e-3, (oh, ow)
+    oy, ox, fl = np.array([3, 0]), np.array([10, 50]), np.array([1, 0])
+    j = T.random_jitter(x, 16, oy, ox, fl)
+    big = T.resize_bilinear(x, 66, 66)
+    assert j.shape == (2, 16, 16, 3)
+    assert np.array_equal(j[0], big[0, 3:19, 10:26][:, ::-1]) and np.array_equal(j[1], big[1, 0:16, 50:66])
+
+
+def test_normalize_and_postprocess_known_answers():
+    """data_load.py:31-34, predict.py:26-27."""
+    from oracle import tf_ops as T
+    assert T.normalize(np.array([0, 255, 51], np.uint8)).tolist() == [-1.0, 1.0, np.float32(51) / np.float32(127.5) - 1]
+    assert T.postprocess_prediction(np.array([-1.0, 1.0, 0.0, 0.999], np.float32)).tolist() == [0, 255, 127, 254]
+
+
+def test_batchnorm_and_dropout_builders_train_step_runs():
+    """The optional config paths build and step in the oracle: BN moving statistics move once per Keras call."""
+    from oracle.train import OracleCycleGan, synthetic_batch
+    gen = dict(C.SMALL_UNET, normalization="batchnorm", dropout=True)
+    disc = dict(C.SMALL_SIMPLE, normalization="batchnorm")
+    o = OracleCycleGan(gen, disc, g_opt=dict(name="rmsprop", learning_rate=1e-4), d_opt=dict(name="sgd", learning_rate=1e-3))
+    a, b = synthetic_batch(2, 16)
+    before = [s.clone() for s in o.g_AB.state]
+    m0 = o.validate_step(a, b)                      # inference: moving statistics, no dropout, state untouched
+    assert all(torch.equal(x, y) for x, y in zip(before, o.g_AB.state))
+    m1 = o.train_step(a, b)
+    assert not torch.equal(before[0], o.g_AB.state[0])
+    assert all(np.isfinite(v) for v in m1.values()) and m0["gAB_loss"] != m1["gAB_loss"]
+    assert len(o.d_A.state) == 2 * 2 and len(o.d_A.variables) == 2 * 2 + 2      # BN(center=False, scale=False): no gamma/beta
