@@ -295,11 +295,12 @@ extern "C" int cg_postprocess_u8(const float* src, uint8_t* dst, size_t n, void*
 // tf.image.resize bilinear with half-pixel centres (TF2 default, antialias=False):
 //   in = (o + 0.5) * scale - 0.5 ; lo = max(floor(in), 0) ; hi = min(ceil(in), size - 1) ; lerp = in - floor(in)
 __device__ __forceinline__ void resize_coord(int o, float scale, int size, int& lo, int& hi, float& lerp) {
-    const float in = ((float)o + 0.5f) * scale - 0.5f;
+    // explicit roundings (no fma contraction): the source coordinate decides which pixels are blended
+    const float in = __fsub_rn(__fmul_rn(__fadd_rn((float)o, 0.5f), scale), 0.5f);
     const float f = floorf(in);
     lo = max((int)f, 0);
     hi = min((int)ceilf(in), size - 1);
-    lerp = in - f;
+    lerp = __fsub_rn(in, f);
 }
 // one thread per output pixel; the C (= 3) channels of the four source pixels are contiguous.  Output pixel (y, x) of
 // image n samples the virtual [Hr, Wr] resized image at (oy[n] + y, ox[n] + x') with x' mirrored when flip[n].
@@ -325,9 +326,10 @@ __global__ void __launch_bounds__(XT) resize_kernel(const float* __restrict__ sr
         const float* p11 = src + (((size_t)n * H + y1) * W + x1) * C;
         float* o = dst + i * C;
         for (int c = 0; c < C; ++c) {
-            const float top = p00[c] + (p01[c] - p00[c]) * lx;
-            const float bot = p10[c] + (p11[c] - p10[c]) * lx;
-            o[c] = top + (bot - top) * ly;
+            // TF's compute_lerp order, every operation rounded on its own (bit-identical to a float32 numpy restatement)
+            const float top = __fadd_rn(p00[c], __fmul_rn(__fsub_rn(p01[c], p00[c]), lx));
+            const float bot = __fadd_rn(p10[c], __fmul_rn(__fsub_rn(p11[c], p10[c]), lx));
+            o[c] = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
         }
     }
 }

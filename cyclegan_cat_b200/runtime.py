@@ -157,13 +157,13 @@ class Model:
         self._push()
 
     def _push(self):
-        if self._dev is not None:
+        if self._dev is not None and self.n_params:
             torch = _torch()
             self._dev.copy_(torch.from_numpy(self._host))
 
     def _flat_host(self):
         if self._dev is not None:
-            self._host = self._dev.detach().cpu().numpy()
+            self._host = self._dev.detach().cpu().numpy()[:self.n_params]
         return self._host
 
     def _state_flat_host(self):
@@ -236,8 +236,8 @@ class Model:
 
     def device_params(self):
         torch = _require_cuda()
-        if self._dev is None:
-            self._dev = torch.from_numpy(self._host).cuda()
+        if self._dev is None:      # a graph without variables still hands the C-ABI a valid (unused) pointer
+            self._dev = torch.from_numpy(self._host).cuda() if self.n_params else torch.zeros(4, device="cuda")
         self.device_state()
         return self._dev
 

@@ -90,9 +90,11 @@ def test_cuda_graph_replay_matches_eager_steps(mode):
             finally:
                 os.environ.pop("CG_DISABLE_GRAPH", None)
         for k, (m1, m2) in enumerate(zip(runs[0][0] + [runs[0][1]], runs[1][0] + [runs[1][1]])):
-            # the first replay (k = 2) must agree tightly; later steps drift apart through Adam (the first updates are
-            # ~ lr * sign(g), and the summation order of the atomics differs from run to run)
-            tol = (2e-4 if k <= 2 else 2e-3) if mode == "fp32" else 2e-2
+            # steps 0-1 (eager / capture) must agree tightly; from the first replay (k = 2) on, the runs drift apart through
+            # Adam (the first updates are ~ lr * sign(g), and the summation order of the atomics differs from run to run):
+            # two EAGER runs of this scenario differ by 1.2e-5, 2.7e-4, 4.3e-4, 4.2e-4 at k = 1..4, graph vs eager by
+            # 9.2e-6, 3.2e-4, 3.7e-4, 1.4e-4 (tools/graph_vs_eager.py) -- the same spread
+            tol = (2e-4 if k <= 1 else 2e-3) if mode == "fp32" else 2e-2
             for key in m1:
                 assert abs(m1[key] - m2[key]) <= tol * max(1.0, abs(m2[key])), (k, key, m1[key], m2[key])
         for w1, w2 in zip(runs[0][2], runs[1][2]):
