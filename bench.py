@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the CycleGAN train step (BASELINE.json metric: train images/sec at 256x256).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C3|C2|C2s|C1] [--mode bf16|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C3|C2|C2s|C1|C5] [--mode bf16|fp32]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...       # the CPU restatement of the reference (torch-CPU oracle), host cores
 
@@ -38,6 +38,8 @@ WORKLOADS = {
     "C2": dict(gen=UNET_G, disc=UNET_D, size=256, batch=4, name="C2: cycle.yaml verbatim (U-Net G + U-Net PatchGAN D), 256x256"),
     "C2s": dict(gen=STRIDED7, disc=UNET_D, size=256, batch=4, name="C2s: strided_unet-7 G + U-Net PatchGAN D, 256x256"),
     "C3": dict(gen=RESNET64, disc=SIMPLE_D4, size=256, batch=16, name="C3: resnet_generator{filters:64} (9 blocks) + simple_discriminator[64,128,256,512] k4, 256x256"),
+    # BASELINE.json configs[4]: generator inference (predict.py path), replicas only -- no discriminator, no backward
+    "C5": dict(gen=UNET_G, disc=None, size=512, batch=32, name="C5: unet_generator(cycle.yaml) forward only (predict.py path), 512x512"),
 }
 LOSS_WEIGHTS = dict(cycle=2.0, identity=0.5, generator=1.0, discriminator=0.5)
 ADAM = dict(name="adam", learning_rate=2e-4, beta_1=0.5)
@@ -149,6 +151,161 @@ def run_reference(args, wl):
                 cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"]),
                 e2e=dict(value=r["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# C5: the predict.py path (predict.py:20-36) -- uint8 image -> normalize -> generator -> uint8, replicas only
+# ---------------------------------------------------------------------------------------------
+INFER_METRIC = "cyclegan_predict_images_per_sec_512x512"
+
+
+def time_oracle_forward(wl, steps, budget_s=60.0):
+    import torch
+    from oracle import models as om, tf_ops as T
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    o = om.create_model(wl["gen"])
+    o.load(om.init_variables(o.var_specs, 42))
+    u8 = np.random.RandomState(1234).randint(0, 256, size=(1, wl["size"], wl["size"], 3)).astype(np.uint8)
+
+    def once():
+        with torch.no_grad():
+            return T.postprocess_prediction(o(T.normalize(u8)).numpy())
+    once()
+    times, t0 = [], time.perf_counter()
+    for _ in range(steps):
+        t1 = time.perf_counter()
+        once()
+        times.append(time.perf_counter() - t1)
+        if time.perf_counter() - t0 > budget_s:
+            break
+    med = float(np.median(times))
+    return dict(value=1.0 / med, ms_per_step=med * 1e3, cores=cores, steps_done=len(times),
+                sample=f"{wl['name']}, batch 1, {len(times)} timed calls (median): normalize -> generator -> uint8, fp32 "
+                       f"torch-CPU restatement of the reference (oneDNN), not TensorFlow")
+
+
+def run_infer_reference(args, wl):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    r = time_oracle_forward(wl, max(args.steps, 3))
+    print(json.dumps(dict(metric=INFER_METRIC, value=r["value"], unit=UNIT, n_gpus=args.gpus, steps=r["steps_done"],
+                          warmup=1, ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None,
+                          dtype="f32", data="synthetic", impl="reference",
+                          config=dict(workload=wl["name"], image_size=wl["size"], batch_per_step=1),
+                          cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"]),
+                          e2e=dict(value=r["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))), flush=True)
+
+
+def run_infer(args, wl):
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from cyclegan_cat_b200 import _lib
+    from cyclegan_cat_b200.cyclegan.model import create_model
+    from cyclegan_cat_b200.transform import data_load as DL
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B, S = args.batch or wl["batch"], wl["size"]
+    g = create_model(wl["gen"], mode=args.mode)
+    g.initialize(42)
+    lib = _lib.load()
+    u8 = np.random.RandomState(1234 + rank).randint(0, 256, size=(B, S, S, 3)).astype(np.uint8)
+    u8_pin = torch.from_numpy(u8).pin_memory()
+    x_dev = DL.normalize_device(u8).torch
+    out_pin = torch.empty((B, S, S, 3), dtype=torch.uint8).pin_memory()
+    out_dev = torch.empty((B, S, S, 3), dtype=torch.uint8, device="cuda")
+    from cyclegan_cat_b200.runtime import _ptr, _stream_ptr
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def e2e_once():      # predict.py:20-36 for a batch: host uint8 in, host uint8 out
+        xd = u8_pin.cuda(non_blocking=True)
+        y = g(DL.normalize_device(xd))
+        _lib.check(lib.cg_postprocess_u8(_ptr(y.torch), _ptr(out_dev), out_dev.numel(), _stream_ptr(torch)), "post")
+        out_pin.copy_(out_dev, non_blocking=True)
+
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        g(x_dev)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib.cg_launch_count(None, 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        g(x_dev)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    launches = ctypes.c_int64()
+    lib.cg_launch_count(ctypes.byref(launches), 0)
+    # tensor-core share: one extra, instrumented call (CUDA-event pairs around every tensor-core launch)
+    lib.cg_prof_enable(1)
+    g(x_dev)
+    pms, pl, pfl = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
+    lib.cg_prof_read(ctypes.byref(pms), ctypes.byref(pl), ctypes.byref(pfl))
+    lib.cg_prof_enable(0)
+    for _ in range(2):
+        e2e_once()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        e2e_once()
+    e3.record()
+    barrier()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    ms_step = ms_total / args.steps
+    fl_img = g.graph.flops(S, S)
+    tfl = fl_img * B / (ms_step * 1e-3) / 1e12
+    tc_tfl = (pfl.value / (pms.value * 1e-3) / 1e12) if pms.value > 0 else None
+    line = dict(metric=INFER_METRIC, value=world * B * args.steps / (ms_total * 1e-3), unit=UNIT, n_gpus=world,
+                steps=args.steps, warmup=W, ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype=args.mode, data="synthetic",
+                config=dict(workload=wl["name"], image_size=S, batch_per_gpu=B, parallelism=f"replicas x{world} (no collective)",
+                            flops_per_image=fl_img, l2="no flush needed: one call streams > 10 GB of activations (>> 126 MB L2)",
+                            weights="random init N(0,0.02), seed 42"),
+                roofline=dict(bound="tensor", kernel="conv_tc_kernel<BK16> (16-channel-group tcgen05 conv; bound by the TMA row "
+                              "rate of its 32-byte rows, DESIGN.md 3.1), all tensor-core launches of one call",
+                              achieved=tc_tfl, peak=pk["tflops"], unit="TFLOP/s", frac=(tc_tfl / pk["tflops"]) if tc_tfl else None,
+                              traffic=None, launches=int(pl.value), share_of_step=(pms.value / ms_step) if ms_step > 0 else None,
+                              peak_source=pk["source"], whole_call_tflops=tfl, whole_call_frac=tfl / pk["tflops"]),
+                clocks=clocks, gpu_launches=int(launches.value),
+                e2e=dict(value=world * B * args.steps / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=int(u8.nbytes),
+                         d2h_bytes_per_step=int(u8.nbytes), ms_per_step=ms_e2e / args.steps,
+                         path="pinned uint8 -> H2D -> cg_normalize_u8 -> cg_net_forward -> cg_postprocess_u8 -> D2H (predict.py:20-36)"))
+    if not args.no_cpu_baseline:
+        r = time_oracle_forward(wl, 5, budget_s=40.0)
+        line["cpu_baseline"] = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"],
+                                    ms_per_step=r["ms_per_step"])
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -341,7 +498,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-input loop (profiling runs)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
-    if args.impl == "reference":
+    if wl["disc"] is None:
+        (run_infer_reference if args.impl == "reference" else run_infer)(args, wl)
+    elif args.impl == "reference":
         run_reference(args, wl)
     else:
         run_gpu(args, wl)

@@ -176,46 +176,64 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
 __device__ __forceinline__ unsigned long long dropout_key(const DropKey& k, int g) {
     const unsigned long long ctr = k.ctr_dev ? *k.ctr_dev : k.ctr_host;
     unsigned long long z = splitmix64(k.seed ^ (ctr * 0xD1342543DE82EF95ull));
-    z = splitmix64(z ^ ((unsigned long long)(unsigned)k.call_id[g] << 32 | (unsigned)k.layer));
+    const int call = g == 0 ? k.call_id[0] : g == 1 ? k.call_id[1] : g == 2 ? k.call_id[2] : k.call_id[3];   // no local-memory indexing
+    z = splitmix64(z ^ ((unsigned long long)(unsigned)call << 32 | (unsigned)k.layer));
     return z;
 }
 
-// MODE 0: forward (b unused).  MODE 1: backward, o (+)= a * mask / (1 - rate)
-template <typename T, int MODE>
+// MODE 0: forward.  MODE 1: backward, o (+)= a * mask / (1 - rate).  VEC elements (one 16-byte access for bf16 x8 /
+// float x4) per thread and iteration; VEC == 1 is the fallback for group sizes that are not a multiple of the vector.
+template <typename T, int MODE, int VEC>
 __global__ void __launch_bounds__(XT) dropout_kernel(const T* __restrict__ a, T* __restrict__ o, size_t group_elems, int groups,
                                                      float rate, float scale, DropKey key, int training, int accumulate) {
-    const size_t total = group_elems * (size_t)groups;
+    const size_t total_v = group_elems * (size_t)groups / VEC;
     int cur_g = -1;
     unsigned long long cur_key = 0;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        float v = ldf(a + i);
+    for (size_t iv = blockIdx.x * (size_t)blockDim.x + threadIdx.x; iv < total_v; iv += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = iv * VEC;
+        float v[VEC];
+        load_vec<T, VEC>(a + i, v);
         if (training) {
-            const int g = (int)(i / group_elems);
+            const int g = (int)(i / group_elems);           // VEC divides group_elems: a vector never straddles two calls
             const size_t e = i - (size_t)g * group_elems;
             if (g != cur_g) { cur_key = dropout_key(key, g); cur_g = g; }
-            const unsigned long long h = splitmix64(cur_key + e * 0x9E3779B97F4A7C15ull);
-            const float u = (float)(h >> 40) * (1.f / 16777216.f);
-            v = u >= rate ? v * scale : 0.f;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const unsigned long long h = splitmix64(cur_key + (e + j) * 0x9E3779B97F4A7C15ull);
+                const float u = (float)(h >> 40) * (1.f / 16777216.f);
+                v[j] = u >= rate ? v[j] * scale : 0.f;
+            }
         }
-        if (MODE == 1 && accumulate) v += ldf(o + i);
-        stf(o + i, v);
+        if (MODE == 1 && accumulate) {
+            float w[VEC];
+            load_vec<T, VEC>(o + i, w);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) v[j] += w[j];
+        }
+        store_vec<T, VEC>(o + i, v);
     }
+}
+template <typename T, int MODE>
+static int dropout_launch(const T* a, T* o, size_t group_elems, int groups, float rate, const DropKey& key, int training,
+                          int accumulate, cudaStream_t st) {
+    if (!group_elems || !groups) return CG_OK;
+    constexpr int VW = VecWidth<T>::value;
+    const float scale = 1.f / (1.f - rate);
+    const size_t total = group_elems * (size_t)groups;
+    if (group_elems % VW == 0 && !(((uintptr_t)a | (uintptr_t)o) & 15))
+        dropout_kernel<T, MODE, VW><<<x_blocks(total / VW), XT, 0, st>>>(a, o, group_elems, groups, rate, scale, key, training, accumulate);
+    else
+        dropout_kernel<T, MODE, 1><<<x_blocks(total), XT, 0, st>>>(a, o, group_elems, groups, rate, scale, key, training, accumulate);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
 }
 template <typename T> int k_dropout_fwd(const T* x, T* y, size_t group_elems, int groups, float rate, const DropKey& key,
                                         int training, cudaStream_t st) {
-    if (!group_elems || !groups) return CG_OK;
-    dropout_kernel<T, 0><<<x_blocks(group_elems * groups), XT, 0, st>>>(x, y, group_elems, groups, rate, 1.f / (1.f - rate), key,
-                                                                          training, 0);
-    CG_LAUNCH_CHECK();
-    return CG_OK;
+    return dropout_launch<T, 0>(x, y, group_elems, groups, rate, key, training, 0, st);
 }
 template <typename T> int k_dropout_bwd(const T* dy, T* dx, size_t group_elems, int groups, float rate, const DropKey& key,
                                         int training, int accumulate, cudaStream_t st) {
-    if (!group_elems || !groups) return CG_OK;
-    dropout_kernel<T, 1><<<x_blocks(group_elems * groups), XT, 0, st>>>(dy, dx, group_elems, groups, rate, 1.f / (1.f - rate), key,
-                                                                          training, accumulate);
-    CG_LAUNCH_CHECK();
-    return CG_OK;
+    return dropout_launch<T, 1>(dy, dx, group_elems, groups, rate, key, training, accumulate, st);
 }
 template int k_dropout_fwd<float>(const float*, float*, size_t, int, float, const DropKey&, int, cudaStream_t);
 template int k_dropout_fwd<bf16>(const bf16*, bf16*, size_t, int, float, const DropKey&, int, cudaStream_t);
@@ -232,31 +250,36 @@ int k_set_counter(unsigned long long* ctr_dev, unsigned long long value, cudaStr
 // ------------------------------------------------------------------------------------------
 // input pipeline
 // ------------------------------------------------------------------------------------------
-// normalize (data_load.py:31-34): 16 bytes in, 4 x 16 bytes out per thread and iteration
+// normalize (data_load.py:31-34).  A thread converts 4-byte groups (one uchar4 in, one float4 out): a warp reads 128
+// and writes 512 contiguous bytes per access, four independent groups in flight per thread.
 __global__ void __launch_bounds__(XT) normalize_u8_kernel(const uint8_t* __restrict__ s, float* __restrict__ d, size_t n) {
-    const size_t n16 = n / 16;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
-        const uint4 q = reinterpret_cast<const uint4*>(s)[i];
-        const unsigned w[4] = {q.x, q.y, q.z, q.w};
+    const size_t n4 = n / 4, stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    auto cvt = [](unsigned w) {
+        float4 o;
+        o.x = (float)(w & 255u) / 127.5f - 1.f;
+        o.y = (float)((w >> 8) & 255u) / 127.5f - 1.f;
+        o.z = (float)((w >> 16) & 255u) / 127.5f - 1.f;
+        o.w = (float)(w >> 24) / 127.5f - 1.f;
+        return o;
+    };
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+        unsigned w[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float4 o;
-            o.x = (float)(w[j] & 255u) / 127.5f - 1.f;
-            o.y = (float)((w[j] >> 8) & 255u) / 127.5f - 1.f;
-            o.z = (float)((w[j] >> 16) & 255u) / 127.5f - 1.f;
-            o.w = (float)(w[j] >> 24) / 127.5f - 1.f;
-            reinterpret_cast<float4*>(d)[i * 4 + j] = o;
-        }
+        for (int u = 0; u < 4; ++u) w[u] = reinterpret_cast<const unsigned*>(s)[i + u * stride];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) reinterpret_cast<float4*>(d)[i + u * stride] = cvt(w[u]);
     }
-    if (blockIdx.x == 0 && threadIdx.x < (n & 15)) {
-        const size_t i = n16 * 16 + threadIdx.x;
-        d[i] = (float)s[i] / 127.5f - 1.f;
+    for (; i < n4; i += stride) reinterpret_cast<float4*>(d)[i] = cvt(reinterpret_cast<const unsigned*>(s)[i]);
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const size_t t = n4 * 4 + threadIdx.x;
+        d[t] = (float)s[t] / 127.5f - 1.f;
     }
 }
 extern "C" int cg_normalize_u8(const uint8_t* src, float* dst, size_t n, void* stream) {
     if (!src || !dst) { cg_set_error("cg_normalize_u8: null argument"); return CG_ERR_INVALID; }
     if (n == 0) return CG_OK;
-    if (((uintptr_t)src | (uintptr_t)dst) & 15) { cg_set_error("cg_normalize_u8: buffers must be 16-byte aligned"); return CG_ERR_INVALID; }
+    if (((uintptr_t)src & 3) || ((uintptr_t)dst & 15)) { cg_set_error("cg_normalize_u8: src must be 4-byte, dst 16-byte aligned"); return CG_ERR_INVALID; }
     normalize_u8_kernel<<<x_blocks(n / 16 + 1), XT, 0, (cudaStream_t)stream>>>(src, dst, n);
     CG_LAUNCH_CHECK();
     return CG_OK;
@@ -268,25 +291,26 @@ __device__ __forceinline__ unsigned post_u8(float v) {
     return (unsigned)fminf(fmaxf(truncf(t), 0.f), 255.f);
 }
 __global__ void __launch_bounds__(XT) postprocess_u8_kernel(const float* __restrict__ s, uint8_t* __restrict__ d, size_t n) {
-    const size_t n16 = n / 16;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
-        unsigned w[4];
+    const size_t n4 = n / 4, stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    auto cvt = [](float4 q) { return post_u8(q.x) | (post_u8(q.y) << 8) | (post_u8(q.z) << 16) | (post_u8(q.w) << 24); };
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+        float4 q[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 q = reinterpret_cast<const float4*>(s)[i * 4 + j];
-            w[j] = post_u8(q.x) | (post_u8(q.y) << 8) | (post_u8(q.z) << 16) | (post_u8(q.w) << 24);
-        }
-        reinterpret_cast<uint4*>(d)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int u = 0; u < 4; ++u) q[u] = reinterpret_cast<const float4*>(s)[i + u * stride];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) reinterpret_cast<unsigned*>(d)[i + u * stride] = cvt(q[u]);
     }
-    if (blockIdx.x == 0 && threadIdx.x < (n & 15)) {
-        const size_t i = n16 * 16 + threadIdx.x;
-        d[i] = (uint8_t)post_u8(s[i]);
+    for (; i < n4; i += stride) reinterpret_cast<unsigned*>(d)[i] = cvt(reinterpret_cast<const float4*>(s)[i]);
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const size_t t = n4 * 4 + threadIdx.x;
+        d[t] = (uint8_t)post_u8(s[t]);
     }
 }
 extern "C" int cg_postprocess_u8(const float* src, uint8_t* dst, size_t n, void* stream) {
     if (!src || !dst) { cg_set_error("cg_postprocess_u8: null argument"); return CG_ERR_INVALID; }
     if (n == 0) return CG_OK;
-    if (((uintptr_t)src | (uintptr_t)dst) & 15) { cg_set_error("cg_postprocess_u8: buffers must be 16-byte aligned"); return CG_ERR_INVALID; }
+    if (((uintptr_t)src & 15) || ((uintptr_t)dst & 3)) { cg_set_error("cg_postprocess_u8: src must be 16-byte, dst 4-byte aligned"); return CG_ERR_INVALID; }
     postprocess_u8_kernel<<<x_blocks(n / 16 + 1), XT, 0, (cudaStream_t)stream>>>(src, dst, n);
     CG_LAUNCH_CHECK();
     return CG_OK;
@@ -302,17 +326,23 @@ __device__ __forceinline__ void resize_coord(int o, float scale, int size, int& 
     hi = min((int)ceilf(in), size - 1);
     lerp = __fsub_rn(in, f);
 }
-// one thread per output pixel; the C (= 3) channels of the four source pixels are contiguous.  Output pixel (y, x) of
-// image n samples the virtual [Hr, Wr] resized image at (oy[n] + y, ox[n] + x') with x' mirrored when flip[n].
-__global__ void __launch_bounds__(XT) resize_kernel(const float* __restrict__ src, int N, int H, int W, int C, int Hr, int Wr,
+// One thread per output PIXEL of one output row segment: grid = (row segments, Ho, N), so the row / image indices come
+// from the block index (no 64-bit divisions) and the interpolation coordinates are computed once per pixel.  With CC = 3
+// (images) the block's 256 x 3 results are staged in shared memory and stored as contiguous 4-byte lanes (a thread's own 12
+// bytes would make every warp store touch three lines); CC = 0 is the run-time-C fallback with direct stores.
+// Output pixel (y, x) of image n samples the virtual [Hr, Wr] resized image at (oy[n] + y, ox[n] + x') with x' mirrored
+// when flip[n].
+template <int CC>
+__global__ void __launch_bounds__(XT) resize_kernel(const float* __restrict__ src, int H, int W, int Crt, int Hr, int Wr,
                                                     float* __restrict__ dst, int Ho, int Wo, const int* __restrict__ oy,
                                                     const int* __restrict__ ox, const int* __restrict__ flip) {
-    const float sy = (float)H / (float)Hr, sx = (float)W / (float)Wr;
-    const size_t total = (size_t)N * Ho * Wo;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int x = (int)(i % Wo);
-        const size_t r = i / Wo;
-        const int y = (int)(r % Ho), n = (int)(r / Ho);
+    __shared__ float stage[CC ? XT * CC : 1];
+    const int C = CC ? CC : Crt;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, n = blockIdx.z;
+    float* out_row = dst + ((size_t)n * Ho + y) * Wo * C;
+    if (x < Wo) {
+        const float sy = (float)H / (float)Hr, sx = (float)W / (float)Wr;
         const int yy = y + (oy ? oy[n] : 0);
         const int xr = (flip && flip[n]) ? Wo - 1 - x : x;
         const int xx = xr + (ox ? ox[n] : 0);
@@ -324,25 +354,35 @@ __global__ void __launch_bounds__(XT) resize_kernel(const float* __restrict__ sr
         const float* p01 = src + (((size_t)n * H + y0) * W + x1) * C;
         const float* p10 = src + (((size_t)n * H + y1) * W + x0) * C;
         const float* p11 = src + (((size_t)n * H + y1) * W + x1) * C;
-        float* o = dst + i * C;
-        for (int c = 0; c < C; ++c) {
+#pragma unroll
+        for (int c = 0; c < (CC ? CC : C); ++c) {
             // TF's compute_lerp order, every operation rounded on its own (bit-identical to a float32 numpy restatement)
             const float top = __fadd_rn(p00[c], __fmul_rn(__fsub_rn(p01[c], p00[c]), lx));
             const float bot = __fadd_rn(p10[c], __fmul_rn(__fsub_rn(p11[c], p10[c]), lx));
-            o[c] = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
+            const float v = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
+            if (CC) stage[threadIdx.x * CC + c] = v;
+            else out_row[(size_t)x * C + c] = v;
         }
+    }
+    if (CC) {
+        __syncthreads();
+        const int e0 = blockIdx.x * blockDim.x * CC;                 // first element of this segment in the output row
+        const int ne = min(XT * CC, Wo * CC - e0);
+        for (int e = threadIdx.x; e < ne; e += XT) out_row[e0 + e] = stage[e];
     }
 }
 extern "C" int cg_resize_crop_flip(const float* src, int N, int H, int W, int C, int Hr, int Wr, float* dst, int Ho, int Wo,
                                    const int32_t* oy, const int32_t* ox, const int32_t* flip, void* stream) {
     if (!src || !dst) { cg_set_error("cg_resize_crop_flip: null argument"); return CG_ERR_INVALID; }
-    if (N < 0 || H <= 0 || W <= 0 || C <= 0 || Hr <= 0 || Wr <= 0 || Ho <= 0 || Wo <= 0 || Ho > Hr || Wo > Wr) {
+    if (N < 0 || H <= 0 || W <= 0 || C <= 0 || Hr <= 0 || Wr <= 0 || Ho <= 0 || Wo <= 0 || Ho > Hr || Wo > Wr || Ho > 65535 ||
+        N > 65535 || (long long)W * C > (1 << 30) || (long long)Wo * C > (1 << 30)) {
         cg_set_error("cg_resize_crop_flip: bad geometry %dx%dx%dx%d -> %dx%d -> crop %dx%d", N, H, W, C, Hr, Wr, Ho, Wo);
         return CG_ERR_INVALID;
     }
     if (N == 0) return CG_OK;
-    resize_kernel<<<x_blocks((size_t)N * Ho * Wo), XT, 0, (cudaStream_t)stream>>>(src, N, H, W, C, Hr, Wr, dst, Ho, Wo, oy, ox,
-                                                                               flip);
+    const dim3 grid(cdiv(Wo, XT), Ho, N);
+    if (C == 3) resize_kernel<3><<<grid, XT, 0, (cudaStream_t)stream>>>(src, H, W, C, Hr, Wr, dst, Ho, Wo, oy, ox, flip);
+    else resize_kernel<0><<<grid, XT, 0, (cudaStream_t)stream>>>(src, H, W, C, Hr, Wr, dst, Ho, Wo, oy, ox, flip);
     CG_LAUNCH_CHECK();
     return CG_OK;
 }

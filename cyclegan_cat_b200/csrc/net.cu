@@ -790,7 +790,7 @@ int net_forward(CallCtx* ctx, const float* params, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------
 template <typename T>
 static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in, float* grads, int n0, int nb,
-                      cudaStream_t st) {
+                      cudaStream_t st, LayerHook hook, void* hook_user) {
     const cg_net_s* net = c->net;
     const int nl = (int)net->layers.size();
     if (!c->bwd || !c->forwarded) { cg_set_error("backward without a planned forward"); return CG_ERR_STATE; }
@@ -1089,13 +1089,14 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
             default: cg_set_error("unknown op %d", d.op); return CG_ERR_INVALID;
         }
         if (want_dx) written[tin] = 1;
+        if (hook) CG_TRY(hook(hook_user, i));
     }
     return CG_OK;
 }
 
 int net_backward(CallCtx* ctx, const float* params, const void* dy, void* dx, float* grads, int n0, int nb,
-                 cudaStream_t st) {
+                 cudaStream_t st, LayerHook hook, void* hook_user) {
     return ctx->net->mode == CG_MODE_BF16
-               ? backward_T<bf16>(ctx, params, (const bf16*)dy, (bf16*)dx, grads, n0, nb, st)
-               : backward_T<float>(ctx, params, (const float*)dy, (float*)dx, grads, n0, nb, st);
+               ? backward_T<bf16>(ctx, params, (const bf16*)dy, (bf16*)dx, grads, n0, nb, st, hook, hook_user)
+               : backward_T<float>(ctx, params, (const float*)dy, (float*)dx, grads, n0, nb, st, hook, hook_user);
 }

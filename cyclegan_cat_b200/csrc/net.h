@@ -109,7 +109,10 @@ int net_out_hw(const cg_net_s* net, int H, int W, int* ho, int* wo);
 int net_forward(CallCtx* ctx, const float* params, cudaStream_t st);
 // backward over samples [n0, n0+nb): dy is dLoss/d(output) for those samples (activation dtype);
 // dx (nullable) receives dLoss/d(input); parameter gradients are ACCUMULATED into grads when non-null.
+// `hook` (nullable) is called after the backward launches of each layer, last layer first: every parameter gradient of
+// the layers >= that index is then complete on `st` (the data-parallel trainer all-reduces them bucket by bucket).
+typedef int (*LayerHook)(void* user, int layer);
 int net_backward(CallCtx* ctx, const float* params, const void* dy, void* dx, float* grads, int n0, int nb,
-                 cudaStream_t st);
+                 cudaStream_t st, LayerHook hook = nullptr, void* hook_user = nullptr);
 // BatchNormalization: fold group g's batch statistics of the last training forward into the moving averages
 int net_update_moving(CallCtx* ctx, int g, cudaStream_t st);

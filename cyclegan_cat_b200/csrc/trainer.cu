@@ -14,6 +14,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <vector>
+
 #include "kernels.h"
 #include "net.h"
 #include "prof.h"
@@ -86,7 +88,36 @@ struct cg_trainer_s {
     long long graph_launches[2] = {0, 0};                      // kernels per replay (for cg_launch_count)
     nccl_comm comm = nullptr; int world = 1, rank = 0;
     cudaStream_t comm_stream = nullptr; cudaEvent_t ev_d = nullptr, ev_g = nullptr, ev_done = nullptr;
+    std::vector<cudaEvent_t> ev_bucket;                        // one fork event per gradient bucket of a step
+    int ev_next = 0;
 };
+
+// Bucketed all-reduce of a generator's gradients under its LAST backward call: the flat gradient buffer is
+// in forward-layer order and the backward retires layers last to first, so after layer i every gradient at an offset >=
+// (first variable of layer i) is final.  Whenever >= 1/4 of the net has accumulated, that tail range is all-reduced on
+// the communication stream (fork by event) while the backward continues.
+struct BucketCtx {
+    cg_trainer_s* tr; int net; cudaStream_t st; long long done_from; long long min_floats; int rc_unused;
+};
+static int bucket_fire(BucketCtx* b, long long lo) {
+    cg_trainer_s* tr = b->tr;
+    if (lo >= b->done_from) return CG_OK;
+    if (tr->ev_next >= (int)tr->ev_bucket.size()) { cg_set_error("gradient buckets: out of events"); return CG_ERR_STATE; }
+    cudaEvent_t ev = tr->ev_bucket[tr->ev_next++];
+    CG_CUDA(cudaEventRecord(ev, b->st));
+    CG_CUDA(cudaStreamWaitEvent(tr->comm_stream, ev, 0));
+    float* g = tr->grads[b->net] + lo;
+    CG_NCCL(g_nccl.AllReduce(g, g, (size_t)(b->done_from - lo), 7, 0, tr->comm, tr->comm_stream));
+    b->done_from = lo;
+    return CG_OK;
+}
+static int bucket_hook(void* user, int layer) {
+    BucketCtx* b = (BucketCtx*)user;
+    const LayerInfo& L = b->tr->net[b->net]->layers[layer];
+    const long long lo = L.w_off >= 0 ? L.w_off : L.g_off;      // first variable of the layer (kernel or gamma)
+    if (lo < 0 || b->done_from - lo < b->min_floats) return CG_OK;
+    return bucket_fire(b, lo);
+}
 
 static size_t es_of(cg_trainer_t tr) { return tr->net[0]->elem_size(); }
 
@@ -200,6 +231,7 @@ extern "C" void cg_trainer_destroy(cg_trainer_t tr) {
     if (tr->ev_d) cudaEventDestroy(tr->ev_d);
     if (tr->ev_g) cudaEventDestroy(tr->ev_g);
     if (tr->ev_done) cudaEventDestroy(tr->ev_done);
+    for (cudaEvent_t e : tr->ev_bucket) cudaEventDestroy(e);
     delete tr;
 }
 
@@ -326,7 +358,21 @@ static int step_body(cg_trainer_t tr, int B, int H, int W, bool train, cudaStrea
     CG_TRY(k_copy_acc<T>(dxC1, seedF1, n_img, 1, st));
     CG_TRY(net_backward(&tr->C2, tr->params[0], seedC2, dxC2, tr->grads[0], 0, B, st));  // theta_AB, d fake_a
     CG_TRY(k_copy_acc<T>(dxC2, seedF2, n_img, 1, st));
-    // first-hop generator calls: [d fake ; d same]
+    // first-hop generator calls: [d fake ; d same].  These are the last contributions to theta_AB / theta_BA, so with a
+    // communicator their gradients are all-reduced bucket by bucket while the backward is still running
+    static const bool buckets_on = [] { const char* e = getenv("CG_DP_BUCKETS"); return !(e && e[0] == '0'); }();
+    if (tr->comm && buckets_on) {
+        tr->ev_next = 0;
+        BucketCtx b0{tr, 0, st, tr->net[0]->n_params, tr->net[0]->n_params / 4 + 1, 0};
+        CG_TRY(net_backward(&tr->F1, tr->params[0], seedF1, nullptr, tr->grads[0], 0, 2 * B, st, bucket_hook, &b0));
+        CG_TRY(bucket_fire(&b0, 0));
+        BucketCtx b1{tr, 1, st, tr->net[1]->n_params, tr->net[1]->n_params / 4 + 1, 0};
+        CG_TRY(net_backward(&tr->F2, tr->params[1], seedF2, nullptr, tr->grads[1], 0, 2 * B, st, bucket_hook, &b1));
+        CG_TRY(bucket_fire(&b1, 0));
+        CG_CUDA(cudaEventRecord(tr->ev_done, tr->comm_stream));
+        CG_CUDA(cudaStreamWaitEvent(st, tr->ev_done, 0));
+        return CG_OK;
+    }
     CG_TRY(net_backward(&tr->F1, tr->params[0], seedF1, nullptr, tr->grads[0], 0, 2 * B, st));
     CG_TRY(net_backward(&tr->F2, tr->params[1], seedF2, nullptr, tr->grads[1], 0, 2 * B, st));
     if (tr->comm) {
@@ -512,6 +558,8 @@ extern "C" int cg_trainer_comm_init(cg_trainer_t tr, const char id_in[128], int 
     CG_CUDA(cudaEventCreateWithFlags(&tr->ev_d, cudaEventDisableTiming));
     CG_CUDA(cudaEventCreateWithFlags(&tr->ev_g, cudaEventDisableTiming));
     CG_CUDA(cudaEventCreateWithFlags(&tr->ev_done, cudaEventDisableTiming));
+    tr->ev_bucket.resize(16);
+    for (cudaEvent_t& e : tr->ev_bucket) CG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (int g = 0; g < 2; ++g) {          // the step body changes (all-reduces): captured graphs are stale
         if (tr->graph_exec[g]) { cudaGraphExecDestroy(tr->graph_exec[g]); tr->graph_exec[g] = nullptr; }
         tr->graph_seen[g] = 0;

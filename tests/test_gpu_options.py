@@ -375,3 +375,26 @@ def test_predict_path_with_device_pipeline():
     out = DL.postprocess_prediction(y)
     assert out.shape == (1, 64, 64, 3) and out.dtype == np.uint8
     assert np.array_equal(out, T.postprocess_prediction(y.numpy()))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_c5_generator_inference_at_512(mode):
+    """BASELINE.json configs[4] (C5): cycle.yaml U-Net generator forward at 512x512 (predict.py path), full image size,
+    against the fp64 oracle.  bf16 gate: 31 conv layers of bf16 activation storage -- rounding the fp64 oracle's OWN
+    activations to bf16 at the points where the CUDA path stores them (no GPU involved) already moves this output by
+    5.1e-2 on exactly this input and these weights; the B200 path measures 5.6e-2 (DESIGN.md "bf16 tolerance")."""
+    m = create_model(C.UNET_G, mode=mode)
+    o = om.create_model(C.UNET_G, torch.float64)
+    w = om.init_variables(o.var_specs, 42)
+    m.set_weights(w)
+    o.load(w)
+    u8 = np.random.RandomState(9).randint(0, 256, size=(1, 512, 512, 3)).astype(np.uint8)
+    y = m(DL.normalize_device(u8))
+    with torch.no_grad():
+        ref = o(T.normalize(u8)).numpy()
+    assert y.shape == (1, 512, 512, 3)
+    assert C.rel_l2(y.numpy(), ref) <= (1e-4 if mode == "fp32" else 8e-2), C.rel_l2(y.numpy(), ref)
+    out, want = DL.postprocess_prediction(y), T.postprocess_prediction(ref)
+    # uint8 results may differ by one level where (p + 1) * 127.5 sits next to an integer
+    if mode == "fp32":
+        assert np.abs(out.astype(np.int32) - want.astype(np.int32)).max() <= 1 and (out != want).mean() <= 1e-3
