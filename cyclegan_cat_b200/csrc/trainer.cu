@@ -359,8 +359,10 @@ static int step_body(cg_trainer_t tr, int B, int H, int W, bool train, cudaStrea
     CG_TRY(net_backward(&tr->C2, tr->params[0], seedC2, dxC2, tr->grads[0], 0, B, st));  // theta_AB, d fake_a
     CG_TRY(k_copy_acc<T>(dxC2, seedF2, n_img, 1, st));
     // first-hop generator calls: [d fake ; d same].  These are the last contributions to theta_AB / theta_BA, so with a
-    // communicator their gradients are all-reduced bucket by bucket while the backward is still running
-    static const bool buckets_on = [] { const char* e = getenv("CG_DP_BUCKETS"); return !(e && e[0] == '0'); }();
+    // communicator their gradients can be all-reduced bucket by bucket while the backward is still running
+    // (CG_DP_BUCKETS=1).  Opt-in: on 2 GPUs it measured neutral (45.58 vs 45.39 ms per step -- the two 45 MB reductions
+    // at the end cost ~0.1 ms there, and NCCL's CTAs compete with the backward's persistent kernels for SMs).
+    static const bool buckets_on = [] { const char* e = getenv("CG_DP_BUCKETS"); return e && e[0] == '1'; }();
     if (tr->comm && buckets_on) {
         tr->ev_next = 0;
         BucketCtx b0{tr, 0, st, tr->net[0]->n_params, tr->net[0]->n_params / 4 + 1, 0};
