@@ -18,6 +18,11 @@ void cg_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+bool cg_pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("CG_DISABLE_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
+
 extern "C" const char* cg_last_error(void) { return g_err; }
 extern "C" int cg_version(void) { return 110; }
 extern "C" int cg_abi_sizeof(int which) {

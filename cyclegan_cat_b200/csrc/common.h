@@ -40,6 +40,24 @@ extern std::atomic<long long> g_launches;      // kernels launched by this libra
         }                                                                                 \
     } while (0)
 
+// Launch with programmatic stream serialization (PDL): the kernel may be scheduled while its predecessor in the stream
+// is still draining; it must call griddep_wait() (ptx_async.h) before touching global memory.  CG_DISABLE_PDL=1 turns
+// the attribute off (plain stream order) for A/B measurements.
+bool cg_pdl_enabled();
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cg_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

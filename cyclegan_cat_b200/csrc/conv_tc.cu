@@ -205,6 +205,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    griddep_launch();        // PDL: the next kernel may take the slots this grid frees and run its prologue
+    griddep_wait();          // everything above is independent of the previous kernel; global memory is not
 
     const int total_tiles = a.nb * a.tiles_per_img * a.n_blocks_n;
     // bk16: cchunks = K steps per tap (blocks of `groups` 16-channel groups), or several taps per K step
@@ -627,6 +629,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    griddep_launch();        // PDL: the next kernel may take the slots this grid frees and run its prologue
+    griddep_wait();          // everything above is independent of the previous kernel; global memory is not
 
     // decode the work unit
     int u = blockIdx.x;
@@ -777,6 +781,8 @@ wgrad16_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    griddep_launch();        // PDL: the next kernel may take the slots this grid frees and run its prologue
+    griddep_wait();          // everything above is independent of the previous kernel; global memory is not
 
     const int split = blockIdx.x % a.splits, mb = blockIdx.x / a.splits;
     const int total_chunks = a.nb * a.chunks_per_img;
@@ -1059,11 +1065,11 @@ int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, const CUten
     int grid = total < slots ? total : slots;
     int pi = prof_begin(st);
     if (dual) {
-        if (a.bk16) conv_tc_kernel<true, true><<<grid, TC_THREADS, smem, st>>>(*mapA, *mapB, out, bias, a);
-        else conv_tc_kernel<false, true><<<grid, TC_THREADS, smem, st>>>(*mapA, *mapB, out, bias, a);
+        if (a.bk16) launch_pdl(conv_tc_kernel<true, true>, dim3(grid), dim3(TC_THREADS), smem, st, *mapA, *mapB, out, bias, a);
+        else launch_pdl(conv_tc_kernel<false, true>, dim3(grid), dim3(TC_THREADS), smem, st, *mapA, *mapB, out, bias, a);
     } else {
-        if (a.bk16) conv_tc_kernel<true, false><<<grid, CONV_THREADS, smem, st>>>(*mapA, *mapB, out, bias, a);
-        else conv_tc_kernel<false, false><<<grid, CONV_THREADS, smem, st>>>(*mapA, *mapB, out, bias, a);
+        if (a.bk16) launch_pdl(conv_tc_kernel<true, false>, dim3(grid), dim3(CONV_THREADS), smem, st, *mapA, *mapB, out, bias, a);
+        else launch_pdl(conv_tc_kernel<false, false>, dim3(grid), dim3(CONV_THREADS), smem, st, *mapA, *mapB, out, bias, a);
     }
     prof_end(pi, st, flops, prof_key(1, a.n_taps, a.cchunks, a.bn, a.tiles_per_img, a.nb));
     CG_LAUNCH_CHECK();
@@ -1092,7 +1098,7 @@ int tc_wgrad_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* dw
         attr_set = true;
     }
     int pi = prof_begin(st);
-    wgrad_tc_kernel<<<units * splits, TC_THREADS, smem, st>>>(*mapX, *mapDY, dw, a);
+    launch_pdl(wgrad_tc_kernel, dim3(units * splits), dim3(TC_THREADS), smem, st, *mapX, *mapDY, dw, a);
     prof_end(pi, st, flops, prof_key(3, a.n_taps, a.a_blocks * a.b_blocks, a.bn, a.chunks_per_img, a.nb));
     CG_LAUNCH_CHECK();
     return CG_OK;
@@ -1118,7 +1124,7 @@ int tc_wgrad16_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* 
         attr_set = true;
     }
     int pi = prof_begin(st);
-    wgrad16_tc_kernel<<<a.m_blocks * splits, TC_THREADS, smem, st>>>(*mapX, *mapDY, dw, a);
+    launch_pdl(wgrad16_tc_kernel, dim3(a.m_blocks * splits), dim3(TC_THREADS), smem, st, *mapX, *mapDY, dw, a);
     prof_end(pi, st, flops, prof_key(4, a.n_taps, a.m_blocks, a.Cout, a.chunks_per_img, a.nb));
     CG_LAUNCH_CHECK();
     return CG_OK;

@@ -3,6 +3,7 @@
 // reductions (value + gradient seed) and the fused Adam update.  NHWC everywhere; 16-byte
 // vector accesses whenever the channel count allows; warp-shuffle reductions.
 #include "kernels.h"
+#include "ptx_async.h"
 
 static const int EW_THREADS = 256;
 static inline int ew_blocks(size_t work) {
@@ -103,6 +104,8 @@ __global__ void __launch_bounds__(256) in_reduce_kernel(const T* __restrict__ x,
 }
 
 __global__ void in_finalize_kernel(float* __restrict__ stats, int NC, float invP, float eps) {
+    griddep_launch();        // PDL: see ptx_async.h
+    griddep_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NC) return;
     float mean = stats[2 * i] * invP;
@@ -122,7 +125,7 @@ static inline void in_reduce_grid(int N, int P, int C, dim3& grid, int& pchunk) 
 }
 
 int k_in_finalize(float* stats, int NC, int P, float eps, cudaStream_t st) {
-    in_finalize_kernel<<<cdiv(NC, 256), 256, 0, st>>>(stats, NC, 1.f / (float)P, eps);
+    launch_pdl(in_finalize_kernel, dim3(cdiv(NC, 256)), dim3(256), 0, st, stats, NC, 1.f / (float)P, eps);
     CG_LAUNCH_CHECK();
     return CG_OK;
 }

@@ -73,6 +73,8 @@ __global__ void __launch_bounds__(ST_THREADS, (MODE == 0 || MODE == 4) ? 3 : 2) 
         fence_barrier_init();
     }
     __syncthreads();
+    griddep_launch();        // PDL: see ptx_async.h
+    griddep_wait();
 
     const size_t img_elems = (size_t)a.P * a.C;
     if (warp == ST_CONSUMERS / 32) {                 // ---- producer ----
@@ -295,7 +297,7 @@ int launch_stream(StreamArgs<T>& a, int N, cudaStream_t st) {
     if (G < 1) G = 1;
     static const bool prof_stream = [] { const char* e = getenv("CG_PROF_STREAM"); return e && e[0] == '1'; }();
     const int pi = prof_stream ? prof_begin(st) : -1;      // diagnostic: in-step timing of the streaming kernels (CSV kinds 8+MODE)
-    kern<<<dim3(G, N), ST_THREADS, smem, st>>>(a);
+    launch_pdl(kern, dim3(G, N), dim3(ST_THREADS), smem, st, a);
     if (pi >= 0) {
         const double bytes = (double)N * a.P * a.C * sizeof(T) * (MODE == 4 ? 1 : (MODE == 0 || MODE == 1) ? 2 : 3);
         prof_end(pi, st, bytes, prof_key(8 + MODE, MODE, 0, a.C, a.tiles_per_img, N));

@@ -29,6 +29,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (spin > (1u << 26)) __trap();
     }
 }
+// Programmatic dependent launch (launch attribute cudaLaunchAttributeProgrammaticStreamSerialization, see launch_pdl in
+// common.h): `griddep_launch` lets the NEXT kernel of the stream start being scheduled (its CTAs take the SM slots this
+// grid frees and run their prologue), `griddep_wait` blocks until the PREVIOUS grid has completed and its memory is
+// visible.  A kernel launched with the attribute must execute the wait before it touches global memory.  Both are
+// no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
