@@ -876,6 +876,45 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restric
     }
 }
 
+// all regular tensor-core layers of a net in ONE launch (the per-layer launches were ~9 us each, 50 per step): a block
+// finds its layer in the prefix table of the job list and packs a grid-stride share of it
+__global__ void pack_weights_multi_kernel(const __grid_constant__ TcPackJobs jobs) {
+    int j = 0;
+    while (j + 1 < jobs.n && (int)blockIdx.x >= jobs.block0[j + 1]) ++j;
+    const float* __restrict__ w = jobs.w[j];
+    bf16* __restrict__ wf = jobs.wf[j];
+    bf16* __restrict__ wd = jobs.wd[j];
+    const int Cin = jobs.cin[j], Cout = jobs.cout[j];
+    const size_t n = (size_t)jobs.taps[j] * Cin * Cout;
+    const int b = blockIdx.x - jobs.block0[j], nb = jobs.block0[j + 1] - jobs.block0[j];
+    for (size_t i = b * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)nb * blockDim.x) {
+        const int co = (int)(i % Cout);
+        const size_t r = i / Cout;
+        const int ci = (int)(r % Cin);
+        const int tap = (int)(r / Cin);
+        const bf16 v = __float2bfloat16(w[i]);
+        wd[i] = v;
+        wf[((size_t)tap * Cout + co) * Cin + ci] = v;
+    }
+}
+
+int tc_pack_weights_multi(TcPackJobs& jobs, cudaStream_t st) {
+    if (jobs.n == 0) return CG_OK;
+    int total = 0;
+    for (int j = 0; j < jobs.n; ++j) {
+        const size_t n = (size_t)jobs.taps[j] * jobs.cin[j] * jobs.cout[j];
+        int blocks = (int)((n + 255) / 256);
+        if (blocks > 148 * 2) blocks = 148 * 2;
+        jobs.block0[j] = total;
+        total += blocks;
+    }
+    jobs.block0[jobs.n] = total;
+    pack_weights_multi_kernel<<<total, 256, 0, st>>>(jobs);
+    CG_LAUNCH_CHECK();
+    jobs.n = 0;
+    return CG_OK;
+}
+
 int tc_pack_weights(const float* w, bf16* wf, bf16* wd, int taps, int Cin, int Cout, cudaStream_t st) {
     size_t n = (size_t)taps * Cin * Cout;
     int blocks = (int)((n + 255) / 256);

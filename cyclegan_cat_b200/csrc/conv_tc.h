@@ -62,6 +62,14 @@ int tc_make_map_2d(CUtensorMap* map, const void* base, int cols, int rows, int b
 int tc_make_map_act16(CUtensorMap* map, const void* base, int C, int W, int H, int N, int box_w, int box_h, int groups);
 int tc_make_map_w16(CUtensorMap* map, const void* base, int cols, int rows, int box_rows, int groups);
 int tc_pack_weights(const float* w, bf16* wf, bf16* wd, int taps, int Cin, int Cout, cudaStream_t st);
+// batched form: fill jobs (n <= TC_PACK_MAX), then one launch; tc_pack_weights_multi resets jobs.n
+enum { TC_PACK_MAX = 32 };
+struct TcPackJobs {
+    const float* w[TC_PACK_MAX]; bf16* wf[TC_PACK_MAX]; bf16* wd[TC_PACK_MAX];
+    int taps[TC_PACK_MAX], cin[TC_PACK_MAX], cout[TC_PACK_MAX], block0[TC_PACK_MAX + 1];
+    int n;
+};
+int tc_pack_weights_multi(TcPackJobs& jobs, cudaStream_t st);
 // mapB2 (nullable): the same weight matrix with a box of bn/2 rows, for the 2-CTA kernel
 int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, const CUtensorMap* mapB2, bf16* out, const float* bias,
                    TcConvArgs a, double flops, cudaStream_t st);

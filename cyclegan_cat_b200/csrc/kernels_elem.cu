@@ -566,6 +566,8 @@ __global__ void rpad_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, in
 // rows the columns 1..p and W-1-p..W-2.  One thread = one 16-byte vector of one affected pixel.
 template <typename T, int VEC>
 __global__ void rpad_bwd_border_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int H, int W, int Cv, int p) {
+    griddep_launch();        // PDL: see ptx_async.h (this kernel sits between the data-gradient conv and the next norm backward)
+    griddep_wait();
     const int Ho = H + 2 * p, Wo = W + 2 * p;
     const int full_rows = 2 * p, side_rows = H - 2 * p;       // affected pixels per image: full_rows*W + side_rows*2p
     const int per_img = full_rows * W + side_rows * 2 * p;
@@ -608,7 +610,7 @@ template <typename T> int k_rpad_bwd_border(const T* dy, T* dx, int N, int H, in
     constexpr int VW = VecWidth<T>::value;
     if (C % VW || H <= 2 * p + 1 || W <= 2 * p + 1) { cg_set_error("rpad_bwd_border: unsupported shape"); return CG_ERR_INVALID; }
     const size_t total = (size_t)N * (2 * p * W + (H - 2 * p) * 2 * p) * (C / VW);
-    rpad_bwd_border_kernel<T, VW><<<ew_blocks(total), EW_THREADS, 0, st>>>(dy, dx, N, H, W, C / VW, p);
+    launch_pdl(rpad_bwd_border_kernel<T, VW>, dim3(ew_blocks(total)), dim3(EW_THREADS), 0, st, dy, dx, N, H, W, C / VW, p);
     CG_LAUNCH_CHECK();
     return CG_OK;
 }

@@ -186,6 +186,8 @@ int net_plan(const cg_net_s* net, int N, int H, int W, bool bwd, CallCtx* ctx) {
 int net_pack(const cg_net_s* net, const float* params, void* packed, cudaStream_t st) {
     if (!net->packed_bytes) return CG_OK;
     if (!packed) { cg_set_error("net_pack: no packed-weight buffer"); return CG_ERR_STATE; }
+    TcPackJobs jobs;
+    jobs.n = 0;
     for (const LayerInfo& L : net->layers) {
         if (!L.tc) continue;
         if (L.tc == TC_STEM) {
@@ -205,10 +207,14 @@ int net_pack(const cg_net_s* net, const float* params, void* packed, cudaStream_
         }
         // the TF kernel of a Conv2DTranspose (kh,kw,Cout,Cin) IS the HWIO kernel of the conv F it back-propagates
         const int cin_f = L.d.op == CG_OP_CONV ? L.d.cin : L.d.cout, cout_f = L.d.op == CG_OP_CONV ? L.d.cout : L.d.cin;
-        CG_TRY(tc_pack_weights(params + L.w_off, (bf16*)((char*)packed + L.pk_f), (bf16*)((char*)packed + L.pk_d),
-                               L.d.k * L.d.k, cin_f, cout_f, st));
+        const int j = jobs.n++;
+        jobs.w[j] = params + L.w_off;
+        jobs.wf[j] = (bf16*)((char*)packed + L.pk_f);
+        jobs.wd[j] = (bf16*)((char*)packed + L.pk_d);
+        jobs.taps[j] = L.d.k * L.d.k; jobs.cin[j] = cin_f; jobs.cout[j] = cout_f;
+        if (jobs.n == TC_PACK_MAX) CG_TRY(tc_pack_weights_multi(jobs, st));
     }
-    return CG_OK;
+    return tc_pack_weights_multi(jobs, st);
 }
 
 static inline int floor_div2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
