@@ -398,3 +398,32 @@ def test_c5_generator_inference_at_512(mode):
     # uint8 results may differ by one level where (p + 1) * 127.5 sits next to an integer
     if mode == "fp32":
         assert np.abs(out.astype(np.int32) - want.astype(np.int32)).max() <= 1 and (out != want).mean() <= 1e-3
+
+
+def test_frozen_fixture_optional_paths_fp32():
+    """The CUDA path against the committed vectors of tests/golden/oracle_options.npz (BatchNormalization + Dropout U-Net
+    G, BatchNormalization simple D, AdaBelief / RMSprop): metrics of two training steps and of an inference step, moving
+    statistics, updated weights, a resize sample (the mask bits are compared bit for bit in
+    test_dropout_keep_fraction_and_scaling)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_options.npz"))
+    g_opt, d_opt = dict(name="adabelief", learning_rate=2e-4), dict(name="rmsprop", learning_rate=2e-4)
+    gan = CycleGan(C.model_config(C.BN_DROP_UNET, C.BN_SIMPLE), C.train_config(g_opt=g_opt, d_opt=d_opt), mode="fp32")
+    for i, n in enumerate(NETS):
+        getattr(gan, n).initialize(42 + i)              # the oracle's init_variables(seed 42..45) draws the same numbers
+        getattr(gan, n).set_dropout_seed(100 + i)
+    a, b = synthetic_batch(2, 32)
+    for step in range(2):
+        got = gan.train_step(a, b)
+        for k in ("gAB_loss", "gBA_loss", "dA_loss", "dB_loss"):
+            ref = float(z[f"step{step}_{k}"])
+            assert abs(float(got[k]) - ref) <= (1e-4 if step == 0 else 5e-3) * max(1.0, abs(ref)), (step, k, float(got[k]), ref)
+    got = gan.validate_step(a, b)
+    for k in ("gAB_loss", "gBA_loss", "dA_loss", "dB_loss"):
+        ref = float(z[f"val_{k}"])
+        assert abs(float(got[k]) - ref) <= 5e-3 * max(1.0, abs(ref)), (k, float(got[k]), ref)
+    assert C.rel_l2(gan.g_AB.non_trainable_variables[0].numpy(), z["g_AB_moving_mean0"]) <= 5e-3
+    assert C.rel_l2(gan.g_AB.non_trainable_variables[1].numpy(), z["g_AB_moving_var0"]) <= 1e-4
+    assert C.rel_l2(gan.d_A.non_trainable_variables[3].numpy(), z["d_A_moving_var1"]) <= 1e-4
+    assert C.rel_l2(gan.d_A.get_weights()[0], z["d_A_var0"]) <= 1e-3
+    assert np.abs(DL.resize(z["resize_in"], (33, 17)).numpy() - z["resize_out"]).max() <= 2e-6

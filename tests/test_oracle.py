@@ -252,3 +252,28 @@ def test_batchnorm_and_dropout_builders_train_step_runs():
     assert not torch.equal(before[0], o.g_AB.state[0])
     assert all(np.isfinite(v) for v in m1.values()) and m0["gAB_loss"] != m1["gAB_loss"]
     assert len(o.d_A.state) == 2 * 2 and len(o.d_A.variables) == 2 * 2 + 2      # BN(center=False, scale=False): no gamma/beta
+
+
+def test_frozen_fixture_optional_paths():
+    """tests/golden/oracle_options.npz (make_golden.py): BatchNormalization + Dropout nets under AdaBelief / RMSprop,
+    dropout mask bits, resize / random_jitter samples -- pins the oracle's optional paths against drift."""
+    from oracle import tf_ops as T
+    z = np.load(os.path.join(GOLD, "oracle_options.npz"))
+    o = OracleCycleGan(C.BN_DROP_UNET, C.BN_SIMPLE, g_opt=dict(name="adabelief", learning_rate=2e-4),
+                       d_opt=dict(name="rmsprop", learning_rate=2e-4))
+    for i, n in enumerate(("g_AB", "g_BA", "d_A", "d_B")):
+        getattr(o, n).drop_seed = 100 + i
+    a, b = synthetic_batch(2, 32)
+    for step in range(2):
+        for k, v in o.train_step(a, b).items():
+            assert abs(v - float(z[f"step{step}_{k}"])) <= 5e-5 * max(1.0, abs(v)), (step, k, v, float(z[f"step{step}_{k}"]))
+    for k, v in o.validate_step(a, b).items():
+        assert abs(v - float(z[f"val_{k}"])) <= 5e-4 * max(1.0, abs(v)), (k, v, float(z[f"val_{k}"]))
+    assert C.rel_l2(o.g_AB.state[0].numpy(), z["g_AB_moving_mean0"]) < 1e-4
+    assert C.rel_l2(o.g_AB.state[1].numpy(), z["g_AB_moving_var0"]) < 1e-5
+    assert C.rel_l2(o.d_A.state[3].numpy(), z["d_A_moving_var1"]) < 1e-5
+    assert C.rel_l2(o.d_A.variables[0].detach().numpy(), z["d_A_var0"]) < 1e-4
+    assert np.array_equal(T.dropout_mask(100, 1, 2, 3, 4096, 0.5).astype(np.uint8), z["dropout_mask"])
+    assert np.array_equal(T.resize_bilinear(z["resize_in"], 33, 17), z["resize_out"])
+    assert np.array_equal(T.random_jitter(z["resize_in"], 16, np.array([5, 50]), np.array([0, 31]), np.array([1, 0])),
+                          z["jitter_out"])
