@@ -184,3 +184,35 @@ def test_product_package_does_not_import_oracle():
     code = "import sys; import cyclegan_cat_b200.cyclegan.model, cyclegan_cat_b200.runtime; " \
            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'"
     subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu(built_lib):
+    """Argument checks of the optional-path / input-pipeline entry points happen before any CUDA call, so they can be
+    exercised on a CPU-only box: null pointers, bad geometry, misaligned buffers -> CG_ERR_INVALID (-1) + a message."""
+    lib = built_lib
+    assert lib.cg_normalize_u8(None, None, 16, None) == -1 and b"null" in lib.cg_last_error()
+    assert lib.cg_postprocess_u8(None, None, 16, None) == -1
+    assert lib.cg_normalize_u8(ctypes.c_void_p(0x1001), ctypes.c_void_p(0x2000), 16, None) == -1      # src not 4-byte aligned
+    assert b"aligned" in lib.cg_last_error()
+    assert lib.cg_postprocess_u8(ctypes.c_void_p(0x1008), ctypes.c_void_p(0x2000), 16, None) == -1     # src not 16-byte aligned
+    assert lib.cg_normalize_u8(ctypes.c_void_p(0x1000), ctypes.c_void_p(0x2000), 0, None) == 0          # empty input: nothing to do
+    p = ctypes.c_void_p(0x1000)
+    assert lib.cg_resize_bilinear(None, 1, 8, 8, 3, p, 4, 4, None) == -1
+    assert lib.cg_resize_bilinear(p, 1, 0, 8, 3, p, 4, 4, None) == -1 and b"geometry" in lib.cg_last_error()
+    assert lib.cg_resize_crop_flip(p, 1, 8, 8, 3, 16, 16, p, 32, 16, None, None, None, None) == -1    # crop larger than the resized image
+    assert lib.cg_resize_bilinear(p, 0, 8, 8, 3, p, 4, 4, None) == 0                                      # empty batch
+    assert lib.cg_net_state_floats(None, None) == -1
+    assert lib.cg_net_set_training(None, 1) == -1 and lib.cg_net_set_seed(None, 1) == -1
+    m = create_model(C.BN_SIMPLE)
+    assert lib.cg_net_bind_state(m.handle(), None) == -1                                                  # a BatchNormalization net needs its state
+    assert lib.cg_net_bind_state(create_model(C.SMALL_SIMPLE).handle(), None) == 0                        # an instance-norm net has none
+    assert lib.cg_net_set_training(m.handle(), 1) == 0 and lib.cg_net_set_seed(m.handle(), 2 ** 63 + 5) == 0
+    # optimizer kinds are validated when the trainer is created
+    cfg = ir.TrainCfg()
+    cfg.loss = 0
+    for i in range(4):
+        cfg.adam[i] = ir.AdamCfg(1e-3, 0.9, 0.999, 1e-7, 7)
+    nets = [create_model(C.SMALL_SIMPLE) for _ in range(4)]
+    h = ctypes.c_void_p()
+    assert lib.cg_trainer_create(*[n.handle() for n in nets], ctypes.byref(cfg), ctypes.byref(h)) == -1
+    assert b"optimizer kind" in lib.cg_last_error()
