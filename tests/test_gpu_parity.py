@@ -297,3 +297,29 @@ def test_linearity_property_of_backward():
     for i, g in enumerate(g1):
         if g.ndim == 4:
             assert C.rel_l2(g2[i], 2 * g1[i]) <= 2e-2, (i, C.rel_l2(g2[i], 2 * g1[i]))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_c3_full_size_train_step(mode):
+    """The headline configuration at its full image size (resnet_generator{filters:64} + simple_discriminator
+    [64,128,256,512], 256x256; batch 1 so that the CPU oracle finishes in seconds): the six metrics and the generated
+    images of one training step.  Every tensor-core layer kind of the C3 schedule runs at its benchmark geometry here."""
+    gan = CycleGan(C.model_config(C.RESNET64, C.SIMPLE_D4), C.train_config(), mode=mode)
+    o = OracleCycleGan(C.RESNET64, C.SIMPLE_D4, dtype=torch.float32)
+    for name in ("g_AB", "g_BA", "d_A", "d_B"):
+        getattr(gan, name).set_weights([v.detach().numpy() for v in getattr(o, name).variables])
+    a, b = synthetic_batch(1, 256)
+    ref_m, _, ref_img = o.gradients(a, b)
+    got = gan.train_step(a, b)
+    tol = TOL[mode]
+    for k in ("gAB_loss", "gBA_loss", "dA_loss", "dB_loss"):
+        # fp32 mode is compared with torch-CPU fp32 here (an fp64 oracle of this size takes too long): 5e-4 covers the
+        # oracle's own fp32 rounding through 2 x 24 conv layers
+        lim = 5e-4 if mode == "fp32" else tol
+        assert abs(float(got[k]) - ref_m[k]) <= lim * max(1.0, abs(ref_m[k])), (k, float(got[k]), ref_m[k])
+    for name in ("fake_b", "fake_a", "same_a", "same_b", "cycled_a", "cycled_b"):
+        lim = (1e-3 if mode == "fp32" else tol * (6 if name.startswith("cycled") else 2))
+        err = C.rel_l2(gan.fetch_image(name).numpy(), ref_img[name].numpy())
+        assert err <= lim, (name, err)
+    w = gan.g_AB_optimizer.get_weights()
+    assert int(w[0]) == 1
