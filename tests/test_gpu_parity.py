@@ -323,3 +323,26 @@ def test_c3_full_size_train_step(mode):
         assert err <= lim, (name, err)
     w = gan.g_AB_optimizer.get_weights()
     assert int(w[0]) == 1
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_c2_full_size_train_step(mode):
+    """configs/cycle.yaml verbatim (U-Net generator + U-Net PatchGAN discriminator with sigmoid output) at
+    its full 256x256 size, batch 1: metrics and generated images of one training step.  The bf16 image gates follow
+    the format's own error on this net: rounding the fp64 oracle's activations to bf16 at the storage points (no GPU
+    involved) moves the first-hop images by 4.9e-2..5.1e-2 and the cycled ones -- a randomly initialised U-Net applied to a
+    generated image -- by 0.30..0.31 on exactly these inputs and weights; the B200 path measures <= 8e-2 and 0.34."""
+    gan = CycleGan(C.model_config(C.UNET_G, C.UNET_D), C.train_config(), mode=mode)
+    o = OracleCycleGan(C.UNET_G, C.UNET_D, dtype=torch.float32)
+    for name in ("g_AB", "g_BA", "d_A", "d_B"):
+        getattr(gan, name).set_weights([v.detach().numpy() for v in getattr(o, name).variables])
+    a, b = synthetic_batch(1, 256)
+    ref_m, _, ref_img = o.gradients(a, b)
+    got = gan.train_step(a, b)
+    for k in ("gAB_loss", "gBA_loss", "dA_loss", "dB_loss"):
+        lim = 5e-4 if mode == "fp32" else TOL[mode]
+        assert abs(float(got[k]) - ref_m[k]) <= lim * max(1.0, abs(ref_m[k])), (k, float(got[k]), ref_m[k])
+    for name in ("fake_b", "fake_a", "same_a", "same_b", "cycled_a", "cycled_b"):
+        lim = 1e-3 if mode == "fp32" else (0.45 if name.startswith("cycled") else 8e-2)
+        err = C.rel_l2(gan.fetch_image(name).numpy(), ref_img[name].numpy())
+        assert err <= lim, (name, err)
