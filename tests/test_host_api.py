@@ -216,3 +216,24 @@ def test_new_entry_points_validate_arguments_without_a_gpu(built_lib):
     h = ctypes.c_void_p()
     assert lib.cg_trainer_create(*[n.handle() for n in nets], ctypes.byref(cfg), ctypes.byref(h)) == -1
     assert b"optimizer kind" in lib.cg_last_error()
+
+
+def test_model_weights_surface_with_batchnorm_state():
+    """keras Model.weights / get_weights / set_weights with non-trainable variables, on the host copies (no GPU)."""
+    m = create_model(C.BN_SIMPLE)
+    nt, ns = len(m.trainable_variables), len(m.non_trainable_variables)
+    assert ns == 4 and len(m.weights) == nt + ns
+    w = m.get_weights()
+    assert [a.shape for a in w[nt:]] == [(8,), (8,), (16,), (16,)]
+    assert all(np.all(a == 0) for a in w[nt::2]) and all(np.all(a == 1) for a in w[nt + 1::2])     # moving mean 0, variance 1
+    new = [a + 1 for a in w]
+    m.set_weights(new)                                      # trainable + non-trainable, Keras order
+    assert all(np.array_equal(x, y) for x, y in zip(m.get_weights(), new))
+    m.set_weights(w[:nt])                                   # trainable only: the state is left alone
+    got = m.get_weights()
+    assert all(np.array_equal(x, y) for x, y in zip(got[:nt], w[:nt]))
+    assert all(np.array_equal(x, y) for x, y in zip(got[nt:], new[nt:]))
+    m.non_trainable_variables[1].assign(np.full((8,), 3.0, np.float32))
+    assert np.all(m.non_trainable_variables[1].numpy() == 3.0) and m.non_trainable_variables[1].role == 5
+    with pytest.raises(AssertionError):
+        m.set_weights(w[:nt - 1])
