@@ -241,6 +241,11 @@ class CycleGan:
             return bytes(buf)
         raw = exchange_unique_id(make_id, dist, device="cuda")
         buf = (ctypes.c_char * 128)(*raw)
+        # every rank trains on its own shard: give it its own dropout stream too (before comm_init, which drops the
+        # captured graphs -- the seed is baked into them)
+        for n in self._nets():
+            if n.graph.has_dropout():
+                n.set_dropout_seed(n._drop_seed + 0x9E3779B9 * rank)
         _lib.check(_lib.load().cg_trainer_comm_init(self._trainer, buf, rank, world), "cg_trainer_comm_init")
         self._world = world
 
