@@ -41,6 +41,8 @@ SIGNATURES = {
                                c_int, c_int, c_int, c_int, c_void_p]),
     "cg_net_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
                                 c_void_p]),
+    "cg_net_fetch_tensor": (c_int, [c_void_p, c_int, c_void_p, ctypes.POINTER(c_int * 4), c_void_p]),
+    "cg_trainer_fetch_tensor": (c_int, [c_void_p, c_int, c_int, c_void_p, ctypes.POINTER(c_int * 4), c_void_p]),
     "cg_trainer_create": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(TrainCfg),
                                   ctypes.POINTER(c_void_p)]),
     "cg_trainer_destroy": (None, [c_void_p]),
@@ -52,6 +54,7 @@ SIGNATURES = {
     "cg_trainer_compute_gradients": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                              c_void_p]),
     "cg_trainer_apply_gradients": (c_int, [c_void_p, c_void_p]),
+    "cg_optimizer_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_i64, c_void_p]),
     "cg_trainer_get_iterations": (c_int, [c_void_p, ctypes.POINTER(c_i64 * 4)]),
     "cg_trainer_set_iterations": (c_int, [c_void_p, ctypes.POINTER(c_i64 * 4)]),
     "cg_trainer_fetch_image": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),

@@ -302,6 +302,7 @@ extern "C" int cg_net_set_seed(cg_net_t net, uint64_t seed) {
     if (!net) { cg_set_error("null argument"); return CG_ERR_INVALID; }
     net->seed = seed;
     net->calls = 0;
+    net->seed_epoch += 1;
     return CG_OK;
 }
 extern "C" int cg_net_var_count(cg_net_t net, int* n) {
@@ -393,6 +394,26 @@ extern "C" int cg_net_forward(cg_net_t net, const float* params, const float* x,
         CG_TRY(k_convert_out<float>((const float*)sc->ctx.act(tout), y, nout, st));
     }
     return CG_OK;
+}
+
+// shared by cg_net_fetch_tensor / cg_trainer_fetch_tensor: copy tensor `t` of a planned, forwarded call out as float32 NHWC
+int fetch_tensor(const CallCtx* c, int t, float* out, int* shape4, cudaStream_t st) {
+    const cg_net_s* net = c->net;
+    if (!net || t < 0 || t > net->out_tensor()) { cg_set_error("fetch_tensor: tensor id %d out of range", t); return CG_ERR_INVALID; }
+    if (shape4) { shape4[0] = c->N; shape4[1] = c->th.empty() ? 0 : c->th[t]; shape4[2] = c->tw.empty() ? 0 : c->tw[t]; shape4[3] = net->chan[t]; }
+    const bool live = c->forwarded && t < (int)c->live.size() && c->live[t] && (t == 0 || net->has_buffer[t]);
+    if (!out) return live ? CG_OK : 1;            // query form: 0 = materialised by the last forward, 1 = not (fused away)
+    if (!live) { cg_set_error("fetch_tensor: tensor %d was not materialised by the last forward", t); return CG_ERR_STATE; }
+    const size_t n = (size_t)c->N * c->sample_elems(t);
+    if (net->mode == CG_MODE_BF16) return k_convert_out<bf16>((const bf16*)c->act(t), out, n, st);
+    return k_convert_out<float>((const float*)c->act(t), out, n, st);
+}
+
+extern "C" int cg_net_fetch_tensor(cg_net_t net, int tensor, float* out, int shape4[4], void* stream) {
+    if (!net) { cg_set_error("null argument"); return CG_ERR_INVALID; }
+    SingleCall* sc = single_of(net);
+    if (!sc->ctx.forwarded) { cg_set_error("cg_net_fetch_tensor: no cg_net_forward on this net yet"); return CG_ERR_STATE; }
+    return fetch_tensor(&sc->ctx, tensor, out, shape4, (cudaStream_t)stream);
 }
 
 extern "C" int cg_net_backward(cg_net_t net, const float* params, const float* dy, float* dx, float* grads,

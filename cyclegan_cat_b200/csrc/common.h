@@ -58,6 +58,15 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
 }
 #endif
 
+// cudaFuncSetAttribute is per device: `if (cg_first_on_device(mask)) { set attributes }` runs its body once per device
+// (and per kernel / template instantiation: each call site owns its `static std::atomic<unsigned long long> mask{0}`)
+static inline bool cg_first_on_device(std::atomic<unsigned long long>& mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    return !(mask.load(std::memory_order_acquire) & bit) && !(mask.fetch_or(bit, std::memory_order_acq_rel) & bit);
+}
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -123,6 +132,16 @@ __device__ __forceinline__ float act_fwd(float x, int act, float slope) {
         default: return x;
     }
 }
+// Normalisation as every forward kernel evaluates it: pre = fma(v, sc, sh) with sc = rstd*gamma, sh = fma(-mean, sc, beta),
+// all three roundings explicit.  Every backward kernel derives its activation mask from the SAME expression, so the
+// gradient is the gradient of exactly the function the forward pass computed (no unit near zero can be "on" forward
+// and "off" backward), and the parity tests can take the masks from the stored forward outputs.
+__device__ __forceinline__ void in_scale_shift(float mean, float rstd, float ga, float be, float& sc, float& sh) {
+    sc = __fmul_rn(rstd, ga);
+    sh = __fmaf_rn(-mean, sc, be);
+}
+__device__ __forceinline__ float in_pre(float v, float sc, float sh) { return __fmaf_rn(v, sc, sh); }
+
 // derivative expressed through the activation OUTPUT y (all four are invertible enough for that)
 __device__ __forceinline__ float act_grad_from_out(float y, int act, float slope) {
     switch (act) {

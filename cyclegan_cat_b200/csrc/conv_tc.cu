@@ -1069,10 +1069,9 @@ int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, const CUten
         a.stages = s2 > 8 ? 8 : s2;
         a.idesc = make_idesc(256, a.bn, 0, 0);
         const size_t smem = (size_t)a.stages * stage + 1024 + 256;
-        static bool attr2 = false;
-        if (!attr2) {
+        static std::atomic<unsigned long long> attr2{0};
+        if (cg_first_on_device(attr2)) {
             CG_CUDA(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr2 = true;
         }
         const int total_pairs = (a.nb * a.tiles_per_img / 2) * a.n_blocks_n;
         int clusters = num_sms() / 2;
@@ -1091,13 +1090,12 @@ int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, const CUten
     }
     a.idesc = make_idesc(128, a.bn, 0, 0);
     const size_t smem = (size_t)a.stages * stage_b + 1024 + 256 + (dual ? EPI_SCRATCH / 2 : EPI_SCRATCH);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_set{0};
+    if (cg_first_on_device(attr_set)) {
         CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        attr_set = true;
     }
     const int total = a.nb * a.tiles_per_img * a.n_blocks_n;
     const int slots = (dual ? 2 : 1) * num_sms();
@@ -1131,10 +1129,9 @@ int tc_wgrad_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* dw
     if (splits > total_chunks) splits = total_chunks;
     a.splits = splits;
     const size_t smem = (size_t)a.stages * stage + 1024 + 256;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_set{0};
+    if (cg_first_on_device(attr_set)) {
         CG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
     }
     int pi = prof_begin(st);
     launch_pdl(wgrad_tc_kernel, dim3(units * splits), dim3(TC_THREADS), smem, st, *mapX, *mapDY, dw, a);
@@ -1157,10 +1154,9 @@ int tc_wgrad16_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* 
     if (splits > total_chunks) splits = total_chunks;
     a.splits = splits;
     const size_t smem = (size_t)a.stages * stage + 1024 + 256;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_set{0};
+    if (cg_first_on_device(attr_set)) {
         CG_CUDA(cudaFuncSetAttribute(wgrad16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
     }
     int pi = prof_begin(st);
     launch_pdl(wgrad16_tc_kernel, dim3(a.m_blocks * splits), dim3(TC_THREADS), smem, st, *mapX, *mapDY, dw, a);

@@ -460,10 +460,9 @@ template <typename T> int k_conv_fwd(const T* x, const float* w, const float* bi
         const int nv = g.Cin % VW == 0 ? g.Cin / VW : 0;
         const size_t tile_bytes = (size_t)(8 * PX + g.k - 1) * (32 + g.k - 1) * g.Cin * sizeof(T);
         if (g.Cout <= 4 && g.s == 1 && g.k >= 3 && nv >= 1 && (nv & (nv - 1)) == 0 && wbytes + tile_bytes <= 200 * 1024) {
-            static bool attr_t = false;
-            if (!attr_t) {
+            static std::atomic<unsigned long long> attr_t{0};
+            if (cg_first_on_device(attr_t)) {
                 CG_CUDA(cudaFuncSetAttribute(conv_fwd_skinny_tiled<T, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                attr_t = true;
             }
             const int tiles_w = cdiv(g.Wo, 32), tiles_h = cdiv(g.Ho, 8 * PX);
             conv_fwd_skinny_tiled<T, PX><<<g.N * tiles_w * tiles_h, 256, wbytes + tile_bytes, st>>>(x, w, bias, y, g, accumulate,
@@ -473,11 +472,10 @@ template <typename T> int k_conv_fwd(const T* x, const float* w, const float* bi
         }
     }
     if (g.Cout <= 4 && wbytes <= 96 * 1024) {
-        static bool attr_done = false;
-        if (!attr_done) {
+        static std::atomic<unsigned long long> attr_done{0};
+        if (cg_first_on_device(attr_done)) {
             CG_CUDA(cudaFuncSetAttribute(conv_fwd_skinny<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             CG_CUDA(cudaFuncSetAttribute(conv_fwd_skinny<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            attr_done = true;
         }
         long long work = (long long)g.N * g.Ho * ((g.Wo + 1) / 2);
         int blocks = (int)((work + 127) / 128 < 148 * 16 ? (work + 127) / 128 : 148 * 16);
@@ -605,11 +603,10 @@ template <typename T> int k_conv_dgrad(const T* dy, const float* w, const float*
                                        int accumulate, cudaStream_t st) {
     const size_t wbytes = (size_t)g.k * g.k * g.Cout * sizeof(float4);
     if (g.Cin <= 4 && wbytes <= 96 * 1024) {
-        static bool attr_done = false;
-        if (!attr_done) {
+        static std::atomic<unsigned long long> attr_done{0};
+        if (cg_first_on_device(attr_done)) {
             CG_CUDA(cudaFuncSetAttribute(conv_dgrad_skinny<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             CG_CUDA(cudaFuncSetAttribute(conv_dgrad_skinny<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            attr_done = true;
         }
         long long work = (long long)g.N * g.Hi * g.Wi;
         int blocks = (int)((work + 127) / 128 < 148 * 16 ? (work + 127) / 128 : 148 * 16);

@@ -58,6 +58,9 @@ __global__ void __launch_bounds__(256) in_reduce_kernel(const T* __restrict__ x,
             rstd = stats[((size_t)n * C + c) * 2 + 1];
             if (gamma) { ga = gamma[c]; be = beta[c]; }
         }
+        float sc, sh, xsc, xsh;
+        in_scale_shift(mean, rstd, ga, be, sc, sh);
+        in_scale_shift(mean, rstd, 1.f, 0.f, xsc, xsh);
         int p = p0 + warp;
         for (; p + 24 < p1; p += 32) {      // 4 independent pixels in flight per lane
             float v[4], gy[4];
@@ -70,8 +73,8 @@ __global__ void __launch_bounds__(256) in_reduce_kernel(const T* __restrict__ x,
             for (int u = 0; u < 4; ++u) {
                 if (MODE == 0) { s += v[u]; ss += v[u] * v[u]; }
                 else {
-                    float xh = (v[u] - mean) * rstd;
-                    float g = gy[u] * act_grad_from_out(xh * ga + be, act, slope);
+                    float xh = in_pre(v[u], xsc, xsh);
+                    float g = gy[u] * act_grad_from_out(in_pre(v[u], sc, sh), act, slope);
                     s += g;
                     ss += g * xh;
                 }
@@ -83,8 +86,8 @@ __global__ void __launch_bounds__(256) in_reduce_kernel(const T* __restrict__ x,
                 s += v;
                 ss += v * v;
             } else {
-                float xh = (v - mean) * rstd;
-                float g = ldf(dy + base + (size_t)p * C) * act_grad_from_out(xh * ga + be, act, slope);
+                float xh = in_pre(v, xsc, xsh);
+                float g = ldf(dy + base + (size_t)p * C) * act_grad_from_out(in_pre(v, sc, sh), act, slope);
                 s += g;
                 ss += g * xh;
             }
@@ -162,8 +165,9 @@ __global__ void in_apply_kernel(const T* __restrict__ x, T* __restrict__ y, cons
         for (int j = 0; j < VEC; ++j) {
             float mean = st[(c + j) * 2], rstd = st[(c + j) * 2 + 1];
             float ga = gamma ? gamma[c + j] : 1.f, be = beta ? beta[c + j] : 0.f;
-            float inv = rstd * ga;
-            v[j] = act_fwd(v[j] * inv + (be - mean * inv), act, slope);
+            float sc, sh;
+            in_scale_shift(mean, rstd, ga, be, sc, sh);
+            v[j] = act_fwd(in_pre(v[j], sc, sh), act, slope);
         }
         store_vec<T, VEC>(y + base + e, v);
     }
@@ -190,8 +194,7 @@ __global__ void __launch_bounds__(256) in_apply_fast_kernel(const T* __restrict_
         const int c = cv * VEC + j;
         const float mean = stats[((size_t)n * C + c) * 2], rstd = stats[((size_t)n * C + c) * 2 + 1];
         const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
-        sc[j] = rstd * ga;
-        sh[j] = be - mean * sc[j];
+        in_scale_shift(mean, rstd, ga, be, sc[j], sh[j]);
     }
     const size_t base = (size_t)n * P * C + (size_t)cv * VEC;
     const int stride = gridDim.x * ppb;
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(256) in_apply_fast_kernel(const T* __restrict_
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) v[u][j] = act_fwd(fmaf(v[u][j], sc[j], sh[j]), act, slope);
+            for (int j = 0; j < VEC; ++j) v[u][j] = act_fwd(in_pre(v[u][j], sc[j], sh[j]), act, slope);
             store_vec<T, VEC>(y + base + (size_t)(p + u * stride) * C, v[u]);
         }
     }
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(256) in_apply_fast_kernel(const T* __restrict_
         float v[VEC];
         load_vec<T, VEC>(x + base + (size_t)p * C, v);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) v[j] = act_fwd(fmaf(v[j], sc[j], sh[j]), act, slope);
+        for (int j = 0; j < VEC; ++j) v[j] = act_fwd(in_pre(v[j], sc[j], sh[j]), act, slope);
         store_vec<T, VEC>(y + base + (size_t)p * C, v);
     }
 }
@@ -235,12 +238,11 @@ __global__ void __launch_bounds__(256, AFFINE ? 2 : 4) in_bwd_apply_fast_kernel(
         const int c = cv * VEC + j;
         const float mean = stats[((size_t)n * C + c) * 2], rstd = stats[((size_t)n * C + c) * 2 + 1];
         const float ga = AFFINE ? gamma[c] : 1.f;
-        ca[j] = rstd;
-        cb[j] = -mean * rstd;
+        in_scale_shift(mean, rstd, 1.f, 0.f, ca[j], cb[j]);
         ck[j] = rstd * ga;
         c1[j] = ck[j] * sums[((size_t)n * C + c) * 2] * invP;
         c2[j] = ck[j] * sums[((size_t)n * C + c) * 2 + 1] * invP;
-        if (AFFINE) { cg[j] = ga; ce[j] = beta[c]; }
+        if (AFFINE) in_scale_shift(mean, rstd, ga, beta[c], cg[j], ce[j]);
     }
     const int Hp = H + 2 * halo, Wp = W + 2 * halo;
     const int PP = Hp * Wp;
@@ -258,8 +260,8 @@ __global__ void __launch_bounds__(256, AFFINE ? 2 : 4) in_bwd_apply_fast_kernel(
             if (accumulate) load_vec<T, VEC>(dx + out_base + (size_t)pp * C, o);
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
-                const float xh = fmaf(v[j], ca[j], cb[j]);
-                const float pre = AFFINE ? fmaf(xh, cg[j], ce[j]) : xh;
+                const float xh = in_pre(v[j], ca[j], cb[j]);
+                const float pre = AFFINE ? in_pre(v[j], cg[j], ce[j]) : xh;
                 const float gg = g[j] * act_grad_from_out(pre, act, slope);
                 const float r = fmaf(ck[j], gg, -fmaf(xh, c2[j], c1[j]));
                 o[j] = accumulate ? o[j] + r : r;
@@ -326,8 +328,11 @@ __global__ void in_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
         for (int j = 0; j < VEC; ++j) {
             float mean = st[(c + j) * 2], rstd = st[(c + j) * 2 + 1];
             float ga = gamma ? gamma[c + j] : 1.f, be = beta ? beta[c + j] : 0.f;
-            float xh = (v[j] - mean) * rstd;
-            float gg = g[j] * act_grad_from_out(xh * ga + be, act, slope);
+            float sc, sh, xsc, xsh;
+            in_scale_shift(mean, rstd, ga, be, sc, sh);
+            in_scale_shift(mean, rstd, 1.f, 0.f, xsc, xsh);
+            float xh = in_pre(v[j], xsc, xsh);
+            float gg = g[j] * act_grad_from_out(in_pre(v[j], sc, sh), act, slope);
             float r = rstd * ga * (gg - sm[(c + j) * 2] * invP - xh * sm[(c + j) * 2 + 1] * invP);
             o[j] = accumulate ? o[j] + r : r;
         }
@@ -362,8 +367,11 @@ __global__ void in_bwd_apply_halo_kernel(const T* __restrict__ x, const T* __res
             for (int j = 0; j < VEC; ++j) {
                 float mean = st[(c + j) * 2], rstd = st[(c + j) * 2 + 1];
                 float ga = gamma ? gamma[c + j] : 1.f, be = beta ? beta[c + j] : 0.f;
-                float xh = (v[j] - mean) * rstd;
-                float gg = g[j] * act_grad_from_out(xh * ga + be, act, slope);
+                float sc, sh, xsc, xsh;
+                in_scale_shift(mean, rstd, ga, be, sc, sh);
+                in_scale_shift(mean, rstd, 1.f, 0.f, xsc, xsh);
+                float xh = in_pre(v[j], xsc, xsh);
+                float gg = g[j] * act_grad_from_out(in_pre(v[j], sc, sh), act, slope);
                 o[j] = rstd * ga * (gg - sm[(c + j) * 2] * invP - xh * sm[(c + j) * 2 + 1] * invP);
             }
         } else {

@@ -108,12 +108,12 @@ __global__ void __launch_bounds__(ST_THREADS, (MODE == 0 || MODE == 4) ? 3 : 2) 
         const float mean = a.stats[((size_t)n * C + c) * 2], rstd = a.stats[((size_t)n * C + c) * 2 + 1];
         const float ga = AFFINE ? a.gamma[c] : 1.f, be = AFFINE ? a.beta[c] : 0.f;
         if constexpr (FWD) {
-            k0[j] = rstd * ga;                     // y = act(v*k0 + k1)
-            k1[j] = be - mean * k0[j];
+            in_scale_shift(mean, rstd, ga, be, k0[j], k1[j]);      // y = act(v*k0 + k1)
         } else {
-            k0[j] = rstd;                          // xhat = v*k0 + k1
-            k1[j] = -mean * rstd;
-            if constexpr (AFFINE) { kg[j] = ga; ke[j] = be; }
+            in_scale_shift(mean, rstd, 1.f, 0.f, k0[j], k1[j]);     // xhat = v*k0 + k1 (= the forward's pre-activation when not affine)
+            // the activation mask is taken from the pre-activation computed EXACTLY as the forward pass computes it
+            // (fmaf(v, rstd*gamma, beta - mean*rstd*gamma)): forward and backward then agree on every unit, bit for bit
+            if constexpr (AFFINE) in_scale_shift(mean, rstd, ga, be, kg[j], ke[j]);
             if constexpr (MODE == 2) {
                 k2[j] = rstd * ga;                 // r = k2*g - (xhat*k4 + k3)
                 k3[j] = k2[j] * a.sums_in[((size_t)n * C + c) * 2] * a.invP;
@@ -169,13 +169,13 @@ __global__ void __launch_bounds__(ST_THREADS, (MODE == 0 || MODE == 4) ? 3 : 2) 
                 // instruction-bound: ~170 warp instructions per 16-byte vector before this)
                 if (a.act == CG_ACT_RELU) {
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) v[u][j] = fmaxf(fmaf(v[u][j], k0[j], k1[j]), 0.f);
+                    for (int j = 0; j < VEC; ++j) v[u][j] = fmaxf(in_pre(v[u][j], k0[j], k1[j]), 0.f);
                 } else if (a.act == CG_ACT_NONE) {
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) v[u][j] = fmaf(v[u][j], k0[j], k1[j]);
+                    for (int j = 0; j < VEC; ++j) v[u][j] = in_pre(v[u][j], k0[j], k1[j]);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) v[u][j] = act_fwd(fmaf(v[u][j], k0[j], k1[j]), a.act, a.slope);
+                    for (int j = 0; j < VEC; ++j) v[u][j] = act_fwd(in_pre(v[u][j], k0[j], k1[j]), a.act, a.slope);
                 }
                 if constexpr (MODE == 3) {
 #pragma unroll
@@ -200,9 +200,9 @@ __global__ void __launch_bounds__(ST_THREADS, (MODE == 0 || MODE == 4) ? 3 : 2) 
                 float o[VEC];
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) {
-                    const float xh = fmaf(v[u][j], k0[j], k1[j]);
+                    const float xh = in_pre(v[u][j], k0[j], k1[j]);
                     float pre = xh;
-                    if constexpr (AFFINE) pre = fmaf(xh, kg[j], ke[j]);
+                    if constexpr (AFFINE) pre = in_pre(v[u][j], kg[j], ke[j]);
                     const float gg = g[u][j] * act_grad_from_out(pre, a.act, a.slope);
                     if constexpr (MODE == 1) {
                         acc_s[j] += gg;
@@ -286,10 +286,9 @@ int launch_stream(StreamArgs<T>& a, int N, cudaStream_t st) {
         if (smem < red) smem = red;
     }
     auto kern = in_stream_kernel<T, VW, MODE, AFFINE>;
-    static bool attr_done = false;                  // one flag per template instantiation
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{0};                  // one flag per template instantiation
+    if (cg_first_on_device(attr_done)) {
         CG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(6 * 2 * ST_TILE + 1024)));
-        attr_done = true;
     }
     const int per_sm = (MODE == 0 || MODE == 4) ? 3 : 2;      // one-operand modes: 64 KB of ring and <= 75 registers -> 3 CTAs per SM
     int G = (per_sm * 148) / N;                      // all CTAs resident at once, no second wave

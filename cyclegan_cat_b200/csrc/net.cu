@@ -631,6 +631,8 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
     const cg_net_s* net = c->net;
     const int N = c->N;
     std::vector<char> stats_done(net->layers.size() + 1, 0), fused_done(net->layers.size() + 1, 0);
+    c->live.assign(net->layers.size() + 1, 0);
+    c->live[0] = 1;
     // every statistics table of this call is zeroed by ONE memset (they are accumulated into by atomics)
     if (c->act_bytes > c->stat_begin) CG_CUDA(cudaMemsetAsync(c->base + c->stat_begin, 0, c->act_bytes - c->stat_begin, st));
     for (size_t i = 0; i < net->layers.size(); ++i) {
@@ -731,6 +733,7 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
                         CG_TRY(k_in_apply_stream<T>(x, nullptr, nullptr, yp, stats, gam, bet, L.fused_act, L.fused_slope, N, h * w,
                                                     d.cin, w, R.d.pad, st));
                         fused_done[L.fuse_rpad] = 1;
+                        c->live[R.out_t] = 1;
                         break;
                     }
                 }
@@ -749,23 +752,28 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
                         CG_TRY(k_in_apply_stream<T>(x, res, ys, yp, stats, gam, bet, L.fused_act, L.fused_slope, N, h * w, d.cin, w,
                                                     pad, st));
                         fused_done[L.fuse_add] = 1;
-                        if (yp) fused_done[Ad.fuse_rpad] = 1;
+                        c->live[Ad.out_t] = 1;
+                        if (yp) { fused_done[Ad.fuse_rpad] = 1; c->live[net->layers[Ad.fuse_rpad].out_t] = 1; }
                         break;
                     }
                 }
                 CG_TRY(k_in_apply<T>(x, y, stats, L.g_off >= 0 ? params + L.g_off : nullptr,
                                      L.be_off >= 0 ? params + L.be_off : nullptr, L.fused_act, L.fused_slope, N,
                                      h * w, d.cin, st));
+                c->live[tout] = 1;
                 break;
             }
             case CG_OP_ACT:
                 CG_TRY(k_act_fwd<T>(x, y, (size_t)N * c->sample_elems(tin), d.act, d.slope, st));
                 break;
             case CG_OP_RPAD:
-                if (!fused_done[i]) CG_TRY(k_rpad_fwd<T>(x, y, N, h, w, d.cin, d.pad, st));
+                if (!fused_done[i]) { CG_TRY(k_rpad_fwd<T>(x, y, N, h, w, d.cin, d.pad, st)); c->live[tout] = 1; }
                 break;
             case CG_OP_ADD:
-                if (!fused_done[i]) CG_TRY(k_add<T>(x, (const T*)c->act(d.in1), y, (size_t)N * c->sample_elems(tin), st));
+                if (!fused_done[i]) {
+                    CG_TRY(k_add<T>(x, (const T*)c->act(d.in1), y, (size_t)N * c->sample_elems(tin), st));
+                    c->live[tout] = 1;
+                }
                 break;
             case CG_OP_CONCAT: {
                 int ca = net->chan[d.in0], cb = net->chan[d.in1];
@@ -784,6 +792,7 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
             }
             default: cg_set_error("unknown op %d", d.op); return CG_ERR_INVALID;
         }
+        if (d.op != CG_OP_INORM && d.op != CG_OP_RPAD && d.op != CG_OP_ADD) c->live[tout] = 1;
     }
     c->forwarded = true;
     return CG_OK;

@@ -56,6 +56,7 @@ struct cg_net_s {
     float* state = nullptr;             // caller-owned device buffer of n_state floats (cg_net_bind_state)
     int training = 0;                   // Keras `training=` of the next single-net forward (cg_net_set_training)
     unsigned long long seed = 0;        // dropout stream (cg_net_set_seed)
+    unsigned long long seed_epoch = 0;  // bumped by every cg_net_set_seed: a trainer whose captured graphs baked the old seed in re-captures
     unsigned long long calls = 0;       // training-mode single-net forwards so far (dropout counter)
     size_t packed_bytes = 0;            // bf16 weight copies for the tensor-core layers
     int out_tensor() const { return (int)layers.size(); }
@@ -95,6 +96,7 @@ struct CallCtx {
     const unsigned long long* drop_ctr_dev = nullptr;
     int call_id[4] = {0, 1, 2, 3};      // dropout: id of each group's Keras call within the step
     std::vector<int> grad_halo;         // per tensor: zero border of the gradient buffer (tensor-core layers)
+    std::vector<char> live;             // per tensor: the last forward materialised it (fused layers skip their own output)
 
     size_t sample_elems(int t) const { return (size_t)th[t] * tw[t] * net->chan[t]; }
     void* act(int t) const { return (t == 0 && ext_input) ? ext_input : (void*)(base + act_off[t]); }

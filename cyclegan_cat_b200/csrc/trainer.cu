@@ -69,6 +69,7 @@ struct cg_trainer_s {
     char* ws = nullptr; size_t ws_bytes = 0;
     long long iters[4] = {0, 0, 0, 0};
     unsigned long long train_calls = 0;         // training-mode steps so far: the dropout counter of the next one
+    unsigned long long seed_epoch[4] = {0, 0, 0, 0};   // cg_net_set_seed generation each net had when the graphs were captured
     size_t o_ctr = 0;                           // device copy of that counter (read by the dropout kernels, also in graph replays)
     // planned shape
     int B = 0, H = 0, W = 0; bool planned = false;
@@ -395,6 +396,18 @@ static int step_T(cg_trainer_t tr, const float* real_a, const float* real_b, int
                   bool train, cudaStream_t st) {
     if (!tr->ws) { cg_set_error("trainer has no bound buffers (cg_trainer_bind)"); return CG_ERR_STATE; }
     if (!tr->planned || tr->B != B || tr->H != H || tr->W != W) CG_TRY(trainer_layout(tr, B, H, W, true));
+    // a re-seeded net (cg_net_set_seed): the dropout key is a kernel argument baked into the captured graphs -> drop them and
+    // restart the step counter, exactly like the single-net path restarts its call counter
+    for (int i = 0; i < 4; ++i)
+        if (tr->seed_epoch[i] != tr->net[i]->seed_epoch) {
+            for (int g = 0; g < 2; ++g) {
+                if (tr->graph_exec[g]) { cudaGraphExecDestroy(tr->graph_exec[g]); tr->graph_exec[g] = nullptr; }
+                tr->graph_seen[g] = 0;
+            }
+            tr->train_calls = 0;
+            for (int j = 0; j < 4; ++j) tr->seed_epoch[j] = tr->net[j]->seed_epoch;
+            break;
+        }
     // ---- inputs: Xab = [a; b], Xba = [b; a] (the only part that touches caller pointers) ------
     const size_t img = (size_t)H * W * 3;
     T* Xab = (T*)tr->F1.act(0);
@@ -474,32 +487,47 @@ extern "C" int cg_trainer_compute_gradients(cg_trainer_t tr, const float* a, con
     return step(tr, a, b, B, H, W, metrics, true, stream);
 }
 
+// one optimizer.apply_gradients over a flat range: `iterations` is optimizer.iterations BEFORE the step
+static int opt_apply(const cg_adam_cfg& a, float* p, const float* g, float* m, float* v, size_t n, long long iterations,
+                     float gscale, cudaStream_t st) {
+    const double t = (double)(iterations + 1);
+    if (n == 0) return CG_OK;
+    if (a.kind == CG_OPT_ADAM) {
+        const double lr_t = (double)a.learning_rate * sqrt(1.0 - pow((double)a.beta_2, t)) / (1.0 - pow((double)a.beta_1, t));
+        return k_adam(p, g, m, v, n, (float)lr_t, a.beta_1, a.beta_2, a.epsilon, gscale, st);
+    }
+    OptCoef c;
+    memset(&c, 0, sizeof(c));
+    c.lr = a.learning_rate; c.b1 = a.beta_1; c.b2 = a.beta_2; c.eps = a.epsilon; c.gscale = gscale;
+    if (a.kind == CG_OPT_ADABELIEF) {       // adabelief_tf: bias corrections and the RAdam rectification term
+        const double b1p = pow((double)a.beta_1, t), b2p = pow((double)a.beta_2, t);
+        const double sma_inf = 2.0 / (1.0 - (double)a.beta_2) - 1.0;
+        const double sma_t = sma_inf - 2.0 * t * b2p / (1.0 - b2p);
+        c.c_m = (float)(1.0 / (1.0 - b1p));
+        c.c_v = (float)(1.0 / (1.0 - b2p));
+        c.rect = sma_t >= 5.0 ? 1 : 0;      // sma_threshold default
+        c.r_t = c.rect ? (float)sqrt((sma_t - 4.0) / (sma_inf - 4.0) * (sma_t - 2.0) / (sma_inf - 2.0) * sma_inf / sma_t) : 0.f;
+    }
+    return k_opt_step(a.kind, p, g, m, v, n, c, st);
+}
+
+extern "C" int cg_optimizer_apply(const cg_adam_cfg* cfg, float* params, const float* grads, float* slot_m, float* slot_v,
+                                  size_t n, int64_t iterations, void* stream) {
+    if (!cfg || !params || !grads) { cg_set_error("cg_optimizer_apply: null argument"); return CG_ERR_INVALID; }
+    if (cfg->kind < CG_OPT_ADAM || cfg->kind > CG_OPT_ADABELIEF) { cg_set_error("unknown optimizer kind %d", cfg->kind); return CG_ERR_INVALID; }
+    const bool need_m = cfg->kind == CG_OPT_ADAM || cfg->kind == CG_OPT_ADABELIEF, need_v = cfg->kind != CG_OPT_SGD;
+    if ((need_m && !slot_m) || (need_v && !slot_v)) { cg_set_error("cg_optimizer_apply: missing slot buffer for optimizer kind %d", cfg->kind); return CG_ERR_INVALID; }
+    if (iterations < 0) { cg_set_error("cg_optimizer_apply: negative iteration count"); return CG_ERR_INVALID; }
+    return opt_apply(*cfg, params, grads, slot_m, slot_v, n, iterations, 1.f, (cudaStream_t)stream);
+}
+
 extern "C" int cg_trainer_apply_gradients(cg_trainer_t tr, void* stream) {
     if (!tr || !tr->ws) { cg_set_error("trainer not bound"); return CG_ERR_STATE; }
     cudaStream_t st = (cudaStream_t)stream;
     const float gscale = 1.f / (float)tr->world;        // data parallel: mean of the per-rank mean gradients
     for (int i = 0; i < 4; ++i) {
-        const cg_adam_cfg& a = tr->cfg.adam[i];
-        const double t = (double)(tr->iters[i] + 1);
-        const size_t n = (size_t)tr->net[i]->n_params;
-        if (a.kind == CG_OPT_ADAM) {
-            const double lr_t = (double)a.learning_rate * sqrt(1.0 - pow((double)a.beta_2, t)) / (1.0 - pow((double)a.beta_1, t));
-            CG_TRY(k_adam(tr->params[i], tr->grads[i], tr->m[i], tr->v[i], n, (float)lr_t, a.beta_1, a.beta_2, a.epsilon, gscale, st));
-        } else {
-            OptCoef c;
-            memset(&c, 0, sizeof(c));
-            c.lr = a.learning_rate; c.b1 = a.beta_1; c.b2 = a.beta_2; c.eps = a.epsilon; c.gscale = gscale;
-            if (a.kind == CG_OPT_ADABELIEF) {       // adabelief_tf: bias corrections and the RAdam rectification term
-                const double b1p = pow((double)a.beta_1, t), b2p = pow((double)a.beta_2, t);
-                const double sma_inf = 2.0 / (1.0 - (double)a.beta_2) - 1.0;
-                const double sma_t = sma_inf - 2.0 * t * b2p / (1.0 - b2p);
-                c.c_m = (float)(1.0 / (1.0 - b1p));
-                c.c_v = (float)(1.0 / (1.0 - b2p));
-                c.rect = sma_t >= 5.0 ? 1 : 0;      // sma_threshold default
-                c.r_t = c.rect ? (float)sqrt((sma_t - 4.0) / (sma_inf - 4.0) * (sma_t - 2.0) / (sma_inf - 2.0) * sma_inf / sma_t) : 0.f;
-            }
-            CG_TRY(k_opt_step(a.kind, tr->params[i], tr->grads[i], tr->m[i], tr->v[i], n, c, st));
-        }
+        CG_TRY(opt_apply(tr->cfg.adam[i], tr->params[i], tr->grads[i], tr->m[i], tr->v[i], (size_t)tr->net[i]->n_params,
+                         tr->iters[i], gscale, st));
         tr->iters[i] += 1;
     }
     return CG_OK;
@@ -538,6 +566,13 @@ extern "C" int cg_trainer_fetch_image(cg_trainer_t tr, int which, float* out, vo
     }
     if (tr->net[0]->mode == CG_MODE_BF16) return k_convert_out<bf16>((const bf16*)src + off, out, n, st);
     return k_convert_out<float>((const float*)src + off, out, n, st);
+}
+
+int fetch_tensor(const CallCtx* c, int t, float* out, int* shape4, cudaStream_t st);     // api.cu
+extern "C" int cg_trainer_fetch_tensor(cg_trainer_t tr, int call, int tensor, float* out, int shape4[4], void* stream) {
+    if (!tr || !tr->planned || call < 0 || call > 5) { cg_set_error("fetch_tensor: bad argument / no step yet"); return CG_ERR_INVALID; }
+    const CallCtx* cs[6] = {&tr->F1, &tr->F2, &tr->C1, &tr->C2, &tr->DA, &tr->DB};
+    return fetch_tensor(cs[call], tensor, out, shape4, (cudaStream_t)stream);
 }
 
 // ---- data parallel ---------------------------------------------------------------------------

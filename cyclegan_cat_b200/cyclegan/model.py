@@ -45,52 +45,86 @@ def accuracy(real, fake):
     return np.float32((predictions == labels).astype(np.float32).mean())
 
 
+class _MetricBuf:
+    """The metric vector one step wrote to device memory, copied to the host at most once and only when someone looks."""
+
+    def __init__(self, dev):
+        self.dev, self.host = dev, None
+
+    def get(self):
+        if self.host is None:
+            self.host = self.dev.cpu().numpy()
+            self.dev = None
+        return self.host
+
+    @staticmethod
+    def fetch_many(bufs):
+        """One synchronisation and one device-to-host copy for any number of pending steps."""
+        todo = [b for b in {id(b): b for b in bufs}.values() if b.host is None]
+        if len(todo) == 1:
+            todo[0].get()
+        elif todo:
+            import torch
+            host = torch.stack([b.dev for b in todo]).cpu().numpy()
+            for b, h in zip(todo, host):
+                b.host, b.dev = h, None
+
+
 class Scalar:
     """A metric living in device memory; `.numpy()` / float() sync lazily (the reference syncs every
     step at model.py:301 -- this does not, until someone looks)."""
 
     def __init__(self, buf, i):
-        self._buf, self._i = buf, i
+        self._buf, self._i = buf if isinstance(buf, _MetricBuf) else _MetricBuf(buf), i
 
     def numpy(self):
-        return np.float32(self._buf[self._i].item())
+        return np.float32(self._buf.get()[self._i])
 
     def __float__(self):
-        return float(self._buf[self._i].item())
+        return float(self._buf.get()[self._i])
 
     def __repr__(self):
         return f"Scalar({float(self):.6g})"
 
 
 class Mean:
-    """keras.metrics.Mean stand-in (model.py:166-183)."""
+    """keras.metrics.Mean stand-in (model.py:166-183).  `update_state` with a device `Scalar` only queues it: nothing
+    is read back until `result()` (the reference's `display_metrics` forces a device->host sync every step, model.py:301;
+    here the steps of one progress-bar refresh are fetched together)."""
 
     def __init__(self, name=None):
-        self.name, self.total, self.count = name, 0.0, 0
+        self.name, self.total, self.count, self._pending = name, 0.0, 0, []
 
     def update_state(self, v):
-        self.total += float(v)
+        if isinstance(v, Scalar):
+            self._pending.append(v)
+        else:
+            self.total += float(v)
         self.count += 1
 
     def result(self):
+        if self._pending:
+            _MetricBuf.fetch_many([s._buf for s in self._pending])
+            self.total += float(sum(float(s) for s in self._pending))
+            self._pending = []
         return np.float32(self.total / max(self.count, 1))
 
     def reset_states(self):
-        self.total, self.count = 0.0, 0
+        self.total, self.count, self._pending = 0.0, 0, []
 
 
 class CycleGan:
     def __init__(self, model_config: Bunch, train_config: Bunch = None, mode: str = "bf16",
-                 summaries: bool = False):
+                 summaries: bool = True, display_interval: float = 0.5):
         self.model_config = model_config
         self.mode = mode
         self.model_folder = join(self.model_config.location, self.model_config.name)
+        # model.py:62-66: the reference always creates the two TensorBoard writers; here they are created on first use
+        # (torch's SummaryWriter), so a CycleGan that never calls train() leaves no event files behind
         self._summaries = summaries
-        self.train_summaries = self.val_summaries = None
-        if summaries:                                   # model.py:62-66 (TensorBoard via torch's writer)
-            from torch.utils.tensorboard import SummaryWriter
-            self.train_summaries = SummaryWriter(join(self.model_folder, "train"))
-            self.val_summaries = SummaryWriter(join(self.model_folder, "validation"))
+        self._writers = {}
+        self.display_interval = display_interval        # seconds between progress-bar metric refreshes (each one syncs)
+        self._last_display = 0.0
         self.train_config = train_config
         self.g_AB_optimizer = get_optimizer(self.train_config.g_opt)      # model.py:68-71
         self.g_BA_optimizer = get_optimizer(self.train_config.g_opt)
@@ -106,6 +140,22 @@ class CycleGan:
             self.model_config.new = False
         else:
             self.load_model()
+
+    def _writer(self, kind):
+        if not self._summaries:
+            return None
+        if kind not in self._writers:
+            from torch.utils.tensorboard import SummaryWriter
+            self._writers[kind] = SummaryWriter(join(self.model_folder, kind))
+        return self._writers[kind]
+
+    @property
+    def train_summaries(self):
+        return self._writer("train")
+
+    @property
+    def val_summaries(self):
+        return self._writer("validation")
 
     def build_models(self):
         gen_config = self.model_config.generator
@@ -148,6 +198,10 @@ class CycleGan:
             self._metrics = torch.zeros(8, dtype=torch.float32, device="cuda")
             self._ws = None
             self._ws_cap = (0, 0, 0)
+            # resume (model.py:335-338,344-362): load_model() read the four `<name>_optimizer.npy` files before any
+            # device buffer existed; now that the slots do, they go in -- `CycleGan(new=False).train()` continues with
+            # the saved iteration counts and moments, no extra call needed
+            self.restore_optimizers()
         cap = self._ws_cap
         if self._ws is None or B > cap[0] or (H, W) != cap[1:]:
             nbytes = ctypes.c_size_t()
@@ -180,7 +234,8 @@ class CycleGan:
         _lib.check(getattr(lib, fn_name)(self._trainer, _ptr(a), _ptr(b), B, H, W, _ptr(out),
                                          _stream_ptr(torch)), fn_name)
         self._last_inputs = (a, b)      # keep alive until the stream has consumed them
-        return {k: Scalar(out, i) for i, k in enumerate(METRIC_KEYS)}
+        buf = _MetricBuf(out)
+        return {k: Scalar(buf, i) for i, k in enumerate(METRIC_KEYS)}
 
     # -- reference surface ---------------------------------------------------------------
     def validate_step(self, real_a, real_b, training: bool = False) -> Dict:
@@ -218,6 +273,17 @@ class CycleGan:
         _lib.check(_lib.load().cg_trainer_fetch_image(self._trainer, names.index(which), _ptr(out),
                                                       _stream_ptr(torch)), "cg_trainer_fetch_image")
         return DeviceTensor(out)
+
+    CALLS = ("g_AB([a;b])", "g_BA([b;a])", "g_BA(fake_b)", "g_AB(fake_a)", "d_A([a;fake_a])", "d_B([b;fake_b])")
+
+    def call_intermediates(self, call: int):
+        """{tensor id: float32 NHWC array} of model call `call` (index into CALLS) of the last step: the probe the
+        layer-by-layer parity tests use (cg_trainer_fetch_tensor)."""
+        from ..runtime import _fetch_all
+        net = (self.g_AB, self.g_BA, self.g_BA, self.g_AB, self.d_A, self.d_B)[call]
+        lib = _lib.load()
+        return _fetch_all(lambda t, out, shape, st: lib.cg_trainer_fetch_tensor(self._trainer, call, t, out, shape, st),
+                          len(net.graph.layers) + 1)
 
     def enable_data_parallel(self):
         """New functionality (the reference is single-device, train.py:36-43): one process per GPU,
@@ -257,6 +323,12 @@ class CycleGan:
         it = (ctypes.c_int64 * 4)()
         _lib.check(_lib.load().cg_trainer_get_iterations(self._trainer, ctypes.byref(it)), "get_iterations")
         return int(it[i])
+
+    def _set_iterations(self, i, value):
+        it = (ctypes.c_int64 * 4)()
+        _lib.check(_lib.load().cg_trainer_get_iterations(self._trainer, ctypes.byref(it)), "get_iterations")
+        it[i] = int(value)
+        _lib.check(_lib.load().cg_trainer_set_iterations(self._trainer, ctypes.byref(it)), "set_iterations")
 
     def _slot_buffers(self, i):
         """Device buffers behind the Keras slots of optimizer i, in slot creation order: Adam / AdaBelief (m, v);
@@ -333,6 +405,7 @@ class CycleGan:
                 losses = self.train_step(images_a, images_b)
                 self.update_metrics(train_metrics_dict, losses)
                 self.display_metrics(train_metrics_dict, train_bar)
+            self.display_metrics(train_metrics_dict, train_bar, force=True)
             self.write_summaries(self.train_summaries, e, train_metrics_dict)
             if e % save_images_every == 0:
                 self.write_images(e, self.a_samples, self.b_samples, tensorboard_samples)
@@ -343,6 +416,7 @@ class CycleGan:
                 losses = self.validate_step(images_a, images_b, training=False)
                 self.update_metrics(validation_metrics_dict, losses)
                 self.display_metrics(validation_metrics_dict, val_bar)
+            self.display_metrics(validation_metrics_dict, val_bar, force=True)
             self.write_summaries(self.val_summaries, e, validation_metrics_dict)
             if e % save_model_every == 0:
                 self.save_model()
@@ -370,7 +444,15 @@ class CycleGan:
         for name in metrics_dict.keys():
             metrics_dict[name].update_state(metrics[name])
 
-    def display_metrics(self, metrics_dict, progress_bar):
+    def display_metrics(self, metrics_dict, progress_bar, force: bool = False):
+        """model.py:291-302.  Evaluating the running means reads device memory, i.e. waits for the steps queued so far;
+        the reference does that after every batch.  Here it happens at most every `display_interval` seconds (and at
+        the end of the loop), so the steps in between are enqueued back to back."""
+        import time
+        now = time.monotonic()
+        if not force and now - self._last_display < self.display_interval:
+            return
+        self._last_display = now
         evaluated_metrics = {k: str(v.result())[:7] for k, v in metrics_dict.items()}
         progress_bar.set_postfix(**evaluated_metrics)
 
@@ -410,9 +492,12 @@ class CycleGan:
                 setattr(self, s, np.load(p))
 
     def restore_optimizers(self):
-        """model.py:344-362 equivalent; call after the trainer exists (prepare/first step)."""
+        """model.py:344-362 (`load_optimizer`): the reference applies zero gradients once to create the slots, then
+        `set_weights`; here the slots are the trainer's device buffers, created zeroed.  Runs automatically when the
+        native trainer is created; harmless to call again (the pending state is consumed)."""
+        pending, self._pending_optimizer_state = getattr(self, "_pending_optimizer_state", {}), {}
         for i, name in enumerate(NET_NAMES):
-            w = getattr(self, "_pending_optimizer_state", {}).get(name)
+            w = pending.get(name)
             if w is not None and len(w):
                 self._optimizer_set_weights(i, list(w))
 

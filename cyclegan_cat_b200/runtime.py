@@ -281,6 +281,14 @@ class Model:
                                       ws.numel(), N, H, W, 0, _stream_ptr(torch)), "cg_net_forward")
         return DeviceTensor(y)
 
+    def intermediates(self):
+        """{tensor id: float32 NHWC numpy array} of every tensor the last `model(x)` / cg_net_forward materialised
+        (tensor 0 = input, i + 1 = output of layer i; fused layers have no tensor of their own).  The Keras
+        counterpart is `keras.Model(model.input, [l.output for l in model.layers])`; the parity tests feed these to the
+        layer-by-layer oracle (cg_net_fetch_tensor)."""
+        return _fetch_all(lambda t, out, shape, st: _lib.load().cg_net_fetch_tensor(self.handle(), t, out, shape, st),
+                          len(self.graph.layers) + 1)
+
     def predict(self, x, batch_size=32):
         """keras Model.predict (model.py:268-269): batched forward, numpy result."""
         x = np.asarray(x) if not _torch().is_tensor(x) and not isinstance(x, DeviceTensor) else x
@@ -296,6 +304,22 @@ class Model:
                 _lib.load().cg_net_destroy(self._handle)
         except Exception:
             pass
+
+
+def _fetch_all(fetch, n_tensors):
+    torch = _require_cuda()
+    st = _stream_ptr(torch)
+    out = {}
+    for t in range(n_tensors):
+        shape = (ctypes.c_int * 4)()
+        rc = fetch(t, ctypes.c_void_p(0), ctypes.byref(shape), st)
+        if rc == 1:
+            continue            # fused away: never materialised
+        _lib.check(rc, "fetch_tensor (query)")
+        buf = torch.empty(tuple(shape), dtype=torch.float32, device="cuda")
+        _lib.check(fetch(t, _ptr(buf), ctypes.byref(shape), st), "fetch_tensor")
+        out[t] = buf.cpu().numpy()
+    return out
 
 
 def reflection_pad_device(x, pad: int):

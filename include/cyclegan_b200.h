@@ -159,6 +159,13 @@ int cg_net_backward(cg_net_t net, const float* params_dev, const float* dy_dev, 
                     float* grads_dev, int accumulate, void* workspace_dev, size_t workspace_bytes,
                     void* stream);
 
+/* Intermediate tensor `tensor` (0 = input, i+1 = output of layer i) of the last cg_net_forward on this handle, as float32
+ * NHWC; shape4 (nullable) receives its shape.  With out_dev == NULL it only queries: returns 0 when the last forward
+ * materialised the tensor, 1 when a fusion skipped it (e.g. an InstanceNormalization folded into its ReLU / reflection
+ * pad).  Replaces `keras.Model(inputs, layer.output)` probes; the parity tests use it to compare every layer with the
+ * oracle on identical inputs (tests/test_gpu_layerwise.py). */
+int cg_net_fetch_tensor(cg_net_t net, int tensor, float* out_dev, int shape4[4], void* stream);
+
 /* ---- trainer: replaces CycleGan.train_step / validate_step (model.py:91-154) */
 int cg_trainer_create(cg_net_t g_AB, cg_net_t g_BA, cg_net_t d_A, cg_net_t d_B,
                       const cg_train_cfg* cfg, cg_trainer_t* out);
@@ -177,10 +184,20 @@ int cg_train_step(cg_trainer_t tr, const float* real_a_dev, const float* real_b_
 int cg_trainer_compute_gradients(cg_trainer_t tr, const float* real_a_dev, const float* real_b_dev,
                                  int B, int H, int W, float* metrics6_dev, void* stream);
 int cg_trainer_apply_gradients(cg_trainer_t tr, void* stream);      /* 4x optimizer.apply_gradients, model.py:149-153 */
+/* optimizer.apply_gradients(zip(grads, variables)) on its own (model.py:149-153, and the zero-gradient step of
+ * load_optimizer, model.py:359-362): ONE fused launch over a flat float32 range.  `iterations` is optimizer.iterations
+ * before the step (the caller increments it); slot_m / slot_v are the Keras slots (Adam, AdaBelief: m and v; RMSprop:
+ * rms in slot_v; SGD: none, both may be NULL). */
+int cg_optimizer_apply(const cg_adam_cfg* cfg, float* params_dev, const float* grads_dev, float* slot_m_dev,
+                       float* slot_v_dev, size_t n, int64_t iterations, void* stream);
 int cg_trainer_get_iterations(cg_trainer_t tr, int64_t iters[4]);   /* optimizer.iterations (model.py:314-315)  */
 int cg_trainer_set_iterations(cg_trainer_t tr, const int64_t iters[4]);
 /* pointer to an image the last step produced, for tests: 0 fake_b 1 same_b 2 fake_a 3 same_a 4 cycled_a 5 cycled_b */
 int cg_trainer_fetch_image(cg_trainer_t tr, int which, float* out_dev, void* stream);
+
+/* the same probe as cg_net_fetch_tensor for one of the six model calls of the last step:
+ * call 0 g_AB([a;b]) 1 g_BA([b;a]) 2 g_BA(fake_b) 3 g_AB(fake_a) 4 d_A([a;fake_a]) 5 d_B([b;fake_b])  (model.py:93-106) */
+int cg_trainer_fetch_tensor(cg_trainer_t tr, int call, int tensor, float* out_dev, int shape4[4], void* stream);
 
 /* ---- input pipeline (transform/data_load.py:20-34, predict.py:20-27), all HBM-bound streaming kernels ---------- */
 /* normalize (data_load.py:31-34): dst = float32(src) / 127.5 - 1 */

@@ -18,13 +18,16 @@ from .models import create_model, init_variables
 
 class OracleCycleGan:
     def __init__(self, gen_config: Dict, disc_config: Dict, loss="mse", loss_weights=None,
-                 g_opt=None, d_opt=None, dtype=torch.float32, seeds=(42, 43, 44, 45)):
+                 g_opt=None, d_opt=None, dtype=torch.float32, seeds=(42, 43, 44, 45), builder=None):
+        """`builder(config, dtype)` defaults to the statement-by-statement builders of oracle/models.py; the layer-by-layer
+        tests pass one that returns `oracle.ir_exec.IRModel`s (pinned bit-identical to them, tests/test_oracle.py)."""
         self.dtype = dtype
+        builder = builder or create_model
         # model.py:80-89 build_models
-        self.g_AB = create_model(gen_config, dtype)
-        self.g_BA = create_model(gen_config, dtype)
-        self.d_A = create_model(disc_config, dtype)
-        self.d_B = create_model(disc_config, dtype)
+        self.g_AB = builder(gen_config, dtype)
+        self.g_BA = builder(gen_config, dtype)
+        self.d_A = builder(disc_config, dtype)
+        self.d_B = builder(disc_config, dtype)
         for net, seed in zip((self.g_AB, self.g_BA, self.d_A, self.d_B), seeds):
             net.load(init_variables(net.var_specs, seed))
         self.loss_obj = T.loss_obj(loss)
@@ -43,32 +46,38 @@ class OracleCycleGan:
     def _to(self, x):
         return torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(self.dtype)
 
-    def forward_all(self, real_a, real_b, training=False):
+    def forward_all(self, real_a, real_b, training=False, force=None, record=None):
         """model.py:93-106.  Each model call is one Keras call: its own batch statistics / moving-average update
-        (BatchNormalization) and its own dropout mask, keyed by the order of the calls on that model."""
+        (BatchNormalization) and its own dropout mask, keyed by the order of the calls on that model.
+        `force` / `record` ({output name: {tensor id: value}}) are handed to IRModel.forward (teacher forcing)."""
         real_a, real_b = self._to(real_a), self._to(real_b)
         calls = {}
 
-        def run(net, x):
+        def run(net, x, key):
             net.training = training
             net.call_id = calls.get(id(net), 0)
             net.drop_counter = self.train_calls
             calls[id(net)] = net.call_id + 1
             try:
-                return net.forward(x)
+                if force is None and record is None:
+                    return net.forward(x)
+                rec = None
+                if record is not None:
+                    rec = record.setdefault(key, {})
+                return net.forward(x, force=None if force is None else force.get(key), record=rec)
             finally:
                 net.training = False
         o = {}
-        o["fake_b"] = run(self.g_AB, real_a)
-        o["cycled_a"] = run(self.g_BA, o["fake_b"])
-        o["fake_a"] = run(self.g_BA, real_b)
-        o["cycled_b"] = run(self.g_AB, o["fake_a"])
-        o["same_a"] = run(self.g_BA, real_a)
-        o["same_b"] = run(self.g_AB, real_b)
-        o["disc_real_a"] = run(self.d_A, real_a)
-        o["disc_real_b"] = run(self.d_B, real_b)
-        o["disc_fake_a"] = run(self.d_A, o["fake_a"])
-        o["disc_fake_b"] = run(self.d_B, o["fake_b"])
+        o["fake_b"] = run(self.g_AB, real_a, "fake_b")
+        o["cycled_a"] = run(self.g_BA, o["fake_b"], "cycled_a")
+        o["fake_a"] = run(self.g_BA, real_b, "fake_a")
+        o["cycled_b"] = run(self.g_AB, o["fake_a"], "cycled_b")
+        o["same_a"] = run(self.g_BA, real_a, "same_a")
+        o["same_b"] = run(self.g_AB, real_b, "same_b")
+        o["disc_real_a"] = run(self.d_A, real_a, "disc_real_a")
+        o["disc_real_b"] = run(self.d_B, real_b, "disc_real_b")
+        o["disc_fake_a"] = run(self.d_A, o["fake_a"], "disc_fake_a")
+        o["disc_fake_b"] = run(self.d_B, o["fake_b"], "disc_fake_b")
         if training:
             self.train_calls += 1
         return real_a, real_b, o
@@ -93,9 +102,9 @@ class OracleCycleGan:
             ra, rb, o = self.forward_all(real_a, real_b, training)
             return {k: float(v) for k, v in self._metrics(ra, rb, o).items()}
 
-    def gradients(self, real_a, real_b):
+    def gradients(self, real_a, real_b, force=None, record=None):
         """model.py:138-147: returns (metrics, grads dict) without applying them."""
-        ra, rb, o = self.forward_all(real_a, real_b, training=True)
+        ra, rb, o = self.forward_all(real_a, real_b, training=True, force=force, record=record)
         metrics = self._metrics(ra, rb, o)
         grads = {}
         for loss_name, net_name in (("gAB_loss", "g_AB"), ("gBA_loss", "g_BA"),

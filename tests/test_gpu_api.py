@@ -45,21 +45,27 @@ def test_epoch_loop_checkpoint_and_resume():
         w_before = gan.g_AB.get_weights()
         opt_before = gan.g_AB_optimizer.get_weights()
         assert int(opt_before[0]) == 2 * 3                  # 2 epochs x 3 batches
-        # resume: new=False -> load_model(); optimizer slots restored once the trainer exists
+        # resume exactly as the reference does it (model.py:75-78,325-362): CycleGan(new=False) loads the four nets AND the
+        # four optimizers; nothing else is called before training continues
         gan2 = _gan(folder, new=False)
         for a, b in zip(w_before, gan2.g_AB.get_weights()):
             assert np.array_equal(a, b)
-        gan2.prepare(2, 32, 32)
-        gan2.restore_optimizers()
-        opt_after = gan2.g_AB_optimizer.get_weights()
-        assert int(opt_after[0]) == 6
-        for a, b in zip(opt_before[1:], opt_after[1:]):
-            assert np.array_equal(a, b)
-        # both continue identically for one more step (same weights, same Adam state)
+        # both continue for one more step: same weights, same Adam moments, same iteration count -> identical step
         a, b = np.stack([t[0] for t in train[:2]]), np.stack([t[1] for t in train[:2]])
         m1, m2 = gan.train_step(a, b), gan2.train_step(a, b)
         for k in m1:
             assert abs(float(m1[k]) - float(m2[k])) <= 1e-5 * max(1.0, abs(float(m1[k]))), k
+        o1, o2 = gan.g_AB_optimizer.get_weights(), gan2.g_AB_optimizer.get_weights()
+        assert int(o1[0]) == int(o2[0]) == 7
+        for x, y in zip(o1[1:], o2[1:]):                    # m and v after the step: equal only if they were restored
+            assert np.allclose(x, y, rtol=1e-5, atol=1e-12)
+        for x, y in zip(gan.g_AB.get_weights(), gan2.g_AB.get_weights()):
+            assert np.allclose(x, y, rtol=0, atol=2e-7)
+        # ... and a full resumed train() picks up the epoch counter (model.py:205-206)
+        gan2.train(train, val)
+        assert gan2.model_config.current_epoch == 4 and int(gan2.d_A_optimizer.get_weights()[0]) == 7 + 6
+        # tensorboard event files are written by default, like the reference (model.py:62-66,247-250)
+        assert any(f.startswith("events") for f in os.listdir(os.path.join(folder, "m", "train")))
     finally:
         shutil.rmtree(folder, ignore_errors=True)
 
@@ -147,3 +153,62 @@ def test_mixed_modes_rejected():
     cfg = TrainCfg()
     rc = _lib.load().cg_trainer_create(a.handle(), a.handle(), b.handle(), b.handle(), ctypes.byref(cfg), ctypes.byref(h))
     assert rc == -1 and b"mode" in _lib.load().cg_last_error()
+
+
+def test_standalone_apply_gradients_matches_keras_adam():
+    """optimizer.apply_gradients(zip(grads, model.trainable_variables)) outside train_step (model.py:149-153,359-362):
+    three Keras-Adam steps on a free-standing model against the oracle's restatement of the update rule."""
+    from cyclegan_cat_b200.cyclegan.optimizers import get_optimizer
+    from oracle import tf_ops as T
+    m = create_model(C.SMALL_SIMPLE, mode="fp32")
+    opt = get_optimizer(dict(C.ADAM))
+    ref_opt = T.get_optimizer(dict(C.ADAM))
+    ref_vars = [torch.from_numpy(w.astype(np.float64)) for w in m.get_weights()]
+    assert opt.get_weights() == [] and opt.iterations == 0
+    rng = np.random.RandomState(0)
+    for step in range(3):
+        grads = [rng.normal(0, 1e-2, v.shape).astype(np.float32) for v in m.trainable_variables]
+        opt.apply_gradients(zip(grads, m.trainable_variables))
+        ref_opt.apply_gradients([torch.from_numpy(g.astype(np.float64)) for g in grads], ref_vars)
+    assert opt.iterations == 3
+    for got, ref in zip(m.get_weights(), ref_vars):
+        assert C.rel_l2(got, ref.numpy()) <= 1e-6
+    w = opt.get_weights()
+    assert int(w[0]) == 3 and len(w) == 1 + 2 * len(m.trainable_variables)
+    for got, ref in zip(w[1:], ref_opt.get_weights()[1:]):
+        assert C.rel_l2(got.reshape(-1), np.asarray(ref).reshape(-1)) <= 1e-5
+
+
+def test_bound_optimizer_apply_gradients_shares_the_trainer_slots():
+    """An optimizer owned by a CycleGan: apply_gradients advances the same `iterations` / m / v that train_step uses."""
+    gan = CycleGan(C.model_config(C.SMALL_RESNET, C.SMALL_SIMPLE), C.train_config(), mode="fp32")
+    gan.prepare(1, 32, 32)
+    zeros = [np.zeros(v.shape, np.float32) for v in gan.d_A.trainable_variables]
+    before = [w.copy() for w in gan.d_A.get_weights()]
+    gan.d_A_optimizer.apply_gradients(zip(zeros, gan.d_A.trainable_variables))    # load_optimizer's zero step, model.py:359-361
+    assert gan.d_A_optimizer.iterations == 1 and gan.d_B_optimizer.iterations == 0
+    for x, y in zip(before, gan.d_A.get_weights()):
+        assert np.array_equal(x, y)
+    a, b = np.random.RandomState(1).uniform(-1, 1, (2, 1, 32, 32, 3)).astype(np.float32)
+    gan.train_step(a, b)
+    assert gan.d_A_optimizer.iterations == 2 and gan.d_B_optimizer.iterations == 1
+
+
+def test_reseeding_dropout_takes_effect_after_graph_capture():
+    """cg_net_set_seed after the step was captured into a CUDA graph: the trainer drops the graphs (the dropout key is
+    a kernel argument) and restarts its step counter, so the same seed replays the same masks."""
+    def run(seeds):
+        gan = CycleGan(C.model_config(C.DROP_UNET, C.SMALL_SIMPLE), C.train_config(), mode="fp32")
+        gan.g_AB.initialize(1); gan.g_BA.initialize(2); gan.d_A.initialize(3); gan.d_B.initialize(4)
+        a, b = np.random.RandomState(1).uniform(-1, 1, (2, 1, 32, 32, 3)).astype(np.float32)
+        out = []
+        for s in seeds:
+            if s is not None:
+                gan.g_AB.set_dropout_seed(s)
+                gan.g_BA.set_dropout_seed(s + 1)
+            out.append(float(gan.validate_step(a, b, training=True)["gAB_loss"]))
+        return out
+    # steps 0-2 capture and replay the graph with seed 5; step 3 re-seeds to 99; step 4 re-seeds back to 5
+    r = run([5, None, None, 99, 5])
+    assert r[3] != r[2]                     # the new seed is honoured although a graph existed
+    assert r[4] == r[0]                     # seed 5 + restarted counter -> the very first mask again

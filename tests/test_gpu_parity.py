@@ -108,6 +108,7 @@ def _net_grads(m, x, dy):
     st = _stream_ptr(torch)
     _lib.check(lib.cg_net_forward(m.handle(), _ptr(p), _ptr(xd), _ptr(y), _ptr(ws), ws.numel(), N, H, W, 1, st), "fwd")
     _lib.check(lib.cg_net_backward(m.handle(), _ptr(p), _ptr(dyd), _ptr(dx), _ptr(g), 0, _ptr(ws), ws.numel(), st), "bwd")
+    m._keepalive = (ws, xd, dyd)      # Model.intermediates() reads this workspace afterwards
     flat = g.cpu().numpy()
     return y.cpu().numpy(), dx.cpu().numpy(), [flat[v.offset:v.offset + v.size].reshape(v.shape) for v in m.trainable_variables]
 

@@ -277,3 +277,73 @@ def test_frozen_fixture_optional_paths():
     assert np.array_equal(T.resize_bilinear(z["resize_in"], 33, 17), z["resize_out"])
     assert np.array_equal(T.random_jitter(z["resize_in"], 16, np.array([5, 50]), np.array([0, 31]), np.array([1, 0])),
                           z["jitter_out"])
+
+
+# ---- the layer-by-layer oracle (oracle/ir_exec.py) is the same oracle as the statement-by-statement builders ----------
+ALL_CFGS = [C.UNET_G, C.UNET_D, C.SIMPLE_D3, C.FIX_UNET, C.FIX_RESNET, C.FIX_SIMPLE, C.SMALL_RESNET, C.SMALL_STRIDED,
+            C.SMALL_UNET, C.SMALL_UNET_D, C.SMALL_SIMPLE, C.BN_STRIDED, C.BN_UNET, C.BN_SIMPLE, C.DROP_UNET,
+            C.BN_DROP_UNET, C.NONORM_UNET]
+
+
+def _ir_pair(cfg, dtype=torch.float64, seed=3):
+    from cyclegan_cat_b200.cyclegan.model import create_model     # host-side builder: emits the IR, no GPU touched
+    from oracle.ir_exec import IRModel
+    g = create_model(cfg).graph
+    a, b = models.create_model(cfg, dtype), IRModel(g, dtype)
+    w = models.init_variables(a.var_specs, seed)
+    rng = np.random.RandomState(seed + 1)
+    w = [x + rng.normal(0, 0.05, x.shape).astype(np.float32) if x.ndim == 1 else x for x in w]
+    a.load(w)
+    b.load(w)
+    return a, b
+
+
+@pytest.mark.parametrize("cfg", ALL_CFGS, ids=lambda c: c["type"])
+def test_ir_interpreter_equals_builder_oracle(cfg):
+    """Forward, input gradient and every variable gradient are bit-identical: the interpreter issues the same torch
+    ops on the same data in the same order as oracle/models.py (which follows unet.py / resnet.py line by line)."""
+    a, b = _ir_pair(cfg)
+    assert [tuple(v.shape) for v in a.variables] == [tuple(v.shape) for v in b.variables]
+    rng = np.random.RandomState(0)
+    x = rng.uniform(-1, 1, (2, 32, 48, 3))
+    for training in (False, True):
+        outs = []
+        for m in (a, b):
+            m.training, m.call_id, m.drop_counter, m.drop_seed = training, 1, 5, 9
+            xt = torch.from_numpy(x).requires_grad_(True)
+            y = m.forward(xt)
+            dy = torch.from_numpy(np.random.RandomState(1).normal(0, 1, tuple(y.shape)))
+            outs.append((y.detach(), torch.autograd.grad(y, [xt] + m.variables, dy, allow_unused=True)))
+            m.training = False
+        assert torch.equal(outs[0][0], outs[1][0])
+        for ga, gb in zip(outs[0][1], outs[1][1]):
+            assert (ga is None and gb is None) or torch.equal(ga, gb)
+    for sa, sb in zip(a.state, b.state):                 # BatchNormalization moving statistics moved identically
+        assert torch.equal(sa, sb)
+
+
+def test_ir_interpreter_teacher_forcing_and_storage_rounding():
+    """force= replaces values but keeps the gradient path; record= holds the oracle's own layer outputs; forcing a tensor
+    with its own recorded value changes nothing.  storage=bf16 rounds exactly the tensors the CUDA path stores."""
+    _, m = _ir_pair(C.SMALL_RESNET)
+    x = torch.from_numpy(np.random.RandomState(0).uniform(-1, 1, (1, 32, 32, 3)))
+    rec = {}
+    y0 = m.forward(x, record=rec)
+    assert len(rec) == len(m.graph.layers)
+    y1 = m.forward(x, force={t: v for t, v in rec.items()})
+    assert torch.equal(y0, y1)
+    # forcing a perturbed tensor: the consumers see the forced VALUE, the producer still receives gradient
+    t_mid = 5
+    bumped = rec[t_mid] * 1.5
+    rec2 = {}
+    y2 = m.forward(x, force={t_mid: bumped}, record=rec2)
+    assert torch.equal(rec2[t_mid], rec[t_mid]) and not torch.equal(y2, y0)
+    g = torch.autograd.grad(y2.sum(), m.variables[0])[0]
+    assert float(g.abs().sum()) > 0
+    # bf16 storage: every stored tensor is bf16-representable, the norm folded into its ReLU is not rounded on its own
+    rec3 = {}
+    m.forward(x, record=rec3, storage=torch.bfloat16)
+    for t, v in rec3.items():
+        if m.stored[t]:
+            assert torch.equal(v, v.to(torch.bfloat16).to(v.dtype)), t
+    assert not all(m.stored)
