@@ -209,6 +209,18 @@ extern "C" int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode
             L.feeds_in = true;
             L.bias_grad_zero = L.d.has_bias != 0;
         }
+        // the same holds through a channel concat (strided_unet, unet.py:66-70: Conv2DTranspose -> Concatenate -> norm over
+        // the concatenated tensor): the norm is per channel, so the conv's slice still has a zero-sum gradient
+        if ((L.d.op == CG_OP_CONV || L.d.op == CG_OP_CONVT) && L.d.has_bias && net->n_consumers[i + 1] == 1) {
+            for (int j = i + 1; j + 1 < n_layers; ++j) {
+                const cg_layer_desc& q = net->layers[j].d;
+                if (q.op != CG_OP_CONCAT || (q.in0 != i + 1 && q.in1 != i + 1)) continue;
+                if (q.in0 != q.in1 && net->n_consumers[j + 1] == 1 && net->layers[j + 1].d.op == CG_OP_INORM &&
+                    net->layers[j + 1].d.in0 == j + 1)
+                    L.bias_grad_zero = true;
+                break;
+            }
+        }
     }
     // tensor-core layers (bf16 mode): 3x3 stride-1 'valid' convs with Cin % 128 == 0 and Cout % 64 == 0 whose output
     // feeds exactly one instance norm (its backward writes the zero-bordered dY the TMA loads expect)

@@ -3,9 +3,15 @@
 
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "conv_special.h"
 #include "kernels.h"
+
+static int zero_region(void* p, size_t bytes, cudaStream_t st) {
+    CG_CUDA(cudaMemsetAsync(p, 0, bytes, st));
+    return CG_OK;
+}
 
 static inline void same_pad(int in, int k, int s, int* before) {
     int out = (in + s - 1) / s;
@@ -634,7 +640,7 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
     c->live.assign(net->layers.size() + 1, 0);
     c->live[0] = 1;
     // every statistics table of this call is zeroed by ONE memset (they are accumulated into by atomics)
-    if (c->act_bytes > c->stat_begin) CG_CUDA(cudaMemsetAsync(c->base + c->stat_begin, 0, c->act_bytes - c->stat_begin, st));
+    if (c->act_bytes > c->stat_begin) CG_TRY(zero_region(c->base + c->stat_begin, c->act_bytes - c->stat_begin, st));
     for (size_t i = 0; i < net->layers.size(); ++i) {
         const LayerInfo& L = net->layers[i];
         if (L.skipped) continue;
@@ -824,7 +830,7 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
     std::vector<char> written(nl + 1, 0), fold_done(nl + 1, 0);
     auto need = [&](int t) -> bool { return dx_in != nullptr || (t != 0 && net->dep_params[t]); };
     // the backward sums of every instance norm of this call are cleared by ONE memset (sub-batch relative tables)
-    if (c->sums_bytes) CG_CUDA(cudaMemsetAsync(c->arena + c->scratch_off, 0, c->sums_bytes, st));
+    if (c->sums_bytes) CG_TRY(zero_region(c->arena + c->scratch_off, c->sums_bytes, st));
     // A tensor-core data gradient whose target is a reflection-padded tensor nobody else reads writes the interior of the
     // padded grid straight into the UNPADDED gradient (accumulating onto the skip path's contribution if that is already
     // there); the pad's backward then only folds the thin border.  Returns the RPAD layer index or -1.

@@ -91,7 +91,24 @@ struct cg_trainer_s {
     cudaStream_t comm_stream = nullptr; cudaEvent_t ev_d = nullptr, ev_g = nullptr, ev_done = nullptr;
     std::vector<cudaEvent_t> ev_bucket;                        // one fork event per gradient bucket of a step
     int ev_next = 0;
+    // two-chain schedule (CG_DUAL_STREAM=1, EXPERIMENTAL, default off): the step is two independent chains until the losses and
+    // again in the backward -- X = {g_AB([a;b]), g_BA(fake_b), d_B}, Y = {g_BA([b;a]), g_AB(fake_a), d_A} -- run on two streams
+    // with their own gradient arena and unfold scratch, so one chain's kernels fill the SMs the other's last wave leaves idle.
+    // Measured: C3 44.5 -> 44.0 ms, C2 24.9 -> 22.9 ms per step.  Off by default: with the two first-hop backward calls
+    // running concurrently the layer-by-layer parity test (tests/test_gpu_layerwise.py::test_c3_full_size_gradients[fp32])
+    // fails in ~3 of 4 runs with 1e-2 errors in one generator's gradients (0 of 7 with host-side stream synchronisation in
+    // place of the events, 0 of 9 single-chain); the cause is not found yet.  CG_DUAL_PARTS selects the parts
+    // that run on two streams (1 forward, 2 backward phase 1, 4 backward phase 2).
+    bool dual = false;
+    cudaStream_t st2 = nullptr;
+    cudaEvent_t ev2[8] = {};
+    size_t o_arena2 = 0, o_tcs2 = 0;
 };
+
+static bool dual_default() {      // read when a trainer is created (tests build single- and two-chain trainers side by side)
+    const char* e = getenv("CG_DUAL_STREAM");
+    return e && e[0] == '1';
+}
 
 // Bucketed all-reduce of a generator's gradients under its LAST backward call: the flat gradient buffer is
 // in forward-layer order and the backward retires layers last to first, so after layer i every gradient at an offset >=
@@ -155,6 +172,7 @@ static int trainer_layout(cg_trainer_t tr, int B, int H, int W, bool assign) {
     size_t arena = 0;
     for (CallCtx* c : {&tr->F1, &tr->F2, &tr->C1, &tr->C2, &tr->DA, &tr->DB}) if (c->grad_bytes > arena) arena = c->grad_bytes;
     tr->o_arena = take(arena);
+    tr->o_arena2 = tr->dual ? take(arena) : tr->o_arena;
     tr->o_seedF1 = take(2 * B * img); tr->o_seedF2 = take(2 * B * img);
     tr->o_seedC1 = take(B * img); tr->o_seedC2 = take(B * img);
     tr->o_dxC1 = take(B * img); tr->o_dxC2 = take(B * img);
@@ -168,12 +186,18 @@ static int trainer_layout(cg_trainer_t tr, int B, int H, int W, bool assign) {
     size_t tcs = 0;
     for (CallCtx* c : {&tr->F1, &tr->F2, &tr->C1, &tr->C2, &tr->DA, &tr->DB}) if (c->tcs_bytes > tcs) tcs = c->tcs_bytes;
     tr->o_tcs = take(align_up(tcs, 1024));
+    tr->o_tcs2 = tr->dual ? take(align_up(tcs, 1024)) : tr->o_tcs;
     tr->total = off;
     if (assign) {
         if (off > tr->ws_bytes) { cg_set_error("trainer workspace %zu < required %zu", tr->ws_bytes, off); return CG_ERR_WORKSPACE; }
         size_t bases[6] = {oF1, oF2, oC1, oC2, oDA, oDB};
         CallCtx* cs[6] = {&tr->F1, &tr->F2, &tr->C1, &tr->C2, &tr->DA, &tr->DB};
-        for (int i = 0; i < 6; ++i) { cs[i]->base = tr->ws + bases[i]; cs[i]->arena = tr->ws + tr->o_arena; cs[i]->ext_input = nullptr; }
+        const int chain[6] = {0, 1, 0, 1, 1, 0};          // F1, C1, DB on chain X; F2, C2, DA on chain Y
+        for (int i = 0; i < 6; ++i) {
+            cs[i]->base = tr->ws + bases[i];
+            cs[i]->arena = tr->ws + (chain[i] ? tr->o_arena2 : tr->o_arena);
+            cs[i]->ext_input = nullptr;
+        }
         // BatchNormalization / Dropout see the Keras calls of model.py:93-106, not the concatenated batches: B samples per
         // call; call ids = the order in which validate_step calls each model (g_AB: real_a, fake_a, real_b; g_BA: fake_b,
         // real_b, real_a; d_A: real_a, fake_a; d_B: real_b, fake_b)
@@ -190,7 +214,7 @@ static int trainer_layout(cg_trainer_t tr, int B, int H, int W, bool assign) {
         const int owner[6] = {0, 1, 1, 0, 2, 3};
         for (int i = 0; i < 6; ++i) {
             cs[i]->packed = tr->ws + tr->o_packed[owner[i]];
-            cs[i]->tcs = tr->ws + tr->o_tcs;
+            cs[i]->tcs = tr->ws + (chain[i] ? tr->o_tcs2 : tr->o_tcs);
             CG_TRY(net_bind(cs[i]));
         }
         for (int g = 0; g < 2; ++g) {
@@ -218,6 +242,7 @@ extern "C" int cg_trainer_create(cg_net_t g_AB, cg_net_t g_BA, cg_net_t d_A, cg_
     cg_trainer_s* tr = new cg_trainer_s();
     tr->net[0] = g_AB; tr->net[1] = g_BA; tr->net[2] = d_A; tr->net[3] = d_B;
     tr->cfg = *cfg;
+    tr->dual = dual_default();
     *out = tr;
     return CG_OK;
 }
@@ -227,6 +252,8 @@ extern "C" void cg_trainer_destroy(cg_trainer_t tr) {
     for (int g = 0; g < 2; ++g)             // graphs first: they may hold NCCL kernels of the communicator
         if (tr->graph_exec[g]) cudaGraphExecDestroy(tr->graph_exec[g]);
     if (tr->cap_stream) cudaStreamDestroy(tr->cap_stream);
+    if (tr->st2) cudaStreamDestroy(tr->st2);
+    for (cudaEvent_t e : tr->ev2) if (e) cudaEventDestroy(e);
     if (tr->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(tr->comm);
     if (tr->comm_stream) cudaStreamDestroy(tr->comm_stream);
     if (tr->ev_d) cudaEventDestroy(tr->ev_d);
@@ -285,24 +312,52 @@ static int step_body(cg_trainer_t tr, int B, int H, int W, bool train, cudaStrea
     const T* ra = Xab;
     const T* rb = Xab + B * img;
 
+    // ---- two chains -------------------------------------------------------------------------
+    // X = {F1, C1, DB} on `st`, Y = {F2, C2, DA} on `sy` (== st when the two-chain schedule is off).  fork(e): sy continues
+    // after everything enqueued on st so far; join(e): st continues after everything enqueued on sy so far.  Inside a
+    // stream capture the events become graph edges, so the captured step has two parallel branches.
+    cudaStream_t sy = st;
+    if (tr->dual) {
+        if (!tr->st2) CG_CUDA(cudaStreamCreateWithFlags(&tr->st2, cudaStreamNonBlocking));
+        for (cudaEvent_t& e : tr->ev2) if (!e) CG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        sy = tr->st2;
+    }
+    auto fork = [&](int e) -> int {
+        if (sy == st) return CG_OK;
+        CG_CUDA(cudaEventRecord(tr->ev2[e], st));
+        CG_CUDA(cudaStreamWaitEvent(sy, tr->ev2[e], 0));
+        return CG_OK;
+    };
+    auto join = [&](int e) -> int {
+        if (sy == st) return CG_OK;
+        CG_CUDA(cudaEventRecord(tr->ev2[e], sy));
+        CG_CUDA(cudaStreamWaitEvent(st, tr->ev2[e], 0));
+        return CG_OK;
+    };
+
     // ---- forward --------------------------------------------------------------------------
     for (CallCtx* c : {&tr->F1, &tr->F2, &tr->C1, &tr->C2, &tr->DA, &tr->DB}) c->training = train;   // model.py:138-141 / :221
-    CG_TRY(net_forward(&tr->F1, tr->params[0], st));
-    CG_TRY(net_forward(&tr->F2, tr->params[1], st));
-    CG_TRY(net_forward(&tr->C1, tr->params[1], st));    // g_BA(fake_b)
-    CG_TRY(net_forward(&tr->C2, tr->params[0], st));    // g_AB(fake_a)
     const T* F1o = (const T*)tr->F1.act(tG);            // [fake_b ; same_b]
     const T* F2o = (const T*)tr->F2.act(tGb);           // [fake_a ; same_a]
     const T* cyc_a = (const T*)tr->C1.act(tGb);
     const T* cyc_b = (const T*)tr->C2.act(tG);
     T* DAin = (T*)tr->DA.act(0);
     T* DBin = (T*)tr->DB.act(0);
-    CG_TRY(k_copy_acc<T>(ra, DAin, B * img, 0, st));
-    CG_TRY(k_copy_acc<T>(F2o, DAin + B * img, B * img, 0, st));       // fake_a
+    static const int parts = [] { const char* e = getenv("CG_DUAL_PARTS"); return e ? atoi(e) : 7; }();   // diagnostic bisect
+    cudaStream_t sy_all = sy;
+    sy = (parts & 1) ? sy_all : st;
+    CG_TRY(fork(0));
+    CG_TRY(net_forward(&tr->F1, tr->params[0], st));
+    CG_TRY(net_forward(&tr->F2, tr->params[1], sy));
+    CG_TRY(net_forward(&tr->C1, tr->params[1], st));    // g_BA(fake_b)
+    CG_TRY(net_forward(&tr->C2, tr->params[0], sy));    // g_AB(fake_a)
     CG_TRY(k_copy_acc<T>(rb, DBin, B * img, 0, st));
     CG_TRY(k_copy_acc<T>(F1o, DBin + B * img, B * img, 0, st));       // fake_b
-    CG_TRY(net_forward(&tr->DA, tr->params[2], st));
+    CG_TRY(k_copy_acc<T>(ra, DAin, B * img, 0, sy));
+    CG_TRY(k_copy_acc<T>(F2o, DAin + B * img, B * img, 0, sy));       // fake_a
     CG_TRY(net_forward(&tr->DB, tr->params[3], st));
+    CG_TRY(net_forward(&tr->DA, tr->params[2], sy));
+    CG_TRY(join(1));
     const T* dA = (const T*)tr->DA.act(tDa);            // [disc_real_a ; disc_fake_a]
     const T* dB = (const T*)tr->DB.act(tDb);
     if (train) {    // BatchNormalization moving averages, one update per Keras call in the order of model.py:93-106
@@ -337,14 +392,23 @@ static int step_body(cg_trainer_t tr, int B, int H, int W, bool train, cudaStrea
     if (!train) return CG_OK;
 
     // ---- backward ---------------------------------------------------------------------------
+    // chain X: d_B loss -> d fake_b through the frozen d_B -> g_BA(fake_b) -> g_AB([a;b]);  chain Y: the mirror image.
+    // Parameter gradients are accumulated with plain read-modify-writes in places, so the two chains never write the same
+    // net at the same time: phase 1 = {X: d_B, g_BA | Y: d_A, g_AB}, phase 2 = {X: g_AB | Y: g_BA}, swapped by two events.
     for (int i = 0; i < 4; ++i)
         CG_CUDA(cudaMemsetAsync(tr->grads[i], 0, sizeof(float) * (size_t)tr->net[i]->n_params, st));
+    sy = (parts & 2) ? sy_all : st;
+    CG_TRY(fork(2));
     // discriminator losses: parameter gradients only
-    CG_TRY(net_backward(&tr->DA, tr->params[2], seedDA, nullptr, tr->grads[2], 0, 2 * B, st));
     CG_TRY(net_backward(&tr->DB, tr->params[3], seedDB, nullptr, tr->grads[3], 0, 2 * B, st));
+    CG_TRY(net_backward(&tr->DA, tr->params[2], seedDA, nullptr, tr->grads[2], 0, 2 * B, sy));
     if (tr->comm) {     // d_A / d_B gradients are final: all-reduce them under the generator backward
         CG_CUDA(cudaEventRecord(tr->ev_d, st));
         CG_CUDA(cudaStreamWaitEvent(tr->comm_stream, tr->ev_d, 0));
+        if (sy != st) {
+            CG_CUDA(cudaEventRecord(tr->ev2[3], sy));
+            CG_CUDA(cudaStreamWaitEvent(tr->comm_stream, tr->ev2[3], 0));
+        }
         CG_NCCL(g_nccl.GroupStart());
         CG_NCCL(g_nccl.AllReduce(tr->grads[2], tr->grads[2], (size_t)tr->net[2]->n_params, 7, 0, tr->comm, tr->comm_stream));
         CG_NCCL(g_nccl.AllReduce(tr->grads[3], tr->grads[3], (size_t)tr->net[3]->n_params, 7, 0, tr->comm, tr->comm_stream));
@@ -352,19 +416,22 @@ static int step_body(cg_trainer_t tr, int B, int H, int W, bool train, cudaStrea
     }
     // adversarial generator terms: data gradient through the frozen discriminators (fake half)
     CG_TRY(net_backward(&tr->DB, tr->params[3], advDB, seedF1, nullptr, B, B, st));      // d fake_b
-    CG_TRY(net_backward(&tr->DA, tr->params[2], advDA, seedF2, nullptr, B, B, st));      // d fake_a
+    CG_TRY(net_backward(&tr->DA, tr->params[2], advDA, seedF2, nullptr, B, B, sy));      // d fake_a
     // cycle terms
     T* dxC1 = (T*)(ws + tr->o_dxC1); T* dxC2 = (T*)(ws + tr->o_dxC2);
     CG_TRY(net_backward(&tr->C1, tr->params[1], seedC1, dxC1, tr->grads[1], 0, B, st));  // theta_BA, d fake_b
     CG_TRY(k_copy_acc<T>(dxC1, seedF1, n_img, 1, st));
-    CG_TRY(net_backward(&tr->C2, tr->params[0], seedC2, dxC2, tr->grads[0], 0, B, st));  // theta_AB, d fake_a
-    CG_TRY(k_copy_acc<T>(dxC2, seedF2, n_img, 1, st));
+    CG_TRY(net_backward(&tr->C2, tr->params[0], seedC2, dxC2, tr->grads[0], 0, B, sy));  // theta_AB, d fake_a
+    CG_TRY(k_copy_acc<T>(dxC2, seedF2, n_img, 1, sy));
+    // swap: X may touch theta_AB only after Y's cycle call has, Y theta_BA only after X's (a full join + fork)
+    CG_TRY(join(4));
+    sy = (parts & 4) ? sy_all : st;
+    CG_TRY(fork(5));
     // first-hop generator calls: [d fake ; d same].  These are the last contributions to theta_AB / theta_BA, so with a
     // communicator their gradients can be all-reduced bucket by bucket while the backward is still running
-    // (CG_DP_BUCKETS=1).  Opt-in: on 2 GPUs it measured neutral (45.58 vs 45.39 ms per step -- the two 45 MB reductions
-    // at the end cost ~0.1 ms there, and NCCL's CTAs compete with the backward's persistent kernels for SMs).
+    // (CG_DP_BUCKETS=1, single-chain schedule only).
     static const bool buckets_on = [] { const char* e = getenv("CG_DP_BUCKETS"); return e && e[0] == '1'; }();
-    if (tr->comm && buckets_on) {
+    if (tr->comm && buckets_on && sy == st) {
         tr->ev_next = 0;
         BucketCtx b0{tr, 0, st, tr->net[0]->n_params, tr->net[0]->n_params / 4 + 1, 0};
         CG_TRY(net_backward(&tr->F1, tr->params[0], seedF1, nullptr, tr->grads[0], 0, 2 * B, st, bucket_hook, &b0));
@@ -377,7 +444,8 @@ static int step_body(cg_trainer_t tr, int B, int H, int W, bool train, cudaStrea
         return CG_OK;
     }
     CG_TRY(net_backward(&tr->F1, tr->params[0], seedF1, nullptr, tr->grads[0], 0, 2 * B, st));
-    CG_TRY(net_backward(&tr->F2, tr->params[1], seedF2, nullptr, tr->grads[1], 0, 2 * B, st));
+    CG_TRY(net_backward(&tr->F2, tr->params[1], seedF2, nullptr, tr->grads[1], 0, 2 * B, sy));
+    CG_TRY(join(6));
     if (tr->comm) {
         CG_CUDA(cudaEventRecord(tr->ev_g, st));
         CG_CUDA(cudaStreamWaitEvent(tr->comm_stream, tr->ev_g, 0));

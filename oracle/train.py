@@ -16,12 +16,30 @@ from . import tf_ops as T
 from .models import create_model, init_variables
 
 
+class _RoundGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dt):
+        ctx.dt = dt
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(ctx.dt).to(g.dtype), None
+
+
+def _round_grad(x, dt):
+    return _RoundGrad.apply(x, dt)
+
+
 class OracleCycleGan:
     def __init__(self, gen_config: Dict, disc_config: Dict, loss="mse", loss_weights=None,
-                 g_opt=None, d_opt=None, dtype=torch.float32, seeds=(42, 43, 44, 45), builder=None):
+                 g_opt=None, d_opt=None, dtype=torch.float32, seeds=(42, 43, 44, 45), builder=None, seed_storage=None):
         """`builder(config, dtype)` defaults to the statement-by-statement builders of oracle/models.py; the layer-by-layer
         tests pass one that returns `oracle.ir_exec.IRModel`s (pinned bit-identical to them, tests/test_oracle.py)."""
         self.dtype = dtype
+        # seed_storage=torch.bfloat16: the loss gradients w.r.t. the ten model outputs are rounded to bf16 once, where the
+        # CUDA path stores them (the bf16 mode keeps its gradient seeds in the activation dtype); forward values untouched
+        self.seed_storage = seed_storage
         builder = builder or create_model
         # model.py:80-89 build_models
         self.g_AB = builder(gen_config, dtype)
@@ -78,6 +96,8 @@ class OracleCycleGan:
         o["disc_real_b"] = run(self.d_B, real_b, "disc_real_b")
         o["disc_fake_a"] = run(self.d_A, o["fake_a"], "disc_fake_a")
         o["disc_fake_b"] = run(self.d_B, o["fake_b"], "disc_fake_b")
+        if self.seed_storage is not None:
+            o = {k: _round_grad(v, self.seed_storage) for k, v in o.items()}
         if training:
             self.train_calls += 1
         return real_a, real_b, o

@@ -112,7 +112,8 @@ def gan_pair(gen, disc, mode, loss="mse", dtype=torch.float64):
     """Product CycleGan + the layer-by-layer oracle (IRModels) with identical weights."""
     from cyclegan_cat_b200.cyclegan.model import CycleGan
     gan = CycleGan(C.model_config(gen, disc, loss), C.train_config(), mode=mode)
-    o = OracleCycleGan(gen, disc, loss=loss, dtype=dtype, builder=ir_builder(mode))
+    o = OracleCycleGan(gen, disc, loss=loss, dtype=dtype, builder=ir_builder(mode),
+                       seed_storage=torch.bfloat16 if mode == "bf16" else None)
     for name in ("g_AB", "g_BA", "d_A", "d_B"):
         getattr(gan, name).set_weights([v.detach().numpy() for v in getattr(o, name).variables])
     return gan, o
@@ -123,8 +124,19 @@ def check_train_step(gan, o, a, b, mode, name, apply=False):
     model calls, the four losses, and every variable gradient of the four nets.  With apply=True the optimizer step is
     taken as well and the post-step weights are compared (Keras Adam restated in oracle/tf_ops.py)."""
     B = a.shape[0]
-    metrics, grads = gan.compute_gradients(a, b)
-    calls = [gan.call_intermediates(i) for i in range(6)]
+    reps = int(os.environ.get("CG_TEST_REPS", "1"))          # diagnostic: >= 3 checks a CUDA-graph replay instead of the eager step
+    if os.environ.get("CG_TEST_SIDE_STREAM") == "1":
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(reps):
+                metrics, grads = gan.compute_gradients(a, b)
+            calls = [gan.call_intermediates(i) for i in range(6)]
+        side.synchronize()
+    else:
+        for _ in range(reps):
+            metrics, grads = gan.compute_gradients(a, b)
+        calls = [gan.call_intermediates(i) for i in range(6)]
     force = {}
     for key, (ci, half) in CALL_OF.items():
         sl = None if half is None else slice(half * B, (half + 1) * B)

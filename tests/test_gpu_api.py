@@ -176,7 +176,9 @@ def test_standalone_apply_gradients_matches_keras_adam():
     w = opt.get_weights()
     assert int(w[0]) == 3 and len(w) == 1 + 2 * len(m.trainable_variables)
     for got, ref in zip(w[1:], ref_opt.get_weights()[1:]):
-        assert C.rel_l2(got.reshape(-1), np.asarray(ref).reshape(-1)) <= 1e-5
+        # float32 slots: 1 - beta_2 = 1 - 0.999f carries a relative 1.3e-5 (as in TensorFlow's float32 kernel); the oracle
+        # evaluates the rule in float64
+        assert C.rel_l2(got.reshape(-1), np.asarray(ref).reshape(-1)) <= 1e-4
 
 
 def test_bound_optimizer_apply_gradients_shares_the_trainer_slots():
@@ -210,5 +212,6 @@ def test_reseeding_dropout_takes_effect_after_graph_capture():
         return out
     # steps 0-2 capture and replay the graph with seed 5; step 3 re-seeds to 99; step 4 re-seeds back to 5
     r = run([5, None, None, 99, 5])
-    assert r[3] != r[2]                     # the new seed is honoured although a graph existed
-    assert r[4] == r[0]                     # seed 5 + restarted counter -> the very first mask again
+    assert abs(r[3] - r[2]) > 1e-4          # the new seed is honoured although a graph existed
+    assert abs(r[4] - r[0]) <= 1e-5         # seed 5 + restarted counter -> the very first mask again (fp32 atomics aside)
+    assert abs(r[1] - r[0]) > 1e-4          # ... while consecutive steps of one seed draw different masks
