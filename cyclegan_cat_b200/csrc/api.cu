@@ -226,6 +226,8 @@ extern "C" int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode
     // feeds exactly one instance norm (its backward writes the zero-bordered dY the TMA loads expect)
     size_t pk = 0;
     const char* no_tc = getenv("CG_DISABLE_TC");     // test hook: force the CUDA-core convs in bf16 mode
+    const char* no_win = getenv("CG_DISABLE_WIN");   // A/B hook: the 16-channel-group kernels instead of the window form
+    const bool win_on = !(no_win && no_win[0] == '1');
     if (mode == CG_MODE_BF16 && !(no_tc && no_tc[0] == '1')) {
         auto chan_ok = [](int cin_f, int cout_f) {      // K chunks of 64, N tiles of <= 256, an M = 128 side for wgrad
             return cin_f % 64 == 0 && cout_f % 64 == 0 && (cin_f <= 256 || cin_f % 256 == 0) &&
@@ -252,10 +254,24 @@ extern "C" int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode
             else if (d.op == CG_OP_CONV && d.stride == 1 && !d.same && d.k >= 3 && d.cout <= 4 && d.k * d.cout <= 21 && d.k <= 12 &&
                      d.cin % 64 == 0 && d.cin <= 256)
                 kind = TC_HEAD;         // c7s1-3 tanh head (resnet.py:82)
+            else if (win_on && d.op == CG_OP_CONV && d.stride == 1 && (d.same || d.k == 1) && d.k <= 7 &&
+                     ((d.cin % 8 == 0 && d.cin <= 2048) || d.cin <= 4) && d.cout % 16 == 0 && d.cout <= 256 &&
+                     d.k * ((d.k * (d.cin <= 4 ? 8 : d.cin) + 63) / 64) <= TC_MAX_STEPS)
+                kind = TC_S1_WIN;       // U-Net double_conv layers (unet.py:25) incl. the 3-channel image-side one: window form
             else if (d.op == CG_OP_CONV && d.stride == 1 && (d.same || d.k == 1) && d.k <= 7 && d.cin % 16 == 0 &&
                      d.cout % 16 == 0 && d.cout <= 256 && d.cin <= 256 * 8)
-                kind = TC_S1_16;        // U-Net double_conv layers (unet.py:25): channel counts are multiples of 16 only
-            if (kind == TC_IM2COL) {
+                kind = TC_S1_16;        // the same layers as 16-channel groups (CG_DISABLE_WIN=1: the round-1 path, kept for A/B)
+            if (kind == TC_S1_WIN) {
+                // packed window weights: forward [k*nch][Cout][64]; data gradient [k*nch_d][Cin][64] when Cin can be an N tile
+                L.tc = kind;
+                const int cp = d.cin <= 4 ? 8 : d.cin;
+                const int nch = (d.k * cp + 63) / 64, nch_d = (d.k * d.cout + 63) / 64;
+                L.pk_f = (long long)pk; pk += align_up((size_t)d.k * nch * d.cout * 64 * 2, 1024);
+                L.pk_d = -1;
+                if (d.cin % 16 == 0 && d.cin <= 256 && d.k * nch_d <= TC_MAX_STEPS) {
+                    L.pk_d = (long long)pk; pk += align_up((size_t)d.k * nch_d * d.cin * 64 * 2, 1024);
+                }
+            } else if (kind == TC_IM2COL) {
                 L.tc = kind;
                 L.pk_f = (long long)pk; pk += align_up((size_t)d.cout * 64 * 2, 1024);
                 L.pk_d = (long long)pk; pk += align_up((size_t)64 * d.cout * 2, 1024);
@@ -340,13 +356,13 @@ struct SingleLayout { size_t act, arena, dy, dx, packed, tcs, total; };
 static int single_layout(const cg_net_s* net, CallCtx* ctx, int N, int H, int W, bool bwd, SingleLayout* lay) {
     CG_TRY(net_plan(net, N, H, W, bwd, ctx));
     size_t es = net->elem_size();
-    lay->act = 0;
-    lay->arena = align_up(ctx->act_bytes, 256);
+    lay->act = 4096;                // slack: the window view of the first tensor starts a few pixels before it (tc_make_map_win)
+    lay->arena = align_up(lay->act + ctx->act_bytes, 256);
     lay->dy = lay->arena + align_up(ctx->grad_bytes, 256);
     lay->dx = lay->dy + (bwd ? align_up((size_t)N * ctx->sample_elems(net->out_tensor()) * es, 256) : 0);
     lay->packed = align_up(lay->dx + (bwd ? align_up((size_t)N * ctx->sample_elems(0) * es, 256) : 0), 1024);
     lay->tcs = align_up(lay->packed + net->packed_bytes, 1024);
-    lay->total = lay->tcs + ctx->tcs_bytes;
+    lay->total = lay->tcs + ctx->tcs_bytes + 4096;
     return CG_OK;
 }
 

@@ -281,3 +281,22 @@ int sp_unpack_im2col(const float* t, float* dw, int k, int Cin, int Cout, cudaSt
     CG_LAUNCH_CHECK();
     return CG_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// image-side layer of the U-Nets (unet.py:25 first double_conv conv, Cin = 3): the window conv (conv_tc.cu) needs a pixel
+// stride of a multiple of 16 bytes, so the 3-channel input is re-laid as 8 channels (3 real + 5 zero) in the scratch
+// ------------------------------------------------------------------------------------------
+__global__ void pad_channels8_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, size_t npix, int cin) {
+    const bf16 zero = __float2bfloat16(0.f);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+        Pack<bf16, 8> pk;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) pk.v[c] = c < cin ? x[i * cin + c] : zero;
+        reinterpret_cast<uint4*>(y)[i] = *reinterpret_cast<uint4*>(&pk);
+    }
+}
+int sp_pad_channels8(const bf16* x, bf16* y, size_t npix, int cin, cudaStream_t st) {
+    pad_channels8_kernel<<<blocks_for(npix), 256, 0, st>>>(x, y, npix, cin);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}

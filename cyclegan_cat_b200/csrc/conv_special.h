@@ -11,3 +11,4 @@ int sp_im2col(const bf16* x, bf16* U, int N, int H, int W, int Cin, int Ho, int 
 int sp_col2im(const bf16* dU, bf16* dx, int N, int H, int W, int Cin, int Ho, int Wo, int k, int s, int pt, int pl, cudaStream_t st);
 int sp_pack_im2col(const float* w, bf16* wf, bf16* wd, int k, int Cin, int Cout, cudaStream_t st);
 int sp_unpack_im2col(const float* t, float* dw, int k, int Cin, int Cout, cudaStream_t st);
+int sp_pad_channels8(const bf16* x, bf16* y, size_t npix, int cin, cudaStream_t st);

@@ -152,6 +152,37 @@ __device__ __forceinline__ float warp_colsum32(float (&s)[32], int lane) {
     return s[0];
 }
 
+// Window mode: zero the 16-byte granules of a freshly landed K-major SWIZZLE_128B tile ([box_h][box_w] rows of 128 bytes,
+// row = pixel) whose window pixel lies outside the image row.  Row (hb, wb) holds elements [c0, c0+64) of the k*C-element
+// window that starts `pl` pixels left of pixel p = w0 + wb; window pixel q = e / C is column p - pl + q.  Only rows within
+// pl of the left edge or k-1-pl of the right edge have anything to zero, so a 128-wide tile of a 256-wide row touches <= 3
+// rows per step.  Called by all 32 lanes of the MMA warp between the TMA-complete wait and the MMA issue; the
+// fence.proxy.async orders the generic-proxy stores before the tensor core's async-proxy reads.
+__device__ __forceinline__ void win_fix(uint32_t tile, int box_w, int box_h, int w0, int W, int C, int k, int pl, int c0,
+                                        int lane) {
+    const int nl = w0 < pl ? min(pl - w0, box_w) : 0;                       // affected columns at the left end of the box
+    const int pr = k - 1 - pl;
+    const int nr = w0 + box_w > W - pr ? min(w0 + box_w - (W - pr), box_w) : 0;      // ... and at the right end
+    const int ne = nl + nr;
+    if (ne == 0) return;
+    const int ncand = ne * box_h * 8;
+    for (int idx = lane; idx < ncand; idx += 32) {
+        const int g = idx & 7, e = idx >> 3;
+        const int hb = e / ne, j = e - hb * ne;
+        const int wb = j < nl ? j : box_w - nr + (j - nl);
+        const int p = w0 + wb;
+        const int lo = max(0, pl - p) * C;                                  // window elements [0, lo) lie left of column 0
+        const int hi = min(k, W - p + pl) * C;                              // ... [hi, k*C) right of column W-1
+        const int el = c0 + 8 * g;
+        if (el < lo || el >= hi) {
+            const int r = hb * box_w + wb;
+            const uint32_t addr = tile + (uint32_t)r * 128u + (uint32_t)((g ^ (r & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
+        }
+    }
+    fence_proxy_async();
+}
+
 static constexpr int TC_THREADS = 192;        // 6 warps: TMA, MMA, 4 x epilogue
 // conv_tc_kernel: 10 warps = TMA, MMA, 8 x epilogue.  The epilogue of a 32-column chunk (tcgen05.ld, bf16 pack, stores,
 // instance-norm column sums) costs a lone warp ~2200 cycles of mostly exposed latency, more than the main loop of every
@@ -171,7 +202,8 @@ static constexpr int TMEM_COLS = 512;
 // each).  With few K steps per tile the single MMA-issuing thread's chain (mbarrier wait -> MMAs -> commit, ~600 cycles
 // per K step; ~2100 cycles per 3-step tile even with loads and epilogue switched off) bounds the SM, not the tensor pipe;
 // two resident CTAs overlap their chains.
-template <bool BK16, bool DUAL>
+// WIN: window mode (TcConvArgs::win_*): the MMA warp patches the image-row edges of every A tile before issuing.
+template <bool BK16, bool DUAL, bool WIN = false>
 __global__ void __launch_bounds__(DUAL ? TC_THREADS : CONV_THREADS, DUAL ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                bf16* __restrict__ out, const float* __restrict__ bias, const TcConvArgs a) {
@@ -250,6 +282,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
         }
     } else if (warp == 1) {
+        if constexpr (WIN) {        // all 32 lanes: wait, patch the row edges of the A tile, then lane 0 issues
+            int s = 0; uint32_t ph = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+                const int ti = (t / a.n_blocks_n) % a.tiles_per_img;
+                const int w0 = (ti % a.tiles_w) * a.Wb;
+                mbar_wait(tempty(acc), acc_ph ^ 1u);
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * ACC_COLS;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(full(s), ph);
+                    const uint32_t sa = smem0 + s * stage_bytes;
+                    win_fix(sa, a.Wb, a.Hb, w0, a.win_W, a.win_C, a.win_k, a.win_pl, a.dc[ks], lane);
+                    __syncwarp();
+                    if (lane == 0) {
+                        tc_fence_after();
+                        const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+                        const uint64_t bdesc = make_smem_desc(sa + A_TILE_BYTES, 16, 1024);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), a.idesc,
+                                      (uint32_t)((ks | k) != 0));
+                        umma_commit(empty(s));
+                    }
+                    __syncwarp();
+                    if (++s == S) { s = 0; ph ^= 1u; }
+                }
+                if (lane == 0) umma_commit(tfull(acc));
+                __syncwarp();
+            }
+        } else
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
             int it = 0;
@@ -330,7 +394,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int c0 = half * 32; c0 < a.bn; c0 += (DUAL ? 32 : 64)) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
-                const int cols = BK16 ? min(32, a.bn - c0) : 32;          // 16 when the N tile is not a multiple of 32 (BK16 only)
+                const int cols = (BK16 || WIN) ? min(32, a.bn - c0) : 32;          // 16 when the N tile is not a multiple of 32
                 if (bias) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
@@ -859,6 +923,167 @@ wgrad16_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------
+// weight gradient in window mode (U-Net layers, any C % 8 == 0): dW[kh][(kw, ci)][co] = sum_pixels Xwin[p][(kw, ci)] * dY[p][co].
+// The A operand is the SAME window tile the forward conv loads (64 window elements x 64 pixels, MN-major here), two K
+// steps of the forward conv stacked in the 128 MMA rows; B = the dY chunk as 16-channel groups (SWIZZLE_32B, one box).
+// K = 64 pixels per stage, split over the pixel range, fp32 vector reductions straight into TF's HWIO gradient (the row
+// index kh*k*C + e of the window element IS the HWIO row).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgradw_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDY,
+                 float* __restrict__ dw, const TcWgradWArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ygroups = a.Cout / 16;
+    const uint32_t stage_bytes = 16384u + (uint32_t)ygroups * 2048u;
+    const int S = a.stages;
+    const uint32_t bar0 = smem0 + S * stage_bytes;
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (S + s); };
+    const uint32_t tfull = bar0 + 8u * (2 * S);
+    const uint32_t tmem_slot = bar0 + 8u * (2 * S + 1);
+    volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapX);
+        tma_prefetch_desc(&mapDY);
+        for (int s = 0; s < S; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    griddep_launch();
+    griddep_wait();
+
+    const int split = blockIdx.x % a.splits, u = blockIdx.x / a.splits;
+    const int total_chunks = a.nb * a.chunks_per_img;
+    const int per = (total_chunks + a.splits - 1) / a.splits;
+    const int q_begin = split * per;
+    const int q_end = min(total_chunks, q_begin + per);
+    const int nq = q_end - q_begin;
+    const int nhalf = min(2, a.steps - 2 * u);          // live 64-row halves of this unit
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int q = q_begin; q < q_end; ++q) {
+                const int img = q / a.chunks_per_img, r = q % a.chunks_per_img;
+                const int w0 = (r % a.chunks_w) * a.Wk, h0 = (r / a.chunks_w) * a.Hk;
+                mbar_wait(empty(s), ph ^ 1u);
+                mbar_expect_tx(full(s), (uint32_t)nhalf * 8192u + (uint32_t)ygroups * 2048u);
+                const uint32_t sa = smem0 + s * stage_bytes;
+                for (int b = 0; b < nhalf; ++b)
+                    tma_load_5d(sa + (uint32_t)b * 8192u, &mapX, full(s), a.dc[2 * u + b], w0, 0, h0 + a.dh[2 * u + b], a.n0 + img);
+                tma_load_5d(sa + 16384u, &mapDY, full(s), 0, w0, h0, 0, a.y_n0 + img);
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (nq > 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int i = 0; i < nq; ++i) {
+                const int q = q_begin + i;
+                const int w0 = ((q % a.chunks_per_img) % a.chunks_w) * a.Wk;
+                mbar_wait(full(s), ph);
+                const uint32_t sa = smem0 + s * stage_bytes;
+                for (int b = 0; b < nhalf; ++b)
+                    win_fix(sa + (uint32_t)b * 8192u, a.Wk, a.Hk, w0, a.W, a.C, a.k, a.pl, a.dc[2 * u + b], lane);
+                __syncwarp();
+                if (lane == 0) {
+                    tc_fence_after();
+                    // A: MN-major SWIZZLE_128B (64 elements contiguous, pixels at 128 B, 8-pixel groups at SBO = 1 KB, the second
+                    // 64-row half at LBO = 8 KB); B: MN-major SWIZZLE_32B 16-channel groups at LBO = 2 KB.  K = 16 pixels per MMA.
+                    const uint64_t adesc = make_smem_desc(sa, 8192, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), make_smem_desc32_mn(sa + 16384u + (uint32_t)k * 512u, 2048),
+                                  a.idesc, (uint32_t)((i | k) != 0));
+                    umma_commit(empty(s));
+                }
+                __syncwarp();
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
+            if (lane == 0) umma_commit(tfull);
+        }
+    } else if (nq > 0) {
+        const int q = warp & 3;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        const int row = q * 32 + lane, half = row >> 6, i = row & 63;
+        const int step = 2 * u + half;
+        bool live = step < a.steps;
+        float* dst = dw;
+        if (live) {
+            const int kh = step / a.nch, j = step - kh * a.nch;
+            const int e = 64 * j + i;
+            const int kw = e / a.C, ci = e - kw * a.C;
+            live = e < a.k * a.C && ci < a.Creal;
+            dst = dw + ((size_t)(kh * a.k + kw) * a.Creal + ci) * a.Cout;
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int c0 = 0; c0 < a.Cout; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + (uint32_t)c0, v);
+            const int cols = min(32, a.Cout - c0);
+            if (live) {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4)
+                    if (j4 * 4 < cols)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + 4 * j4),
+                                     "f"(__uint_as_float(v[4 * j4])), "f"(__uint_as_float(v[4 * j4 + 1])),
+                                     "f"(__uint_as_float(v[4 * j4 + 2])), "f"(__uint_as_float(v[4 * j4 + 3]))
+                                     : "memory");
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+// packed window weights (see tc_pack_win in conv_tc.h)
+__global__ void pack_win_kernel(const float* __restrict__ w, bf16* __restrict__ wf, int k, int C, int Creal, int n_rows, int npad,
+                                int Cin_w, int Cout_w, int flip) {
+    const int nch = (k * C + 63) / 64;
+    const size_t total = (size_t)k * nch * npad * 64;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx & 63);
+        size_t r = idx >> 6;
+        const int n = (int)(r % npad); r /= npad;
+        const int j = (int)(r % nch);
+        const int s = (int)(r / nch);
+        const int e = 64 * j + i, q = e / C, c = e - q * C;
+        float v = 0.f;
+        if (e < k * C && c < Creal && n < n_rows) {
+            // forward: rows = output channels, window element = (kw, ci);  flip: rows = input channels, element = (kw', co)
+            const int kh = flip ? k - 1 - s : s, kw = flip ? k - 1 - q : q;
+            const int ci = flip ? n : c, co = flip ? c : n;
+            v = w[(((size_t)kh * k + kw) * Cin_w + ci) * Cout_w + co];
+        }
+        wf[idx] = __float2bfloat16(v);
+    }
+}
+
+int tc_pack_win(const float* w, bf16* wf, int k, int C, int Creal, int n_rows, int npad, int Cin_w, int Cout_w, int flip,
+                cudaStream_t st) {
+    const int nch = (k * C + 63) / 64;
+    const size_t total = (size_t)k * nch * npad * 64;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    pack_win_kernel<<<blocks, 256, 0, st>>>(w, wf, k, C, Creal, n_rows, npad, Cin_w, Cout_w, flip);
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // weight packing: float32 HWIO -> bf16 [tap][Cout][Cin] (forward B operand) and bf16 [tap][Cin][Cout]
 // (data-gradient B operand; same order as HWIO)
 // ------------------------------------------------------------------------------------------
@@ -1096,19 +1321,24 @@ int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, const CUten
         CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     }
     const int total = a.nb * a.tiles_per_img * a.n_blocks_n;
     const int slots = (dual ? 2 : 1) * num_sms();
     int grid = total < slots ? total : slots;
     int pi = prof_begin(st);
-    if (dual) {
+    if (a.win_C > 0) {
+        if (dual) launch_pdl(conv_tc_kernel<false, true, true>, dim3(grid), dim3(TC_THREADS), smem, st, *mapA, *mapB, out, bias, a);
+        else launch_pdl(conv_tc_kernel<false, false, true>, dim3(grid), dim3(CONV_THREADS), smem, st, *mapA, *mapB, out, bias, a);
+    } else if (dual) {
         if (a.bk16) launch_pdl(conv_tc_kernel<true, true>, dim3(grid), dim3(TC_THREADS), smem, st, *mapA, *mapB, out, bias, a);
         else launch_pdl(conv_tc_kernel<false, true>, dim3(grid), dim3(TC_THREADS), smem, st, *mapA, *mapB, out, bias, a);
     } else {
         if (a.bk16) launch_pdl(conv_tc_kernel<true, false>, dim3(grid), dim3(CONV_THREADS), smem, st, *mapA, *mapB, out, bias, a);
         else launch_pdl(conv_tc_kernel<false, false>, dim3(grid), dim3(CONV_THREADS), smem, st, *mapA, *mapB, out, bias, a);
     }
-    prof_end(pi, st, flops, prof_key(1, a.n_taps, a.cchunks, a.bn, a.tiles_per_img, a.nb));
+    prof_end(pi, st, flops, prof_key(a.win_C > 0 ? 5 : 1, a.n_taps, a.cchunks, a.bn, a.tiles_per_img, a.nb));
     CG_LAUNCH_CHECK();
     return CG_OK;
 }
@@ -1161,6 +1391,48 @@ int tc_wgrad16_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* 
     int pi = prof_begin(st);
     launch_pdl(wgrad16_tc_kernel, dim3(a.m_blocks * splits), dim3(TC_THREADS), smem, st, *mapX, *mapDY, dw, a);
     prof_end(pi, st, flops, prof_key(4, a.n_taps, a.m_blocks, a.Cout, a.chunks_per_img, a.nb));
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+int tc_make_map_win(CUtensorMap* map, const void* x, int C, int k, int pl, int W, int H, int N, int box_w, int box_h) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { cg_set_error("cuTensorMapEncodeTiled is not available from the driver"); return CG_ERR_CUDA; }
+    if (C % 8) { cg_set_error("window view needs C %% 8 == 0 (got %d)", C); return CG_ERR_INVALID; }
+    const char* base = (const char*)x - (size_t)pl * C * 2;            // coordinate p of dim 1 = window starting at pixel p - pl
+    cuuint64_t dims[5] = {(cuuint64_t)k * C, (cuuint64_t)W, 1, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)box_w, 1, (cuuint32_t)box_h, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<char*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        cg_set_error("cuTensorMapEncodeTiled(window C=%d k=%d W=%d H=%d N=%d box %dx%d) failed: %d", C, k, W, H, N, box_w, box_h, (int)r);
+        return CG_ERR_CUDA;
+    }
+    return CG_OK;
+}
+
+int tc_wgradw_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* dw, TcWgradWArgs a, double flops, cudaStream_t st) {
+    const int stage = 16384 + (a.Cout / 16) * 2048;
+    const int per_sm = stage * 3 + 2048 <= 110 * 1024 ? 2 : 1;       // two resident CTAs overlap their issue chains (see tc_wgrad_launch)
+    int s = ((per_sm == 2 ? 110 : 227) * 1024 - 2048) / stage;
+    a.stages = s > 8 ? 8 : s;
+    a.idesc = make_idesc(128, a.Cout, 1, 1);
+    a.units = (a.steps + 1) / 2;
+    const int total_chunks = a.nb * a.chunks_per_img;
+    int splits = (2 * per_sm * num_sms()) / a.units;
+    if (splits < 1) splits = 1;
+    if (splits > total_chunks) splits = total_chunks;
+    a.splits = splits;
+    const size_t smem = (size_t)a.stages * stage + 1024 + 256;
+    static std::atomic<unsigned long long> attr_set{0};
+    if (cg_first_on_device(attr_set))
+        CG_CUDA(cudaFuncSetAttribute(wgradw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int pi = prof_begin(st);
+    launch_pdl(wgradw_tc_kernel, dim3(a.units * splits), dim3(TC_THREADS), smem, st, *mapX, *mapDY, dw, a);
+    prof_end(pi, st, flops, prof_key(6, a.steps, a.units, a.Cout, a.chunks_per_img, a.nb));
     CG_LAUNCH_CHECK();
     return CG_OK;
 }

@@ -4,6 +4,7 @@
 
 #include "common.h"
 
+enum { TC_MAX_STEPS = 64 };
 struct TcConvArgs {
     int n_taps, cchunks, bn, n_blocks_n;        // K loop = taps x 64-channel chunks; N tile
     int tiles_per_img, tiles_w, Wb, Hb;         // M tiling: 128 output pixels = Wb x Hb box
@@ -21,9 +22,33 @@ struct TcConvArgs {
     // pixels go to `out`; rpad_bwd_border then folds those few pixels
     bf16* out2;
     int fold_pad, fold_acc;
+    // window mode (conv_tc_kernel<.., WIN>): the A operand is the "window view" of an NHWC tensor with C % 8 == 0 -- row p of
+    // a K step is the 128 contiguous bytes that start at element dc[step] of the k*C-element window [pixel p-pl .. p-pl+k-1]
+    // of image row h0+dh[step] (tc_make_map_win).  Window pixels outside [0, W) are zeroed in shared memory before the MMAs.
+    int win_C, win_k, win_pl, win_W;
     // per K-loop tap: TMA coordinate offsets into the 5-D activation view (c, w, p, h, n) and the weight row block
-    short dc[49], dw[49], dp[49], dh[49], tb[49];
+    short dc[TC_MAX_STEPS], dw[TC_MAX_STEPS], dp[TC_MAX_STEPS], dh[TC_MAX_STEPS], tb[TC_MAX_STEPS];
 };
+
+// weight gradient in window mode (wgradw_tc_kernel): M = two 64-element window chunks (K steps 2u, 2u+1 of the forward
+// conv), N = Cout (16-channel groups of dY, SWIZZLE_32B), K = 64 pixels per stage, split over the pixel range
+struct TcWgradWArgs {
+    int steps, nch, k, C, Creal, Cout, units, splits, stages;
+    int n0, nb, y_n0;
+    int chunks_per_img, chunks_w, Wk, Hk;
+    int W, pl;
+    uint32_t idesc;
+    short dc[TC_MAX_STEPS], dh[TC_MAX_STEPS];
+};
+int tc_wgradw_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* dw, TcWgradWArgs a, double flops, cudaStream_t st);
+// window view of an NHWC bf16 tensor (C % 8 == 0): dims (k*C, W, 1, H, N), pixel stride C (overlapping rows), base shifted
+// left by `pl` pixels; box {64, box_w, 1, box_h, 1}, SWIZZLE_128B; elements beyond k*C are zero-filled by TMA
+int tc_make_map_win(CUtensorMap* map, const void* x, int C, int k, int pl, int W, int H, int N, int box_w, int box_h);
+// packed weights of the window form: wf[step][npad][64] with step = (kh, chunk j) and element e = 64j+i <-> (kw = e / C,
+// ci = e % C); flip = data-gradient orientation (w[k-1-kh][k-1-kw], rows = input channels); rows >= n_rows and elements
+// >= k*C (and channels >= Creal) are zero
+int tc_pack_win(const float* w, bf16* wf, int k, int C, int Creal, int n_rows, int npad, int Cin_w, int Cout_w, int flip,
+                cudaStream_t st);
 
 struct TcWgradArgs {
     int n_taps, a_blocks, b_blocks, bn, splits, stages;   // M = 128-row blocks of operand A, N = bn-column blocks of B
@@ -35,7 +60,7 @@ struct TcWgradArgs {
     int dy_off;                                 // halo of the dY buffer
     int Cin, Cout;
     uint32_t idesc;
-    short dc[49], dw[49], dp[49], dh[49];       // X coordinate offsets per tap (5-D view)
+    short dc[TC_MAX_STEPS], dw[TC_MAX_STEPS], dp[TC_MAX_STEPS], dh[TC_MAX_STEPS];       // X coordinate offsets per tap (5-D view)
 };
 
 // 5-D activation view (c, w, p, h, n).  parity = 0: dense NHWC tensor, p is a dummy dim of size 1.
@@ -47,7 +72,7 @@ struct TcWgrad16Args {
     int y_n0;
     int chunks_per_img, chunks_w, Wk, Hk;       // chunks_w may round up: out-of-range pixels are zero in both operands
     uint32_t idesc;
-    short dw[49], dh[49];
+    short dw[TC_MAX_STEPS], dh[TC_MAX_STEPS];
 };
 int tc_wgrad16_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* dw, TcWgrad16Args a, double flops,
                       cudaStream_t st);

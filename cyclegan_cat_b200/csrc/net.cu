@@ -137,6 +137,12 @@ int net_plan(const cg_net_s* net, int N, int H, int W, bool bwd, CallCtx* ctx) {
         }
         else if (kind == TC_S1_16) {
             ok = boxable(wo, ho, 128) && d.cin <= 256;      // dgrad N tile = Cin
+        } else if (kind == TC_S1_WIN) {
+            ok = boxable(wo, ho, 128);
+            if (ok && d.cin <= 4) {          // scratch: the input re-laid with 8 channels per pixel
+                const size_t need = align_up((size_t)N * hi * wi * 8 * 2, 1024);
+                if (need > ctx->tcs_bytes) ctx->tcs_bytes = need;
+            }
         } else if (kind == TC_IM2COL) {
             ok = boxable(wo, ho, 128) && boxable(wo, ho, 64);
         } else if (kind == TC_STEM) {
@@ -199,6 +205,15 @@ int net_pack(const cg_net_s* net, const float* params, void* packed, cudaStream_
         if (L.tc == TC_STEM) {
             CG_TRY(sp_pack_stem(params + L.w_off, (bf16*)((char*)packed + L.pk_f), L.d.k, L.d.cin, L.d.cout, st));
             CG_TRY(sp_pack_stem_d(params + L.w_off, (bf16*)((char*)packed + L.pk_d), L.d.k, L.d.cin, L.d.cout, st));
+            continue;
+        }
+        if (L.tc == TC_S1_WIN) {
+            const int cp = L.d.cin <= 4 ? 8 : L.d.cin;
+            CG_TRY(tc_pack_win(params + L.w_off, (bf16*)((char*)packed + L.pk_f), L.d.k, cp, L.d.cin, L.d.cout, L.d.cout, L.d.cin,
+                               L.d.cout, 0, st));
+            if (L.pk_d >= 0)
+                CG_TRY(tc_pack_win(params + L.w_off, (bf16*)((char*)packed + L.pk_d), L.d.k, L.d.cout, L.d.cout, L.d.cin, L.d.cin,
+                                   L.d.cin, L.d.cout, 1, st));
             continue;
         }
         if (L.tc == TC_IM2COL) {
@@ -454,6 +469,56 @@ int net_bind(CallCtx* c) {
                 CG_TRY(tc_make_map_act16(&t.mapDYw, dy, d.cout, wo, ho, c->N, a.Wk, a.Hk, d.cout / 16));
                 t.wg16 = true;
             }
+        } else if (L.tc == TC_S1_WIN) {
+            // stride-1 'same' (or 1x1) conv in window form: a K step = 64 contiguous elements of the k*C-element window of one
+            // kernel row; forward and data gradient are the same launch shape over x / dY
+            int pt = 0, pl = 0;
+            if (d.same) { same_pad(hi, k, 1, &pt); same_pad(wi, k, 1, &pl); }
+            const int cp = d.cin <= 4 ? 8 : d.cin;
+            const void* xs = d.cin <= 4 ? (const void*)c->tcs : x;
+            if (d.cin <= 4 && !c->tcs) { cg_set_error("net_bind: no scratch for the 8-channel input"); return CG_ERR_STATE; }
+            auto make_win = [&](TcConvLaunch& Ln, const void* in, int cin_k, const bf16* wmat, int n_out, int p_t, int p_l) -> int {
+                TcConvArgs& a = Ln.a;
+                memset(&a, 0, sizeof(a));
+                set_tiles(a, wo, ho);
+                const int nch = (k * cin_k + 63) / 64;
+                a.n_taps = k * nch; a.cchunks = 1;
+                a.bn = n_out; a.n_blocks_n = 1;
+                a.nb = c->N; a.out_H = ho; a.out_W = wo; a.Cout = n_out; a.out_sy = a.out_sx = 1;
+                a.b_rows_per_tap = n_out;
+                for (int kh = 0; kh < k; ++kh)
+                    for (int j = 0; j < nch; ++j) {
+                        const int st_ = kh * nch + j;
+                        a.tb[st_] = (short)st_; a.dc[st_] = (short)(64 * j); a.dh[st_] = (short)(kh - p_t);
+                    }
+                a.win_C = cin_k; a.win_k = k; a.win_pl = p_l; a.win_W = wo;
+                CG_TRY(tc_make_map_win(&Ln.mapA, in, cin_k, k, p_l, wo, ho, c->N, a.Wb, a.Hb));
+                CG_TRY(tc_make_map_2d(&Ln.mapB, wmat, 64, a.n_taps * n_out, n_out));
+                Ln.mapB2 = Ln.mapB;
+                return CG_OK;
+            };
+            t.fwd.assign(1, TcConvLaunch());
+            CG_TRY(make_win(t.fwd[0], xs, cp, wf, d.cout, pt, pl));
+            if (!c->bwd) continue;
+            if (L.pk_d >= 0) {
+                t.dgrad.assign(1, TcConvLaunch());
+                CG_TRY(make_win(t.dgrad[0], dy, d.cout, wd, d.cin, k - 1 - pt, k - 1 - pl));
+            }
+            const char* now = getenv("CG_DISABLE_WGRADW");       // test hook: CUDA-core weight gradient for these layers
+            if (!(now && now[0] == '1') && ((wo % 64 == 0) || (64 % wo == 0 && ho % (64 / wo) == 0))) {
+                TcWgradWArgs& a = t.waw;
+                memset(&a, 0, sizeof(a));
+                a.k = k; a.C = cp; a.Creal = d.cin; a.Cout = d.cout;
+                a.nch = (k * cp + 63) / 64; a.steps = k * a.nch;
+                a.Wk = wo % 64 == 0 ? 64 : wo; a.Hk = 64 / a.Wk;
+                a.chunks_w = wo / a.Wk; a.chunks_per_img = a.chunks_w * (ho / a.Hk);
+                a.W = wi; a.pl = pl;
+                for (int kh = 0; kh < k; ++kh)
+                    for (int j = 0; j < a.nch; ++j) { a.dc[kh * a.nch + j] = (short)(64 * j); a.dh[kh * a.nch + j] = (short)(kh - pt); }
+                CG_TRY(tc_make_map_win(&t.mapXw, xs, cp, k, pl, wi, hi, c->N, a.Wk, a.Hk));
+                CG_TRY(tc_make_map_act16(&t.mapDYw, dy, d.cout, wo, ho, c->N, a.Wk, a.Hk, d.cout / 16));
+                t.wgw = true;
+            }
         } else if (L.tc == TC_IM2COL) {
             if (!c->tcs) { cg_set_error("net_bind: no scratch for the unfolded input"); return CG_ERR_STATE; }
             const void* U = c->tcs;                         // [N][ho][wo][64]: the receptive field of every output pixel
@@ -664,7 +729,14 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
                 ConvGeom g = conv_geom(d, N, h, w, oh, ow);
                 const float* bias = L.b_off >= 0 ? params + L.b_off : nullptr;
                 const double fl = 2.0 * N * oh * ow * (double)d.cout * d.k * d.k * d.cin;
-                if (c->tc[i].on && L.tc == TC_IM2COL) {
+                if (c->tc[i].on && L.tc == TC_S1_WIN) {
+                    const TcConvLaunch& tl = c->tc[i].fwd[0];
+                    if (d.cin <= 4) CG_TRY(sp_pad_channels8((const bf16*)x, (bf16*)c->tcs, (size_t)N * h * w, d.cin, st));
+                    TcConvArgs a = tl.a;
+                    a.nb = N;
+                    a.stats = fused_stats;
+                    CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, (bf16*)y, bias, a, fl, st));
+                } else if (c->tc[i].on && L.tc == TC_IM2COL) {
                     const TcConvLaunch& tl = c->tc[i].fwd[0];
                     CG_TRY(sp_im2col((const bf16*)x, (bf16*)c->tcs, N, h, w, d.cin, oh, ow, d.k, d.stride, g.pt, g.pl, st));
                     TcConvArgs a = tl.a;
@@ -884,6 +956,32 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                             a.nb = nb;
                             CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, (bf16*)dx, nullptr, a,
                                                   2.0 * nb * oh * ow * (double)d.cout * d.k * d.k * d.cin, st));
+                        }
+                    }
+                    break;
+                }
+                if (c->tc[i].on && L.tc == TC_S1_WIN) {
+                    const double fl = 2.0 * nb * oh * ow * (double)d.cout * d.k * d.k * d.cin;
+                    if (grads) {
+                        if (c->tc[i].wgw) {
+                            if (d.cin <= 4) CG_TRY(sp_pad_channels8((const bf16*)A(tin), (bf16*)c->tcs, (size_t)nb * h * w, d.cin, st));
+                            TcWgradWArgs a = c->tc[i].waw;
+                            a.n0 = d.cin <= 4 ? 0 : n0; a.y_n0 = 0; a.nb = nb;      // dY lives in the (sub-batch relative) arena
+                            CG_TRY(tc_wgradw_launch(&c->tc[i].mapXw, &c->tc[i].mapDYw, grads + L.w_off, a, fl, st));
+                        } else {
+                            CG_TRY(k_conv_wgrad<T>(A(tin), dy, grads + L.w_off, g, st));
+                        }
+                        if (L.b_off >= 0 && !L.bias_grad_zero)
+                            CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
+                    }
+                    if (want_dx) {
+                        if (acc || c->tc[i].dgrad.empty()) {
+                            CG_TRY(k_conv_dgrad<T>(dy, params + L.w_off, nullptr, dx, g, acc, st));
+                        } else {
+                            const TcConvLaunch& tl = c->tc[i].dgrad[0];
+                            TcConvArgs a = tl.a;
+                            a.nb = nb;
+                            CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, (bf16*)dx, nullptr, a, fl, st));
                         }
                     }
                     break;

@@ -17,11 +17,13 @@ struct TcLayer {
     CUtensorMap mapXw, mapDYw;
     TcWgradArgs wa;
     TcWgrad16Args wa16;
+    TcWgradWArgs waw;
     bool wg16 = false;
+    bool wgw = false;                   // TC_S1_WIN: the window weight-gradient kernel applies (64-pixel chunks tile the grid)
     int wg_x_is_dy = 0;                 // Conv2DTranspose: the "X" operand of the weight gradient is dY
     size_t sc_tmp = 0;                  // TC_STEM / TC_HEAD: offset of the fp32 weight-gradient staging buffer in the scratch
 };
-enum { TC_NONE = 0, TC_S1_VALID = 1, TC_CONV_S2 = 2, TC_CONVT_S2 = 3, TC_STEM = 4, TC_HEAD = 5, TC_S1_16 = 6, TC_IM2COL = 7 };
+enum { TC_NONE = 0, TC_S1_VALID = 1, TC_CONV_S2 = 2, TC_CONVT_S2 = 3, TC_STEM = 4, TC_HEAD = 5, TC_S1_16 = 6, TC_IM2COL = 7, TC_S1_WIN = 8 };
 
 struct LayerInfo {
     cg_layer_desc d;

@@ -165,7 +165,7 @@ static int trainer_layout(cg_trainer_t tr, int B, int H, int W, bool assign) {
     }
     const size_t es = es_of(tr);
     const size_t img = (size_t)H * W * 3 * es, dout = (size_t)tr->d_h * tr->d_w * tr->d_c * es;
-    size_t off = 0;
+    size_t off = 4096;          // slack before the first tensor: window views start a few pixels before their tensor
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
     size_t oF1 = take(tr->F1.act_bytes), oF2 = take(tr->F2.act_bytes), oC1 = take(tr->C1.act_bytes),
            oC2 = take(tr->C2.act_bytes), oDA = take(tr->DA.act_bytes), oDB = take(tr->DB.act_bytes);
@@ -187,6 +187,7 @@ static int trainer_layout(cg_trainer_t tr, int B, int H, int W, bool assign) {
     for (CallCtx* c : {&tr->F1, &tr->F2, &tr->C1, &tr->C2, &tr->DA, &tr->DB}) if (c->tcs_bytes > tcs) tcs = c->tcs_bytes;
     tr->o_tcs = take(align_up(tcs, 1024));
     tr->o_tcs2 = tr->dual ? take(align_up(tcs, 1024)) : tr->o_tcs;
+    off += 4096;                // ... and end a few pixels after it
     tr->total = off;
     if (assign) {
         if (off > tr->ws_bytes) { cg_set_error("trainer workspace %zu < required %zu", tr->ws_bytes, off); return CG_ERR_WORKSPACE; }

@@ -66,6 +66,17 @@ def test_train_step_layer_by_layer(gen, disc, size, batch, loss, mode):
 
 
 @pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_c2_full_size_gradients(mode):
+    """configs/cycle.yaml verbatim (C2: U-Net generator + U-Net PatchGAN discriminator) at its full 256x256 size, batch 1:
+    every stored tensor, the losses, all variable gradients and the optimizer update.  The geometry the window-form
+    kernels (conv_tc_kernel<WIN>, wgradw_tc_kernel) run at in the C2 / C5 benchmarks."""
+    dtype = torch.float64 if mode == "fp32" else torch.float32
+    gan, o = LW.gan_pair(C.UNET_G, C.UNET_D, mode, dtype=dtype)
+    a, b = synthetic_batch(1, 256)
+    LW.check_train_step(gan, o, a, b, mode, f"step/C2/256x1/{mode}", apply=True)
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
 def test_c3_full_size_gradients(mode):
     """The headline configuration at its benchmark geometry (C3: resnet_generator{filters:64} + simple_discriminator
     [64,128,256,512], 256x256; batch 1 so that the CPU oracle finishes in a minute or two): every stored tensor of the
@@ -137,13 +148,16 @@ def _tc_nets():
         ("down-up-k3", _updown_net(128, 256, 3), (2, 32, 32)),    # stride-2 parity view fwd, parity-class dgrad, convT classes
         ("down-up-k4", _updown_net(64, 128, 4), (2, 32, 64)),     # wgrad_tc transposed roles (Cin = 64)
         ("stem-head-64", _stem_head_net(64), (2, 32, 64)),        # unfolded 7x7 stem / head, stack2 weight gradient
-        ("double-conv-k4", _double_conv_net(16, 32, 4), (2, 32, 32)),     # 16-channel-group conv + wgrad16_tc
+        ("double-conv-k4", _double_conv_net(16, 32, 4), (2, 32, 32)),     # window-form conv (fwd + dgrad) + wgradw_tc
         ("double-conv-k5", _double_conv_net(80, 32, 5), (1, 32, 64)),
         ("double-conv-k3", _double_conv_net(192, 128, 3), (2, 16, 16)),
+        ("unet-first-k4", _double_conv_net(3, 16, 4), (2, 64, 128)),      # 3-channel image-side layer: 8-channel re-layout
+        ("unet-first-k7", _double_conv_net(3, 16, 7), (1, 128, 256)),     # cycle.yaml discriminator level 0 at full width
+        ("double-conv-k4-256", _double_conv_net(16, 16, 4), (1, 64, 256)),   # two 128-pixel tiles per row: one edge each
     ]
 
 
-@pytest.mark.parametrize("case", range(8))
+@pytest.mark.parametrize("case", range(11))
 def test_tc_kernels_against_fp64(case):
     """wgrad_tc_kernel, flat-mode and parity-class data gradients, transposed-conv classes, the stem / head forms and the
     16-channel-group kernels, each inside a two-conv net whose weights and input are exactly representable in bf16 and
