@@ -163,7 +163,8 @@ def test_tc_kernels_against_fp64(case):
     16-channel-group kernels, each inside a two-conv net whose weights and input are exactly representable in bf16 and
     whose every tensor is forced into the fp64 oracle: what is left is fp32 accumulation order and ONE bf16 rounding per
     stored tensor (two for the thin-output forms of the 7x7 layers, whose unfolded intermediate is bf16 as well).
-    Gates: every layer output within one bf16 ulp (2^-8 = 3.9e-3), every gradient within 1.5 ulp (6e-3)."""
+    Gates: every layer output within one bf16 ulp (2^-8 = 3.9e-3), every kernel / input gradient within 1.5 ulp (6e-3);
+    the per-channel vectors (gamma, beta, bias: sums over all pixels with heavy cancellation) within 1e-2."""
     from cyclegan_cat_b200.runtime import Model
     name, graph, (n, h, w) = _tc_nets()[case]
     m = Model(graph, name=name, mode="bf16", seed=0)
@@ -176,4 +177,5 @@ def test_tc_kernels_against_fp64(case):
     dy = LW.bf16_round(rng.normal(0, 1, m.out_shape(n, h, w)))
     out = LW.check_single_net(m, o, x, dy, "bf16", _net_grads, f"kernel/{name}")
     assert out["dx"] <= 6e-3, (name, "dx", out["dx"])
-    assert max(out["grads"]) <= 6e-3, (name, out["grads"])
+    for e, shape in zip(out["grads"], out["shapes"]):
+        assert e <= (6e-3 if len(shape) == 4 else 1e-2), (name, shape, e)
