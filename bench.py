@@ -309,6 +309,138 @@ def run_infer(args, wl):
 
 
 # ---------------------------------------------------------------------------------------------
+# short loops attached to the default line: BASELINE.json configs[1] (C2), configs[4] (C5), and C3 at the per-GPU batch of
+# configs[3] (global batch 64 split over the ranks: the strong-scaling point next to the weak headline)
+# ---------------------------------------------------------------------------------------------
+# HBM-side roofline of the narrow-N U-Net workloads: per conv-output element the forward must at least write
+# it (conv), read and re-write it (instance norm + activation) and read it again (next conv) = 8 bytes in bf16; the backward
+# reads x and dy for the norm's reduction and again for its apply, writes the norm's dx, reads it (weight gradient) and
+# writes / reads the conv's dx = 16 bytes.  Train step: 6 generator + 4 discriminator calls forward, all of them backward
+# (the discriminators twice on the fake half) -> 24 bytes x elements x calls; inference: 8 bytes x elements.
+def hbm_bytes_train(gen_graph, disc_graph, size, batch):
+    eg, ed = gen_graph.conv_out_elems(size, size), disc_graph.conv_out_elems(size, size)
+    return batch * (6 * eg * 24 + 4 * ed * 24 + 2 * ed * 8)
+
+
+def quick_train(wl, mode, batch, steps, warmup, world, barrier, max_over_ranks, rank):
+    """Device-resident and end-to-end train-step timing of one workload (no per-launch events)."""
+    import torch
+    from cyclegan_cat_b200.cyclegan.model import CycleGan
+    S = wl["size"]
+    mc = bunch(name="bench", new=True, location="/tmp/cg_b200_bench", generator=dict(wl["gen"]),
+               discriminator=dict(wl["disc"]), loss="mse", loss_weights=dict(LOSS_WEIGHTS))
+    tc = bunch(epochs=1, batch_size=batch, image_size=S, g_opt=dict(ADAM), d_opt=dict(ADAM),
+               summary=dict(samples=1, images=5, model=20))
+    gan = CycleGan(mc, tc, mode=mode)
+    for i, n in enumerate((gan.g_AB, gan.g_BA, gan.d_A, gan.d_B)):
+        n.initialize(42 + i)
+    gan.prepare(batch, S, S)
+    if world > 1:
+        gan.enable_data_parallel()
+    a_np, b_np = synthetic_batch(batch, S, rank)
+    a_dev, b_dev = torch.from_numpy(a_np).cuda(), torch.from_numpy(b_np).cuda()
+    a_pin, b_pin = torch.from_numpy(a_np).pin_memory(), torch.from_numpy(b_np).pin_memory()
+    for _ in range(max(warmup, 3)):
+        gan.train_step(a_dev, b_dev)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        gan.train_step(a_dev, b_dev)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    for _ in range(2):
+        gan.train_step(a_pin, b_pin)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(steps):
+        mm = gan.train_step(a_pin, b_pin)
+        _ = [float(v) for v in mm.values()]
+    e3.record()
+    barrier()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    fl = step_flops(gan.g_AB.graph, gan.d_A.graph, S) * batch
+    hb = hbm_bytes_train(gan.g_AB.graph, gan.d_A.graph, S, batch)
+    pk = peaks()
+    ms_step = ms / steps
+    out = dict(workload=wl["name"], batch_per_gpu=batch, global_batch=batch * world, steps=steps,
+               value=world * batch * steps / (ms * 1e-3), unit=UNIT, ms_per_step=ms_step,
+               e2e=dict(value=world * batch * steps / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=int(2 * a_np.nbytes),
+                        d2h_bytes_per_step=24, ms_per_step=ms_e2e / steps),
+               roofline=dict(tensor=dict(achieved=fl / (ms_step * 1e-3) / 1e12, peak=pk["tflops"], unit="TFLOP/s",
+                                         frac=fl / (ms_step * 1e-3) / 1e12 / pk["tflops"], flops_per_step=fl),
+                             hbm=dict(achieved=hb / (ms_step * 1e-3) / 1e9, peak=pk["hbm"], unit="GB/s",
+                                      frac=hb / (ms_step * 1e-3) / 1e9 / pk["hbm"], algorithmic_bytes_per_step=hb,
+                                      model="24 B per conv-output element and model call (bench.py hbm_bytes_train)"),
+                             note="whole-step figures: algorithmic FLOPs / bytes of the step over its measured time"))
+    del gan
+    torch.cuda.empty_cache()
+    return out
+
+
+def quick_infer(wl, mode, batch, steps, warmup, world, barrier, max_over_ranks, rank):
+    """Generator inference (predict.py path): device-resident calls and the uint8-to-uint8 end-to-end loop."""
+    import torch
+    from cyclegan_cat_b200 import _lib
+    from cyclegan_cat_b200.cyclegan.model import create_model
+    from cyclegan_cat_b200.runtime import _ptr, _stream_ptr
+    from cyclegan_cat_b200.transform import data_load as DL
+    S = wl["size"]
+    lib = _lib.load()
+    g = create_model(wl["gen"], mode=mode)
+    g.initialize(42)
+    u8 = np.random.RandomState(1234 + rank).randint(0, 256, size=(batch, S, S, 3)).astype(np.uint8)
+    u8_pin = torch.from_numpy(u8).pin_memory()
+    x_dev = DL.normalize_device(u8).torch
+    out_pin = torch.empty((batch, S, S, 3), dtype=torch.uint8).pin_memory()
+    out_dev = torch.empty((batch, S, S, 3), dtype=torch.uint8, device="cuda")
+
+    def e2e_once():
+        xd = u8_pin.cuda(non_blocking=True)
+        y = g(DL.normalize_device(xd))
+        _lib.check(lib.cg_postprocess_u8(_ptr(y.torch), _ptr(out_dev), out_dev.numel(), _stream_ptr(torch)), "post")
+        out_pin.copy_(out_dev, non_blocking=True)
+    for _ in range(max(warmup, 3)):
+        g(x_dev)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        g(x_dev)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    for _ in range(2):
+        e2e_once()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(steps):
+        e2e_once()
+    e3.record()
+    barrier()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    pk = peaks()
+    ms_step = ms / steps
+    fl = g.graph.flops(S, S) * batch
+    hb = g.graph.conv_out_elems(S, S) * 8 * batch
+    out = dict(workload=wl["name"], metric=INFER_METRIC, batch_per_gpu=batch, steps=steps,
+               value=world * batch * steps / (ms * 1e-3), unit=UNIT, ms_per_step=ms_step,
+               e2e=dict(value=world * batch * steps / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=int(u8.nbytes),
+                        d2h_bytes_per_step=int(u8.nbytes), ms_per_step=ms_e2e / steps),
+               roofline=dict(tensor=dict(achieved=fl / (ms_step * 1e-3) / 1e12, peak=pk["tflops"], unit="TFLOP/s",
+                                         frac=fl / (ms_step * 1e-3) / 1e12 / pk["tflops"], flops_per_step=fl),
+                             hbm=dict(achieved=hb / (ms_step * 1e-3) / 1e9, peak=pk["hbm"], unit="GB/s",
+                                      frac=hb / (ms_step * 1e-3) / 1e9 / pk["hbm"], algorithmic_bytes_per_step=hb,
+                                      model="8 B per conv-output element (conv write, norm read + write, next conv read)")))
+    del g
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 def run_gpu(args, wl):
@@ -417,6 +549,18 @@ def run_gpu(args, wl):
     barrier()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
 
+    # ---- attached workloads (default C3 invocation only; every rank takes part, rank 0 reports) ------------------
+    extra = {}
+    g_graph, d_graph = gan.g_AB.graph, gan.d_A.graph
+    if args.workload == "C3" and not args.batch and not args.no_extra and args.mode == "bf16":
+        del gan
+        torch.cuda.empty_cache()
+        q = dict(mode=args.mode, warmup=3, world=world, barrier=barrier, max_over_ranks=max_over_ranks, rank=rank)
+        if 64 % world == 0:      # BASELINE.json configs[3]: global batch 64 over the ranks (strong scaling; at N = 1 its baseline)
+            extra["c4_strong"] = quick_train(WORKLOADS["C3"], batch=64 // world, steps=4 if world == 1 else 8, **q)
+            extra["c4_strong"]["scaling"] = "strong"
+        extra["C2"] = quick_train(WORKLOADS["C2"], batch=WORKLOADS["C2"]["batch"], steps=10, **q)
+        extra["C5"] = quick_infer(WORKLOADS["C5"], batch=WORKLOADS["C5"]["batch"], steps=5, **q)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -428,7 +572,7 @@ def run_gpu(args, wl):
         import csv
         agg = {}
         for r in csv.DictReader(open(prof_csv)):
-            if int(r["kind"]) not in (1, 2):
+            if int(r["kind"]) not in (1, 2, 5):          # conv_tc_kernel: 64-channel form, pair kernel, window form
                 continue
             k = (int(r["taps"]), int(r["cchunks"]), int(r["bn"]))
             a = agg.setdefault(k, [0.0, 0.0, 0])
@@ -443,18 +587,21 @@ def run_gpu(args, wl):
         os.remove(prof_csv)
     except Exception as e:      # the aggregate below is still reported
         dom["geom"] = f"unavailable ({type(e).__name__})"
-    traffic = None
+    # dram bytes per launch from the committed `ncu --set full` capture: valid only for the geometry it was taken at (the C3
+    # trunk conv, 32-image launch); any other dominant kernel reports null rather than a number measured elsewhere
+    traffic, traffic_source = None, None
     tp = os.path.join(ROOT, "profiles", "r01_tc_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and args.workload == "C3" and B == 16 and dom["geom"] == "taps=9 k_chunks=4 n_tile=256":
         traffic = json.load(open(tp)).get("conv_tc_kernel_trunk_fwd_dram_bytes_per_launch")
-    fl_pair = step_flops(gan.g_AB.graph, gan.d_A.graph, S)
+        traffic_source = "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one 32-image trunk launch (profiles/r01_ncu_trunk_conv.md)"
+    fl_pair = step_flops(g_graph, d_graph, S)
     ms_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
     step_tflops = fl_pair * B / (ms_step * 1e-3) / 1e12
     roof = dict(bound="tensor", kernel=f"conv_tc_kernel (tcgen05 implicit-GEMM conv, forward + data gradient) at {dom['geom']}",
                 achieved=(dom["flops"] / (dom["ms"] * 1e-3) / 1e12) if dom["ms"] > 0 else None, peak=pk["tflops"],
-                unit="TFLOP/s", frac=None, traffic=traffic, launches=int(dom["n"]),
+                unit="TFLOP/s", frac=None, traffic=traffic, traffic_source=traffic_source, launches=int(dom["n"]),
                 avg_launch_ms=(dom["ms"] / dom["n"]) if dom["n"] else None,
                 share_of_step=(dom["ms"] / ms_step) if ms_total > 0 else None, peak_source=pk["source"],
                 algorithmic_flops_per_launch=(dom["flops"] / dom["n"]) if dom["n"] else None,
@@ -480,6 +627,8 @@ def run_gpu(args, wl):
         r = time_oracle(c1, steps=2, warmup=1, budget_s=60.0)
         line["cpu_baseline"] = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"],
                                     ms_per_step=r["ms_per_step"])
+    if extra:
+        line["workloads"] = extra
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -496,6 +645,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-input loop (profiling runs)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the attached C2 / C5 / c4_strong loops of the default C3 run")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if wl["disc"] is None:

@@ -936,7 +936,11 @@ wgradw_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ygroups = a.Cout / 16;
-    const uint32_t stage_bytes = 16384u + (uint32_t)ygroups * 2048u;
+    // a unit = `halves` (2 or 4) window chunks = 1 or 2 accumulators of 128 rows that share ONE dY load and one barrier
+    // round trip per 64-pixel stage (the per-stage chain of the issuing thread, not the tensor pipe, bounds these layers)
+    const int halves = a.halves;
+    const uint32_t a_bytes = (uint32_t)halves * 8192u;
+    const uint32_t stage_bytes = a_bytes + (uint32_t)ygroups * 2048u;
     const int S = a.stages;
     const uint32_t bar0 = smem0 + S * stage_bytes;
     auto full = [&](int s) { return bar0 + 8u * s; };
@@ -944,6 +948,7 @@ wgradw_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     const uint32_t tfull = bar0 + 8u * (2 * S);
     const uint32_t tmem_slot = bar0 + 8u * (2 * S + 1);
     volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    const uint32_t acc_cols = a.Cout <= 128 ? 128u : 256u;      // column pitch of the accumulators (halves == 4 needs Cout <= 128)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapX);
@@ -966,7 +971,9 @@ wgradw_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     const int q_begin = split * per;
     const int q_end = min(total_chunks, q_begin + per);
     const int nq = q_end - q_begin;
-    const int nhalf = min(2, a.steps - 2 * u);          // live 64-row halves of this unit
+    const int step0 = halves * u;
+    const int nhalf = min(halves, a.steps - step0);          // live 64-row halves of this unit
+    const int npair = (nhalf + 1) / 2;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -978,8 +985,8 @@ wgradw_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 mbar_expect_tx(full(s), (uint32_t)nhalf * 8192u + (uint32_t)ygroups * 2048u);
                 const uint32_t sa = smem0 + s * stage_bytes;
                 for (int b = 0; b < nhalf; ++b)
-                    tma_load_5d(sa + (uint32_t)b * 8192u, &mapX, full(s), a.dc[2 * u + b], w0, 0, h0 + a.dh[2 * u + b], a.n0 + img);
-                tma_load_5d(sa + 16384u, &mapDY, full(s), 0, w0, h0, 0, a.y_n0 + img);
+                    tma_load_5d(sa + (uint32_t)b * 8192u, &mapX, full(s), a.dc[step0 + b], w0, 0, h0 + a.dh[step0 + b], a.n0 + img);
+                tma_load_5d(sa + a_bytes, &mapDY, full(s), 0, w0, h0, 0, a.y_n0 + img);
                 if (++s == S) { s = 0; ph ^= 1u; }
             }
         }
@@ -992,17 +999,19 @@ wgradw_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 mbar_wait(full(s), ph);
                 const uint32_t sa = smem0 + s * stage_bytes;
                 for (int b = 0; b < nhalf; ++b)
-                    win_fix(sa + (uint32_t)b * 8192u, a.Wk, a.Hk, w0, a.W, a.C, a.k, a.pl, a.dc[2 * u + b], lane);
+                    win_fix(sa + (uint32_t)b * 8192u, a.Wk, a.Hk, w0, a.W, a.C, a.k, a.pl, a.dc[step0 + b], lane);
                 __syncwarp();
                 if (lane == 0) {
                     tc_fence_after();
                     // A: MN-major SWIZZLE_128B (64 elements contiguous, pixels at 128 B, 8-pixel groups at SBO = 1 KB, the second
                     // 64-row half at LBO = 8 KB); B: MN-major SWIZZLE_32B 16-channel groups at LBO = 2 KB.  K = 16 pixels per MMA.
-                    const uint64_t adesc = make_smem_desc(sa, 8192, 1024);
+                    for (int pi = 0; pi < npair; ++pi) {
+                        const uint64_t adesc = make_smem_desc(sa + (uint32_t)pi * 16384u, 8192, 1024);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), make_smem_desc32_mn(sa + 16384u + (uint32_t)k * 512u, 2048),
-                                  a.idesc, (uint32_t)((i | k) != 0));
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tmem_base + (uint32_t)pi * acc_cols, adesc + (uint64_t)(k * 128),
+                                      make_smem_desc32_mn(sa + a_bytes + (uint32_t)k * 512u, 2048), a.idesc, (uint32_t)((i | k) != 0));
+                    }
                     umma_commit(empty(s));
                 }
                 __syncwarp();
@@ -1015,29 +1024,31 @@ wgradw_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         mbar_wait(tfull, 0);
         tc_fence_after();
         const int row = q * 32 + lane, half = row >> 6, i = row & 63;
-        const int step = 2 * u + half;
-        bool live = step < a.steps;
-        float* dst = dw;
-        if (live) {
-            const int kh = step / a.nch, j = step - kh * a.nch;
-            const int e = 64 * j + i;
-            const int kw = e / a.C, ci = e - kw * a.C;
-            live = e < a.k * a.C && ci < a.Creal;
-            dst = dw + ((size_t)(kh * a.k + kw) * a.Creal + ci) * a.Cout;
-        }
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        for (int c0 = 0; c0 < a.Cout; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(taddr + (uint32_t)c0, v);
-            const int cols = min(32, a.Cout - c0);
+        for (int pi = 0; pi < npair; ++pi) {
+            const int step = step0 + 2 * pi + half;
+            bool live = step < a.steps;
+            float* dst = dw;
             if (live) {
+                const int kh = step / a.nch, j = step - kh * a.nch;
+                const int e = 64 * j + i;
+                const int kw = e / a.C, ci = e - kw * a.C;
+                live = e < a.k * a.C && ci < a.Creal;
+                dst = dw + ((size_t)(kh * a.k + kw) * a.Creal + ci) * a.Cout;
+            }
+            const uint32_t taddr = tmem_base + (uint32_t)pi * acc_cols + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < a.Cout; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)c0, v);
+                const int cols = min(32, a.Cout - c0);
+                if (live) {
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4)
-                    if (j4 * 4 < cols)
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + 4 * j4),
-                                     "f"(__uint_as_float(v[4 * j4])), "f"(__uint_as_float(v[4 * j4 + 1])),
-                                     "f"(__uint_as_float(v[4 * j4 + 2])), "f"(__uint_as_float(v[4 * j4 + 3]))
-                                     : "memory");
+                    for (int j4 = 0; j4 < 8; ++j4)
+                        if (j4 * 4 < cols)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + 4 * j4),
+                                         "f"(__uint_as_float(v[4 * j4])), "f"(__uint_as_float(v[4 * j4 + 1])),
+                                         "f"(__uint_as_float(v[4 * j4 + 2])), "f"(__uint_as_float(v[4 * j4 + 3]))
+                                         : "memory");
+                }
             }
         }
     }
@@ -1049,12 +1060,19 @@ wgradw_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     }
 }
 
-// packed window weights (see tc_pack_win in conv_tc.h)
-__global__ void pack_win_kernel(const float* __restrict__ w, bf16* __restrict__ wf, int k, int C, int Creal, int n_rows, int npad,
-                                int Cin_w, int Cout_w, int flip) {
+// packed window weights (see tc_pack_win in conv_tc.h); all window layers of a net in ONE launch: a block finds its
+// job in the prefix table and packs a grid-stride share of it
+__global__ void pack_win_multi_kernel(const __grid_constant__ TcPackWinJobs jobs) {
+    int jb = 0;
+    while (jb + 1 < jobs.n && (int)blockIdx.x >= jobs.block0[jb + 1]) ++jb;
+    const float* __restrict__ w = jobs.w[jb];
+    bf16* __restrict__ wf = jobs.wf[jb];
+    const int k = jobs.k[jb], C = jobs.C[jb], Creal = jobs.Creal[jb], n_rows = jobs.n_rows[jb], npad = jobs.npad[jb];
+    const int Cin_w = jobs.cin_w[jb], Cout_w = jobs.cout_w[jb], flip = jobs.flip[jb];
     const int nch = (k * C + 63) / 64;
     const size_t total = (size_t)k * nch * npad * 64;
-    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int b = blockIdx.x - jobs.block0[jb], nb = jobs.block0[jb + 1] - jobs.block0[jb];
+    for (size_t idx = b * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)nb * blockDim.x) {
         const int i = (int)(idx & 63);
         size_t r = idx >> 6;
         const int n = (int)(r % npad); r /= npad;
@@ -1072,14 +1090,30 @@ __global__ void pack_win_kernel(const float* __restrict__ w, bf16* __restrict__ 
     }
 }
 
-int tc_pack_win(const float* w, bf16* wf, int k, int C, int Creal, int n_rows, int npad, int Cin_w, int Cout_w, int flip,
-                cudaStream_t st) {
-    const int nch = (k * C + 63) / 64;
-    const size_t total = (size_t)k * nch * npad * 64;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 4) blocks = 148 * 4;
-    pack_win_kernel<<<blocks, 256, 0, st>>>(w, wf, k, C, Creal, n_rows, npad, Cin_w, Cout_w, flip);
+int tc_pack_win_flush(TcPackWinJobs& jobs, cudaStream_t st) {
+    if (jobs.n == 0) return CG_OK;
+    int total = 0;
+    for (int j = 0; j < jobs.n; ++j) {
+        const int nch = (jobs.k[j] * jobs.C[j] + 63) / 64;
+        const size_t n = (size_t)jobs.k[j] * nch * jobs.npad[j] * 64;
+        int blocks = (int)((n + 1023) / 1024);
+        if (blocks > 148) blocks = 148;
+        jobs.block0[j] = total;
+        total += blocks;
+    }
+    jobs.block0[jobs.n] = total;
+    pack_win_multi_kernel<<<total, 256, 0, st>>>(jobs);
     CG_LAUNCH_CHECK();
+    jobs.n = 0;
+    return CG_OK;
+}
+
+int tc_pack_win(TcPackWinJobs& jobs, const float* w, bf16* wf, int k, int C, int Creal, int n_rows, int npad, int Cin_w,
+                int Cout_w, int flip, cudaStream_t st) {
+    const int j = jobs.n++;
+    jobs.w[j] = w; jobs.wf[j] = wf; jobs.k[j] = k; jobs.C[j] = C; jobs.Creal[j] = Creal; jobs.n_rows[j] = n_rows;
+    jobs.npad[j] = npad; jobs.cin_w[j] = Cin_w; jobs.cout_w[j] = Cout_w; jobs.flip[j] = flip;
+    if (jobs.n == TC_PACK_MAX) return tc_pack_win_flush(jobs, st);
     return CG_OK;
 }
 
@@ -1415,12 +1449,15 @@ int tc_make_map_win(CUtensorMap* map, const void* x, int C, int k, int pl, int W
 }
 
 int tc_wgradw_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* dw, TcWgradWArgs a, double flops, cudaStream_t st) {
-    const int stage = 16384 + (a.Cout / 16) * 2048;
+    static const int force_halves = [] { const char* e = getenv("CG_WGRADW_HALVES"); return e ? atoi(e) : 0; }();    // A/B hook
+    a.halves = (a.Cout <= 128 && a.steps >= 4) ? 4 : 2;
+    if (force_halves == 2) a.halves = 2;
+    const int stage = a.halves * 8192 + (a.Cout / 16) * 2048;
     const int per_sm = stage * 3 + 2048 <= 110 * 1024 ? 2 : 1;       // two resident CTAs overlap their issue chains (see tc_wgrad_launch)
     int s = ((per_sm == 2 ? 110 : 227) * 1024 - 2048) / stage;
     a.stages = s > 8 ? 8 : s;
     a.idesc = make_idesc(128, a.Cout, 1, 1);
-    a.units = (a.steps + 1) / 2;
+    a.units = (a.steps + a.halves - 1) / a.halves;
     const int total_chunks = a.nb * a.chunks_per_img;
     int splits = (2 * per_sm * num_sms()) / a.units;
     if (splits < 1) splits = 1;

@@ -34,6 +34,7 @@ struct TcConvArgs {
 // conv), N = Cout (16-channel groups of dY, SWIZZLE_32B), K = 64 pixels per stage, split over the pixel range
 struct TcWgradWArgs {
     int steps, nch, k, C, Creal, Cout, units, splits, stages;
+    int halves;                                 // window chunks per unit: 2 (one accumulator) or 4 (two, Cout <= 128)
     int n0, nb, y_n0;
     int chunks_per_img, chunks_w, Wk, Hk;
     int W, pl;
@@ -47,8 +48,15 @@ int tc_make_map_win(CUtensorMap* map, const void* x, int C, int k, int pl, int W
 // packed weights of the window form: wf[step][npad][64] with step = (kh, chunk j) and element e = 64j+i <-> (kw = e / C,
 // ci = e % C); flip = data-gradient orientation (w[k-1-kh][k-1-kw], rows = input channels); rows >= n_rows and elements
 // >= k*C (and channels >= Creal) are zero
-int tc_pack_win(const float* w, bf16* wf, int k, int C, int Creal, int n_rows, int npad, int Cin_w, int Cout_w, int flip,
-                cudaStream_t st);
+// batched: tc_pack_win queues a job (flushing when the table is full), tc_pack_win_flush launches what is queued
+struct TcPackWinJobs {
+    const float* w[32]; bf16* wf[32];
+    int k[32], C[32], Creal[32], n_rows[32], npad[32], cin_w[32], cout_w[32], flip[32], block0[33];
+    int n;
+};
+int tc_pack_win(TcPackWinJobs& jobs, const float* w, bf16* wf, int k, int C, int Creal, int n_rows, int npad, int Cin_w,
+                int Cout_w, int flip, cudaStream_t st);
+int tc_pack_win_flush(TcPackWinJobs& jobs, cudaStream_t st);
 
 struct TcWgradArgs {
     int n_taps, a_blocks, b_blocks, bn, splits, stages;   // M = 128-row blocks of operand A, N = bn-column blocks of B

@@ -200,6 +200,8 @@ int net_pack(const cg_net_s* net, const float* params, void* packed, cudaStream_
     if (!packed) { cg_set_error("net_pack: no packed-weight buffer"); return CG_ERR_STATE; }
     TcPackJobs jobs;
     jobs.n = 0;
+    TcPackWinJobs wjobs;
+    wjobs.n = 0;
     for (const LayerInfo& L : net->layers) {
         if (!L.tc) continue;
         if (L.tc == TC_STEM) {
@@ -209,11 +211,11 @@ int net_pack(const cg_net_s* net, const float* params, void* packed, cudaStream_
         }
         if (L.tc == TC_S1_WIN) {
             const int cp = L.d.cin <= 4 ? 8 : L.d.cin;
-            CG_TRY(tc_pack_win(params + L.w_off, (bf16*)((char*)packed + L.pk_f), L.d.k, cp, L.d.cin, L.d.cout, L.d.cout, L.d.cin,
-                               L.d.cout, 0, st));
+            CG_TRY(tc_pack_win(wjobs, params + L.w_off, (bf16*)((char*)packed + L.pk_f), L.d.k, cp, L.d.cin, L.d.cout, L.d.cout,
+                               L.d.cin, L.d.cout, 0, st));
             if (L.pk_d >= 0)
-                CG_TRY(tc_pack_win(params + L.w_off, (bf16*)((char*)packed + L.pk_d), L.d.k, L.d.cout, L.d.cout, L.d.cin, L.d.cin,
-                                   L.d.cin, L.d.cout, 1, st));
+                CG_TRY(tc_pack_win(wjobs, params + L.w_off, (bf16*)((char*)packed + L.pk_d), L.d.k, L.d.cout, L.d.cout, L.d.cin,
+                                   L.d.cin, L.d.cin, L.d.cout, 1, st));
             continue;
         }
         if (L.tc == TC_IM2COL) {
@@ -235,6 +237,7 @@ int net_pack(const cg_net_s* net, const float* params, void* packed, cudaStream_
         jobs.taps[j] = L.d.k * L.d.k; jobs.cin[j] = cin_f; jobs.cout[j] = cout_f;
         if (jobs.n == TC_PACK_MAX) CG_TRY(tc_pack_weights_multi(jobs, st));
     }
+    CG_TRY(tc_pack_win_flush(wjobs, st));
     return tc_pack_weights_multi(jobs, st);
 }
 

@@ -224,6 +224,30 @@ class Graph:
                 hw.append((h, w))
         return total
 
+    def conv_out_elems(self, H: int, W: int) -> int:
+        """Conv / transposed-conv output elements per image (the unit of the HBM-side roofline)."""
+        hw = [(H, W)]
+        total = 0
+        for L in self.layers:
+            h, w = hw[L.in0]
+            if L.op == OP_CONV:
+                ho = -(-h // L.stride) if L.same else (h - L.k) // L.stride + 1
+                wo = -(-w // L.stride) if L.same else (w - L.k) // L.stride + 1
+                total += ho * wo * L.cout
+                hw.append((ho, wo))
+            elif L.op == OP_CONVT:
+                total += h * L.stride * w * L.stride * L.cout
+                hw.append((h * L.stride, w * L.stride))
+            elif L.op == OP_RPAD:
+                hw.append((h + 2 * L.pad, w + 2 * L.pad))
+            elif L.op == OP_AVGPOOL:
+                hw.append((h // 2, w // 2))
+            elif L.op == OP_UPSAMPLE:
+                hw.append((h * 2, w * 2))
+            else:
+                hw.append((h, w))
+        return total
+
     def first_layer_flops(self, H: int, W: int) -> float:
         """FLOPs of the first conv, whose data-gradient is never needed."""
         hw = [(H, W)]

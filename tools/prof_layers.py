@@ -8,7 +8,8 @@ from collections import defaultdict
 
 agg = defaultdict(lambda: [0, 0.0, 0.0])
 for r in csv.DictReader(open(sys.argv[1])):
-    key = (("conv", "conv", "conv2cta", "wgrad")[int(r["kind"])] if int(r["kind"]) < 4 else r["kind"], int(r["taps"]),
+    names = {0: "conv", 1: "conv", 2: "conv2cta", 3: "wgrad", 4: "wgrad16", 5: "conv-win", 6: "wgrad-win"}
+    key = (names.get(int(r["kind"]), r["kind"]), int(r["taps"]),
            int(r["cchunks"]), int(r["bn"]), int(r["tiles"]), int(r["nb"]))
     a = agg[key]
     a[0] += 1
