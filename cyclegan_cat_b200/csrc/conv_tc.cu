@@ -474,6 +474,191 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------
+// Window-form convolution with vertical halo reuse (the U-Net layers: stride-1 'same' convs, C % 8 == 0, N <= 256).
+// conv_tc_kernel<WIN> loads one 16 KB A tile per (kernel row kh, window chunk j): k*k times the unique input bytes go
+// through the L2 -> shared-memory path, and these narrow-N layers sit on its cap (measured ~11.4 TB/s of L2 reads against
+// ~12 TB/s, 0.5 us per K step whatever N is).  Here the M tile is an 8 x 16 pixel box, a stage holds the (8 + k - 1) x 16
+// HALO of one window chunk plus the k weight tiles of that chunk (rows (kh*nch + j)*N of the packed [kh][j][N][64] matrix), and the k kernel rows are k shifted views of the same
+// shared-memory tile (descriptor start + kh * 16 rows): (8 + k - 1) / (8 k) of the A traffic (0.34 for k = 4, 0.25 for
+// k = 7) and one barrier round trip per k K-steps.  Same warp roles and epilogue as conv_tc_kernel.
+// ------------------------------------------------------------------------------------------
+template <bool DUAL>
+__global__ void __launch_bounds__(DUAL ? TC_THREADS : CONV_THREADS, DUAL ? 2 : 1)
+convw_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                bf16* __restrict__ out, const float* __restrict__ bias, const TcConvArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = a.win_k, nch = a.cchunks, halo_h = a.Hb + k - 1;
+    const uint32_t a_bytes = (uint32_t)(halo_h * a.Wb) * 128u, b_tile = (uint32_t)a.bn * 128u;
+    const uint32_t stage_bytes = a_bytes + (uint32_t)k * b_tile;
+    const int S = a.stages;
+    const uint32_t bar0 = smem0 + S * stage_bytes;
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (S + s); };
+    auto tfull = [&](int i) { return bar0 + 8u * (2 * S + i); };
+    auto tempty = [&](int i) { return bar0 + 8u * (2 * S + 2 + i); };
+    const uint32_t tmem_slot = bar0 + 8u * (2 * S + 4);
+    volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    float* stat_sm = reinterpret_cast<float*>(smem_raw + (bar0 + 256u - smem_u32(smem_raw)));
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+        for (int s = 0; s < S; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), DUAL ? 4 : EPI_WARPS); }
+        fence_barrier_init();
+    }
+    constexpr uint32_t ACC_COLS = DUAL ? 128u : 256u;
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * ACC_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    griddep_launch();
+    griddep_wait();
+
+    const int total_tiles = a.nb * a.tiles_per_img;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int img = a.n0 + t / a.tiles_per_img, ti = t % a.tiles_per_img;
+                const int w0 = (ti % a.tiles_w) * a.Wb, h0 = (ti / a.tiles_w) * a.Hb;
+                for (int j = 0; j < nch; ++j) {
+                    mbar_wait(empty(s), ph ^ 1u);
+                    mbar_expect_tx(full(s), stage_bytes);
+                    const uint32_t sa = smem0 + s * stage_bytes;
+                    tma_load_5d(sa, &mapA, full(s), 64 * j, w0, 0, h0 - a.win_pt, img);
+                    for (int kh = 0; kh < k; ++kh)
+                        tma_load_2d(sa + a_bytes + (uint32_t)kh * b_tile, &mapB, full(s), 0, (kh * nch + j) * a.bn);
+                    if (++s == S) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        int s = 0; uint32_t ph = 0;
+        int it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+            const int ti = t % a.tiles_per_img;
+            const int w0 = (ti % a.tiles_w) * a.Wb;
+            mbar_wait(tempty(acc), acc_ph ^ 1u);
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * ACC_COLS;
+            for (int j = 0; j < nch; ++j) {
+                mbar_wait(full(s), ph);
+                const uint32_t sa = smem0 + s * stage_bytes;
+                win_fix(sa, a.Wb, halo_h, w0, a.win_W, a.win_C, k, a.win_pl, 64 * j, lane);
+                __syncwarp();
+                if (lane == 0) {
+                    tc_fence_after();
+                    for (int kh = 0; kh < k; ++kh) {
+                        const uint64_t adesc = make_smem_desc(sa + (uint32_t)(kh * a.Wb) * 128u, 16, 1024);
+                        const uint64_t bdesc = make_smem_desc(sa + a_bytes + (uint32_t)kh * b_tile, 16, 1024);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_bf16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), a.idesc,
+                                      (uint32_t)((j | kh | kk) != 0));
+                    }
+                    umma_commit(empty(s));
+                }
+                __syncwarp();
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
+            if (lane == 0) umma_commit(tfull(acc));
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        float* tr = stat_sm + (warp - 2) * (32 * 17);
+        int it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+            const int img = t / a.tiles_per_img, ti = t % a.tiles_per_img;          // img relative to the output base
+            const int w0 = (ti % a.tiles_w) * a.Wb, h0 = (ti / a.tiles_w) * a.Hb;
+            const int rr = q * 32 + lane;                                         // tile row = (rr / Wb, rr % Wb) of the pixel box
+            const int oh = h0 + rr / a.Wb, ow = w0 + rr % a.Wb;
+            bf16* dst = out + (((size_t)img * a.out_H + oh) * a.out_W + ow) * a.Cout;
+            bf16* rowptr[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const unsigned long long pv = __shfl_sync(0xffffffffu, (unsigned long long)dst, (lane >> 2) + 8 * i);
+                rowptr[i] = reinterpret_cast<bf16*>(pv);
+            }
+            mbar_wait(tfull(acc), acc_ph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t)acc * ACC_COLS + ((uint32_t)(q * 32) << 16);
+            for (int c0 = half * 32; c0 < a.bn; c0 += (DUAL ? 32 : 64)) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)c0, v);
+                const int cols = min(32, a.bn - c0);
+                if (bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < cols) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(bias + c0 + j));
+                }
+                {
+                    uint4* stg = reinterpret_cast<uint4*>(tr);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        stg[lane * 4 + (j ^ ((lane >> 1) & 3))] =
+                            make_uint4(pack_bf16x2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                                       pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                                       pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                                       pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+                    __syncwarp();
+                    const int g = lane & 3;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = (lane >> 2) + 8 * i;
+                        const uint4 val = stg[r * 4 + (g ^ ((r >> 1) & 3))];
+                        if (g * 8 < cols) *reinterpret_cast<uint4*>(rowptr[i] + c0 + g * 8) = val;
+                    }
+                    __syncwarp();
+                }
+                if (a.stats) {
+                    float* sp = a.stats + ((size_t)img * a.Cout + c0) * 2;
+#pragma unroll
+                    for (int pass = 0; pass < 2; ++pass) {
+                        if (pass * 16 < cols) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) tr[lane * 17 + j] = __uint_as_float(v[pass * 16 + j]);
+                            __syncwarp();
+                            const float* col = tr + (lane >> 4) * 16 * 17 + (lane & 15);
+                            float s1 = 0.f, s2 = 0.f, s1b = 0.f, s2b = 0.f;
+#pragma unroll
+                            for (int r = 0; r < 16; r += 2) {
+                                const float x0 = col[r * 17], x1 = col[(r + 1) * 17];
+                                s1 += x0; s2 = fmaf(x0, x0, s2);
+                                s1b += x1; s2b = fmaf(x1, x1, s2b);
+                            }
+                            s1 += s1b; s2 += s2b;
+                            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                            s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+                            atomicAdd(sp + pass * 32 + 2 * (lane & 15) + (lane >> 4), (lane >> 4) ? s2 : s1);
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty(acc));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * ACC_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // 2-CTA variant (cta_group::2): a CTA pair (one TPC) computes a 256-pixel x BN tile.  Each CTA loads ITS 128 pixel rows
 // of A and HALF of the B rows; the leader's single thread issues tcgen05.mma.cta_group::2 (M = 256), which reads A/B
 // halves from both CTAs' shared memory and writes 128 accumulator rows into each CTA's TMEM.  Per SM this halves the
@@ -1076,14 +1261,16 @@ __global__ void pack_win_multi_kernel(const __grid_constant__ TcPackWinJobs jobs
         const int i = (int)(idx & 63);
         size_t r = idx >> 6;
         const int n = (int)(r % npad); r /= npad;
-        const int j = (int)(r % nch);
-        const int s = (int)(r / nch);
+        // row-major steps (kh, j) for conv_tc_kernel<WIN> / wgradw, chunk-major (j, kh) for convw_tc_kernel (flip bit 1)
+        const int j = (flip & 2) ? (int)(r / k) : (int)(r % nch);
+        const int s = (flip & 2) ? (int)(r % k) : (int)(r / nch);
         const int e = 64 * j + i, q = e / C, c = e - q * C;
         float v = 0.f;
         if (e < k * C && c < Creal && n < n_rows) {
             // forward: rows = output channels, window element = (kw, ci);  flip: rows = input channels, element = (kw', co)
-            const int kh = flip ? k - 1 - s : s, kw = flip ? k - 1 - q : q;
-            const int ci = flip ? n : c, co = flip ? c : n;
+            const bool fl = (flip & 1) != 0;
+            const int kh = fl ? k - 1 - s : s, kw = fl ? k - 1 - q : q;
+            const int ci = fl ? n : c, co = fl ? c : n;
             v = w[(((size_t)kh * k + kw) * Cin_w + ci) * Cout_w + co];
         }
         wf[idx] = __float2bfloat16(v);
@@ -1470,6 +1657,40 @@ int tc_wgradw_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* d
     int pi = prof_begin(st);
     launch_pdl(wgradw_tc_kernel, dim3(a.units * splits), dim3(TC_THREADS), smem, st, *mapX, *mapDY, dw, a);
     prof_end(pi, st, flops, prof_key(6, a.steps, a.units, a.Cout, a.chunks_per_img, a.nb));
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+// window conv with vertical halo reuse: a.Wb x a.Hb pixel boxes, a.cchunks window chunks, a.win_* set; the same packed weights as
+// conv_tc_kernel<WIN> ([kh][j][bn][64]).  Returns CG_ERR_INVALID when fewer than two stages fit (the caller then uses the per-row form).
+int tc_convw_stages(int bn, int k, int Wb, int Hb, bool* dual) {
+    const int stage = (Hb + k - 1) * Wb * 128 + k * bn * 128;
+    *dual = bn <= 128 && 2 * stage + 1024 + 256 + EPI_SCRATCH / 2 <= 110 * 1024;
+    const int budget = (*dual ? 110 : 227) * 1024 - 1024 - 256 - (*dual ? EPI_SCRATCH / 2 : EPI_SCRATCH);
+    int s = budget / stage;
+    return s > 6 ? 6 : s;
+}
+
+int tc_convw_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, bf16* out, const float* bias, TcConvArgs a, double flops,
+                    cudaStream_t st) {
+    bool dual = false;
+    a.stages = tc_convw_stages(a.bn, a.win_k, a.Wb, a.Hb, &dual);
+    if (a.stages < 2) { cg_set_error("window conv: a stage of %d bytes does not fit twice", (a.Hb + a.win_k - 1) * a.Wb * 128 + a.win_k * a.bn * 128); return CG_ERR_INVALID; }
+    a.idesc = make_idesc(128, a.bn, 0, 0);
+    const int stage = (a.Hb + a.win_k - 1) * a.Wb * 128 + a.win_k * a.bn * 128;
+    const size_t smem = (size_t)a.stages * stage + 1024 + 256 + (dual ? EPI_SCRATCH / 2 : EPI_SCRATCH);
+    static std::atomic<unsigned long long> attr_set{0};
+    if (cg_first_on_device(attr_set)) {
+        CG_CUDA(cudaFuncSetAttribute(convw_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CG_CUDA(cudaFuncSetAttribute(convw_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    }
+    const int total = a.nb * a.tiles_per_img;
+    const int slots = (dual ? 2 : 1) * num_sms();
+    const int grid = total < slots ? total : slots;
+    int pi = prof_begin(st);
+    if (dual) launch_pdl(convw_tc_kernel<true>, dim3(grid), dim3(TC_THREADS), smem, st, *mapA, *mapB, out, bias, a);
+    else launch_pdl(convw_tc_kernel<false>, dim3(grid), dim3(CONV_THREADS), smem, st, *mapA, *mapB, out, bias, a);
+    prof_end(pi, st, flops, prof_key(7, a.win_k * a.cchunks, a.cchunks, a.bn, a.tiles_per_img, a.nb));
     CG_LAUNCH_CHECK();
     return CG_OK;
 }

@@ -26,6 +26,7 @@ struct TcConvArgs {
     // a K step is the 128 contiguous bytes that start at element dc[step] of the k*C-element window [pixel p-pl .. p-pl+k-1]
     // of image row h0+dh[step] (tc_make_map_win).  Window pixels outside [0, W) are zeroed in shared memory before the MMAs.
     int win_C, win_k, win_pl, win_W;
+    int win_pt;                                 // convw_tc_kernel: rows above the tile that the halo starts at (top padding)
     // per K-loop tap: TMA coordinate offsets into the 5-D activation view (c, w, p, h, n) and the weight row block
     short dc[TC_MAX_STEPS], dw[TC_MAX_STEPS], dp[TC_MAX_STEPS], dh[TC_MAX_STEPS], tb[TC_MAX_STEPS];
 };
@@ -57,6 +58,10 @@ struct TcPackWinJobs {
 int tc_pack_win(TcPackWinJobs& jobs, const float* w, bf16* wf, int k, int C, int Creal, int n_rows, int npad, int Cin_w,
                 int Cout_w, int flip, cudaStream_t st);
 int tc_pack_win_flush(TcPackWinJobs& jobs, cudaStream_t st);
+// window conv with vertical halo reuse (convw_tc_kernel): stages that fit / launch
+int tc_convw_stages(int bn, int k, int Wb, int Hb, bool* dual);
+int tc_convw_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, bf16* out, const float* bias, TcConvArgs a, double flops,
+                    cudaStream_t st);
 
 struct TcWgradArgs {
     int n_taps, a_blocks, b_blocks, bn, splits, stages;   // M = 128-row blocks of operand A, N = bn-column blocks of B

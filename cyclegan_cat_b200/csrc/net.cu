@@ -480,23 +480,33 @@ int net_bind(CallCtx* c) {
             const int cp = d.cin <= 4 ? 8 : d.cin;
             const void* xs = d.cin <= 4 ? (const void*)c->tcs : x;
             if (d.cin <= 4 && !c->tcs) { cg_set_error("net_bind: no scratch for the 8-channel input"); return CG_ERR_STATE; }
+            static const bool halo_on = [] { const char* e = getenv("CG_DISABLE_HALO"); return !(e && e[0] == '1'); }();   // A/B hook
             auto make_win = [&](TcConvLaunch& Ln, const void* in, int cin_k, const bf16* wmat, int n_out, int p_t, int p_l) -> int {
                 TcConvArgs& a = Ln.a;
                 memset(&a, 0, sizeof(a));
-                set_tiles(a, wo, ho);
                 const int nch = (k * cin_k + 63) / 64;
-                a.n_taps = k * nch; a.cchunks = 1;
                 a.bn = n_out; a.n_blocks_n = 1;
                 a.nb = c->N; a.out_H = ho; a.out_W = wo; a.Cout = n_out; a.out_sy = a.out_sx = 1;
                 a.b_rows_per_tap = n_out;
-                for (int kh = 0; kh < k; ++kh)
-                    for (int j = 0; j < nch; ++j) {
-                        const int st_ = kh * nch + j;
-                        a.tb[st_] = (short)st_; a.dc[st_] = (short)(64 * j); a.dh[st_] = (short)(kh - p_t);
-                    }
-                a.win_C = cin_k; a.win_k = k; a.win_pl = p_l; a.win_W = wo;
-                CG_TRY(tc_make_map_win(&Ln.mapA, in, cin_k, k, p_l, wo, ho, c->N, a.Wb, a.Hb));
-                CG_TRY(tc_make_map_2d(&Ln.mapB, wmat, 64, a.n_taps * n_out, n_out));
+                a.win_C = cin_k; a.win_k = k; a.win_pl = p_l; a.win_W = wo; a.win_pt = p_t;
+                bool dual_unused = false;
+                Ln.halo = halo_on && wo % 16 == 0 && ho % 8 == 0 && tc_convw_stages(n_out, k, 16, 8, &dual_unused) >= 2;
+                if (Ln.halo) {       // 8 x 16 pixel boxes; a stage = the (8 + k - 1)-row halo of one window chunk
+                    a.Wb = 16; a.Hb = 8; a.tiles_w = wo / 16; a.tiles_per_img = a.tiles_w * (ho / 8);
+                    a.out_P = wo; a.out_wvalid = wo; a.out_hvalid = ho;
+                    a.n_taps = k * nch; a.cchunks = nch;
+                    CG_TRY(tc_make_map_win(&Ln.mapA, in, cin_k, k, p_l, wo, ho, c->N, 16, 8 + k - 1));
+                } else {
+                    set_tiles(a, wo, ho);
+                    a.n_taps = k * nch; a.cchunks = 1;
+                    for (int kh = 0; kh < k; ++kh)
+                        for (int j = 0; j < nch; ++j) {
+                            const int st_ = kh * nch + j;
+                            a.tb[st_] = (short)st_; a.dc[st_] = (short)(64 * j); a.dh[st_] = (short)(kh - p_t);
+                        }
+                    CG_TRY(tc_make_map_win(&Ln.mapA, in, cin_k, k, p_l, wo, ho, c->N, a.Wb, a.Hb));
+                }
+                CG_TRY(tc_make_map_2d(&Ln.mapB, wmat, 64, k * nch * n_out, n_out));
                 Ln.mapB2 = Ln.mapB;
                 return CG_OK;
             };
@@ -738,7 +748,8 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
                     TcConvArgs a = tl.a;
                     a.nb = N;
                     a.stats = fused_stats;
-                    CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, (bf16*)y, bias, a, fl, st));
+                    if (tl.halo) CG_TRY(tc_convw_launch(&tl.mapA, &tl.mapB, (bf16*)y, bias, a, fl, st));
+                    else CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, (bf16*)y, bias, a, fl, st));
                 } else if (c->tc[i].on && L.tc == TC_IM2COL) {
                     const TcConvLaunch& tl = c->tc[i].fwd[0];
                     CG_TRY(sp_im2col((const bf16*)x, (bf16*)c->tcs, N, h, w, d.cin, oh, ow, d.k, d.stride, g.pt, g.pl, st));
@@ -984,7 +995,8 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                             const TcConvLaunch& tl = c->tc[i].dgrad[0];
                             TcConvArgs a = tl.a;
                             a.nb = nb;
-                            CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, (bf16*)dx, nullptr, a, fl, st));
+                            if (tl.halo) CG_TRY(tc_convw_launch(&tl.mapA, &tl.mapB, (bf16*)dx, nullptr, a, fl, st));
+                            else CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, (bf16*)dx, nullptr, a, fl, st));
                         }
                     }
                     break;

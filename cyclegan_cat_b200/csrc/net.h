@@ -9,7 +9,7 @@
 #include "conv_tc.h"
 
 // tensor-core plan of one eligible conv layer for one planned call
-struct TcConvLaunch { CUtensorMap mapA, mapB, mapB2; TcConvArgs a; double flop_share = 1.0; };
+struct TcConvLaunch { CUtensorMap mapA, mapB, mapB2; TcConvArgs a; double flop_share = 1.0; bool halo = false; /* convw_tc_kernel */ };
 struct TcLayer {
     bool on = false;
     std::vector<TcConvLaunch> fwd;      // 1 launch (Conv2D) or 4 stride-parity classes (Conv2DTranspose)
