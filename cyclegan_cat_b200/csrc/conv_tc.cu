@@ -1245,6 +1245,132 @@ wgradw_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// The same weight gradient with vertical halo reuse: one unit = one window chunk j, a stage = the (4 + k - 1) x 16 halo of
+// that chunk around a 4 x 16 pixel block plus the dY block; the k kernel rows are k shifted views of the halo, stacked two
+// by two in the 128 MMA rows (LBO = one image row of the tile), each pair with its own TMEM accumulator.  (4 + k - 1) /
+// (4 k) of the X traffic of wgradw_tc_kernel and one dY load / barrier round trip for all k rows.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgradh_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDY,
+                 float* __restrict__ dw, const TcWgradWArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ygroups = a.Cout / 16;
+    const int k = a.k, halo_h = a.Hk + k - 1;
+    const uint32_t a_bytes = (uint32_t)(halo_h * a.Wk) * 128u;
+    const uint32_t stage_bytes = a_bytes + (uint32_t)ygroups * 2048u;
+    const int S = a.stages;
+    const uint32_t bar0 = smem0 + S * stage_bytes;
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (S + s); };
+    const uint32_t tfull = bar0 + 8u * (2 * S);
+    const uint32_t tmem_slot = bar0 + 8u * (2 * S + 1);
+    volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    const int npair = (k + 1) / 2;
+    const uint32_t acc_cols = (uint32_t)a.acc_pitch;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapX);
+        tma_prefetch_desc(&mapDY);
+        for (int s = 0; s < S; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    griddep_launch();
+    griddep_wait();
+
+    const int split = blockIdx.x % a.splits, j = blockIdx.x / a.splits;       // unit = window chunk j
+    const int total_chunks = a.nb * a.chunks_per_img;
+    const int per = (total_chunks + a.splits - 1) / a.splits;
+    const int q_begin = split * per;
+    const int q_end = min(total_chunks, q_begin + per);
+    const int nq = q_end - q_begin;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int q = q_begin; q < q_end; ++q) {
+                const int img = q / a.chunks_per_img, r = q % a.chunks_per_img;
+                const int w0 = (r % a.chunks_w) * a.Wk, h0 = (r / a.chunks_w) * a.Hk;
+                mbar_wait(empty(s), ph ^ 1u);
+                mbar_expect_tx(full(s), stage_bytes);
+                const uint32_t sa = smem0 + s * stage_bytes;
+                tma_load_5d(sa, &mapX, full(s), 64 * j, w0, 0, h0 - a.pt, a.n0 + img);
+                tma_load_5d(sa + a_bytes, &mapDY, full(s), 0, w0, h0, 0, a.y_n0 + img);
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (nq > 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int i = 0; i < nq; ++i) {
+                const int q = q_begin + i;
+                const int w0 = ((q % a.chunks_per_img) % a.chunks_w) * a.Wk;
+                mbar_wait(full(s), ph);
+                const uint32_t sa = smem0 + s * stage_bytes;
+                win_fix(sa, a.Wk, halo_h, w0, a.W, a.C, k, a.pl, 64 * j, lane);
+                __syncwarp();
+                if (lane == 0) {
+                    tc_fence_after();
+                    for (int pi = 0; pi < npair; ++pi) {
+                        // rows 0-63 = kernel row 2*pi, rows 64-127 = kernel row 2*pi+1: the same halo one image row further down
+                        const uint64_t adesc = make_smem_desc(sa + (uint32_t)(2 * pi * a.Wk) * 128u, (uint32_t)a.Wk * 128u, 1024);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_bf16(tmem_base + (uint32_t)pi * acc_cols, adesc + (uint64_t)(kk * 128),
+                                      make_smem_desc32_mn(sa + a_bytes + (uint32_t)kk * 512u, 2048), a.idesc, (uint32_t)((i | kk) != 0));
+                    }
+                    umma_commit(empty(s));
+                }
+                __syncwarp();
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
+            if (lane == 0) umma_commit(tfull);
+        }
+    } else if (nq > 0) {
+        const int q = warp & 3;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        const int row = q * 32 + lane, half = row >> 6, i = row & 63;
+        const int e = 64 * j + i;
+        const int kw = e / a.C, ci = e - kw * a.C;
+        const bool live_e = e < k * a.C && ci < a.Creal;
+        for (int pi = 0; pi < npair; ++pi) {
+            const int kh = 2 * pi + half;
+            const bool live = live_e && kh < k;
+            float* dst = dw + ((size_t)(kh * k + kw) * a.Creal + ci) * a.Cout;
+            const uint32_t taddr = tmem_base + (uint32_t)pi * acc_cols + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < a.Cout; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)c0, v);
+                const int cols = min(32, a.Cout - c0);
+                if (live) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4)
+                        if (j4 * 4 < cols)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + 4 * j4),
+                                         "f"(__uint_as_float(v[4 * j4])), "f"(__uint_as_float(v[4 * j4 + 1])),
+                                         "f"(__uint_as_float(v[4 * j4 + 2])), "f"(__uint_as_float(v[4 * j4 + 3]))
+                                         : "memory");
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+    }
+}
+
 // packed window weights (see tc_pack_win in conv_tc.h); all window layers of a net in ONE launch: a block finds its
 // job in the prefix table and packs a grid-stride share of it
 __global__ void pack_win_multi_kernel(const __grid_constant__ TcPackWinJobs jobs) {
@@ -1691,6 +1817,44 @@ int tc_convw_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, bf16* out,
     if (dual) launch_pdl(convw_tc_kernel<true>, dim3(grid), dim3(TC_THREADS), smem, st, *mapA, *mapB, out, bias, a);
     else launch_pdl(convw_tc_kernel<false>, dim3(grid), dim3(CONV_THREADS), smem, st, *mapA, *mapB, out, bias, a);
     prof_end(pi, st, flops, prof_key(7, a.win_k * a.cchunks, a.cchunks, a.bn, a.tiles_per_img, a.nb));
+    CG_LAUNCH_CHECK();
+    return CG_OK;
+}
+
+// halo form of the window weight gradient (wgradh_tc_kernel): a.Wk x a.Hk = 16 x 4 pixel blocks, a.pt set; returns
+// CG_ERR_INVALID when the accumulators do not fit TMEM or fewer than two stages fit
+int tc_wgradh_ok(int k, int Cout) {
+    const int npair = (k + 1) / 2, pitch = Cout <= 32 ? 32 : Cout <= 64 ? 64 : Cout <= 128 ? 128 : 256;
+    return npair * pitch <= 512;
+}
+
+int tc_wgradh_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* dw, TcWgradWArgs a, double flops, cudaStream_t st) {
+    const int npair = (a.k + 1) / 2;
+    a.acc_pitch = a.Cout <= 32 ? 32 : a.Cout <= 64 ? 64 : a.Cout <= 128 ? 128 : 256;
+    int cols = npair * a.acc_pitch;
+    if (cols > 512) { cg_set_error("wgradh: %d accumulators of %d columns exceed TMEM", npair, a.acc_pitch); return CG_ERR_INVALID; }
+    int tm = 32;
+    while (tm < cols) tm *= 2;
+    a.tmem_cols = tm;
+    const int stage = (a.Hk + a.k - 1) * a.Wk * 128 + (a.Cout / 16) * 2048;
+    const int per_sm = (tm <= 256 && stage * 3 + 2048 <= 110 * 1024) ? 2 : 1;
+    int s = ((per_sm == 2 ? 110 : 227) * 1024 - 2048) / stage;
+    a.stages = s > 8 ? 8 : s;
+    if (a.stages < 2) { cg_set_error("wgradh: stage of %d bytes does not fit twice", stage); return CG_ERR_INVALID; }
+    a.idesc = make_idesc(128, a.Cout, 1, 1);
+    a.units = a.nch;
+    const int total_chunks = a.nb * a.chunks_per_img;
+    int splits = (2 * per_sm * num_sms()) / a.units;
+    if (splits < 1) splits = 1;
+    if (splits > total_chunks) splits = total_chunks;
+    a.splits = splits;
+    const size_t smem = (size_t)a.stages * stage + 1024 + 256;
+    static std::atomic<unsigned long long> attr_set{0};
+    if (cg_first_on_device(attr_set))
+        CG_CUDA(cudaFuncSetAttribute(wgradh_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int pi = prof_begin(st);
+    launch_pdl(wgradh_tc_kernel, dim3(a.units * splits), dim3(TC_THREADS), smem, st, *mapX, *mapDY, dw, a);
+    prof_end(pi, st, flops, prof_key(8, a.steps, a.units, a.Cout, a.chunks_per_img, a.nb));
     CG_LAUNCH_CHECK();
     return CG_OK;
 }

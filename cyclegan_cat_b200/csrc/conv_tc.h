@@ -39,10 +39,14 @@ struct TcWgradWArgs {
     int n0, nb, y_n0;
     int chunks_per_img, chunks_w, Wk, Hk;
     int W, pl;
+    int pt, acc_pitch, tmem_cols;               // wgradh_tc_kernel: top padding, TMEM column pitch of the accumulators, columns allocated
     uint32_t idesc;
     short dc[TC_MAX_STEPS], dh[TC_MAX_STEPS];
 };
 int tc_wgradw_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* dw, TcWgradWArgs a, double flops, cudaStream_t st);
+// halo form (wgradh_tc_kernel): 16 x 4 pixel blocks, one unit per window chunk
+int tc_wgradh_ok(int k, int Cout);
+int tc_wgradh_launch(const CUtensorMap* mapX, const CUtensorMap* mapDY, float* dw, TcWgradWArgs a, double flops, cudaStream_t st);
 // window view of an NHWC bf16 tensor (C % 8 == 0): dims (k*C, W, 1, H, N), pixel stride C (overlapping rows), base shifted
 // left by `pl` pixels; box {64, box_w, 1, box_h, 1}, SWIZZLE_128B; elements beyond k*C are zero-filled by TMA
 int tc_make_map_win(CUtensorMap* map, const void* x, int C, int k, int pl, int W, int H, int N, int box_w, int box_h);

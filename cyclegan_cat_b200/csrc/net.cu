@@ -523,12 +523,15 @@ int net_bind(CallCtx* c) {
                 memset(&a, 0, sizeof(a));
                 a.k = k; a.C = cp; a.Creal = d.cin; a.Cout = d.cout;
                 a.nch = (k * cp + 63) / 64; a.steps = k * a.nch;
-                a.Wk = wo % 64 == 0 ? 64 : wo; a.Hk = 64 / a.Wk;
+                a.W = wi; a.pl = pl; a.pt = pt;
+                t.wgh = halo_on && wo % 16 == 0 && ho % 4 == 0 && tc_wgradh_ok(k, d.cout) &&
+                        (4 + k - 1) * 16 * 128 + (d.cout / 16) * 2048 <= 100 * 1024;
+                if (t.wgh) { a.Wk = 16; a.Hk = 4; }
+                else { a.Wk = wo % 64 == 0 ? 64 : wo; a.Hk = 64 / a.Wk; }
                 a.chunks_w = wo / a.Wk; a.chunks_per_img = a.chunks_w * (ho / a.Hk);
-                a.W = wi; a.pl = pl;
                 for (int kh = 0; kh < k; ++kh)
                     for (int j = 0; j < a.nch; ++j) { a.dc[kh * a.nch + j] = (short)(64 * j); a.dh[kh * a.nch + j] = (short)(kh - pt); }
-                CG_TRY(tc_make_map_win(&t.mapXw, xs, cp, k, pl, wi, hi, c->N, a.Wk, a.Hk));
+                CG_TRY(tc_make_map_win(&t.mapXw, xs, cp, k, pl, wi, hi, c->N, a.Wk, t.wgh ? a.Hk + k - 1 : a.Hk));
                 CG_TRY(tc_make_map_act16(&t.mapDYw, dy, d.cout, wo, ho, c->N, a.Wk, a.Hk, d.cout / 16));
                 t.wgw = true;
             }
@@ -981,7 +984,8 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                             if (d.cin <= 4) CG_TRY(sp_pad_channels8((const bf16*)A(tin), (bf16*)c->tcs, (size_t)nb * h * w, d.cin, st));
                             TcWgradWArgs a = c->tc[i].waw;
                             a.n0 = d.cin <= 4 ? 0 : n0; a.y_n0 = 0; a.nb = nb;      // dY lives in the (sub-batch relative) arena
-                            CG_TRY(tc_wgradw_launch(&c->tc[i].mapXw, &c->tc[i].mapDYw, grads + L.w_off, a, fl, st));
+                            if (c->tc[i].wgh) CG_TRY(tc_wgradh_launch(&c->tc[i].mapXw, &c->tc[i].mapDYw, grads + L.w_off, a, fl, st));
+                            else CG_TRY(tc_wgradw_launch(&c->tc[i].mapXw, &c->tc[i].mapDYw, grads + L.w_off, a, fl, st));
                         } else {
                             CG_TRY(k_conv_wgrad<T>(A(tin), dy, grads + L.w_off, g, st));
                         }

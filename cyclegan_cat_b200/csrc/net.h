@@ -19,6 +19,7 @@ struct TcLayer {
     TcWgrad16Args wa16;
     TcWgradWArgs waw;
     bool wg16 = false;
+    bool wgh = false;                   // ... in its halo form (wgradh_tc_kernel)
     bool wgw = false;                   // TC_S1_WIN: the window weight-gradient kernel applies (64-pixel chunks tile the grid)
     int wg_x_is_dy = 0;                 // Conv2DTranspose: the "X" operand of the weight gradient is dY
     size_t sc_tmp = 0;                  // TC_STEM / TC_HEAD: offset of the fp32 weight-gradient staging buffer in the scratch
