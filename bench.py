@@ -527,7 +527,13 @@ def run_gpu(args, wl):
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
     barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_mine = e0.elapsed_time(e1)
+    ms_total = max_over_ranks(ms_mine)
+    rank_ms = [ms_mine / args.steps]
+    if world > 1:       # per-rank step time of the same timed region: the spread is the rank skew max_over_ranks pays for
+        t_all = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(t_all, torch.tensor([ms_mine / args.steps], dtype=torch.float64, device="cuda"))
+        rank_ms = [float(t.item()) for t in t_all]
     clocks = sampler.stop()
     launches = ctypes.c_int64()
     lib.cg_launch_count(ctypes.byref(launches), 0)
@@ -615,7 +621,7 @@ def run_gpu(args, wl):
                 ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.mode,
                 data="synthetic",
                 config=dict(workload=wl["name"], image_size=S, batch_per_gpu=B, global_batch=B * world,
-                            parallelism=f"dp{world}", pairs_per_step=B * world,
+                            parallelism=f"dp{world}", pairs_per_step=B * world, rank_ms_per_step=rank_ms,
                             individual_images_per_sec=2 * value, flops_per_pair=fl_pair,
                             l2="no flush needed: one step streams tens of GB of activations (>> 126 MB L2)",
                             weights="random init N(0,0.02), seeds 42-45", last_metrics=last_metrics),

@@ -403,7 +403,8 @@ static int step_body(cg_trainer_t tr, int B, int H, int W, bool train, cudaStrea
     // discriminator losses: parameter gradients only
     CG_TRY(net_backward(&tr->DB, tr->params[3], seedDB, nullptr, tr->grads[3], 0, 2 * B, st));
     CG_TRY(net_backward(&tr->DA, tr->params[2], seedDA, nullptr, tr->grads[2], 0, 2 * B, sy));
-    if (tr->comm) {     // d_A / d_B gradients are final: all-reduce them under the generator backward
+    static const bool skip_ar = [] { const char* e = getenv("CG_DP_SKIP_AR"); return e && e[0] == '1'; }();   // measurement only
+    if (tr->comm && !skip_ar) {     // d_A / d_B gradients are final: all-reduce them under the generator backward
         CG_CUDA(cudaEventRecord(tr->ev_d, st));
         CG_CUDA(cudaStreamWaitEvent(tr->comm_stream, tr->ev_d, 0));
         if (sy != st) {
@@ -447,7 +448,7 @@ static int step_body(cg_trainer_t tr, int B, int H, int W, bool train, cudaStrea
     CG_TRY(net_backward(&tr->F1, tr->params[0], seedF1, nullptr, tr->grads[0], 0, 2 * B, st));
     CG_TRY(net_backward(&tr->F2, tr->params[1], seedF2, nullptr, tr->grads[1], 0, 2 * B, sy));
     CG_TRY(join(6));
-    if (tr->comm) {
+    if (tr->comm && !skip_ar) {
         CG_CUDA(cudaEventRecord(tr->ev_g, st));
         CG_CUDA(cudaStreamWaitEvent(tr->comm_stream, tr->ev_g, 0));
         CG_NCCL(g_nccl.GroupStart());
