@@ -599,8 +599,74 @@ __global__ void __launch_bounds__(256) conv_dgrad_simt(const T* __restrict__ dy,
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// 1x1 convolutions with <= 4 output channels (the U-Net heads, unet.py:121: Conv2D(output_channels, 1)): both gradients are
+// pure streaming passes over the input-side tensor (read x once / write dx once), so one thread owns one 16-byte channel
+// vector of a pixel; the generic kernels above run these at ~0.2 TB/s (4 active lanes per warp / a K = 3 GEMM).
+//   wgrad: dw[ci][co] += sum_p x[p][ci] * dy[p][co]        dgrad: dx[p][ci] (+)= sum_co dy[p][co] * w[ci][co]
+// ------------------------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) conv1x1_thin_wgrad(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw,
+                                                          size_t npix, int Cin, int Cout) {
+    const int nv = Cin / VEC, cv = threadIdx.x % nv, prow = threadIdx.x / nv, ppb = 256 / nv;
+    float acc[VEC][4] = {};
+    for (size_t p = blockIdx.x * (size_t)ppb + prow; p < npix; p += (size_t)gridDim.x * ppb) {
+        float a[VEC], d[4];
+        load_vec<T, VEC>(x + p * Cin + (size_t)cv * VEC, a);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) d[c] = c < Cout ? ldf(dy + p * Cout + c) : 0.f;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[j][c] = fmaf(a[j], d[c], acc[j][c]);
+    }
+    // block reduction over the pixel rows of the same channel vector, then one atomic per (ci, co)
+    __shared__ float red[256][4 * VEC + 1];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) red[threadIdx.x][j * 4 + c] = acc[j][c];
+    __syncthreads();
+    for (int o = threadIdx.x; o < Cin * Cout; o += 256) {
+        const int ci = o / Cout, co = o - ci * Cout, v = ci / VEC, j = ci - v * VEC;
+        float sum = 0.f;
+        for (int r = 0; r < ppb; ++r) sum += red[r * nv + v][j * 4 + co];
+        atomicAdd(dw + o, sum);
+    }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) conv1x1_thin_dgrad(const T* __restrict__ dy, const float* __restrict__ w, T* __restrict__ dx,
+                                                          size_t npix, int Cin, int Cout, int accumulate) {
+    const int nv = Cin / VEC;
+    const size_t total = npix * nv;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t p = i / nv;
+        const int ci0 = (int)(i - p * nv) * VEC;
+        float d[4], o[VEC];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) d[c] = c < Cout ? ldf(dy + p * Cout + c) : 0.f;
+        if (accumulate) load_vec<T, VEC>(dx + p * Cin + ci0, o);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            float v = 0.f;
+            for (int c = 0; c < Cout; ++c) v = fmaf(d[c], __ldg(w + (size_t)(ci0 + j) * Cout + c), v);
+            o[j] = accumulate ? o[j] + v : v;
+        }
+        store_vec<T, VEC>(dx + p * Cin + ci0, o);
+    }
+}
+
 template <typename T> int k_conv_dgrad(const T* dy, const float* w, const float* bias, T* dx, ConvGeom g,
                                        int accumulate, cudaStream_t st) {
+    constexpr int VW1 = VecWidth<T>::value;
+    if (g.k == 1 && g.s == 1 && g.Cout <= 4 && g.Cin % VW1 == 0 && !bias) {       // 1x1 thin-output head: streaming pass
+        const size_t npix = (size_t)g.N * g.Hi * g.Wi, total = npix * (g.Cin / VW1);
+        const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+        conv1x1_thin_dgrad<T, VW1><<<blocks, 256, 0, st>>>(dy, w, dx, npix, g.Cin, g.Cout, accumulate);
+        CG_LAUNCH_CHECK();
+        return CG_OK;
+    }
     const size_t wbytes = (size_t)g.k * g.k * g.Cout * sizeof(float4);
     if (g.Cin <= 4 && wbytes <= 96 * 1024) {
         static std::atomic<unsigned long long> attr_done{0};
@@ -714,6 +780,19 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt(const T* __restrict__ x, 
 template <typename T> int k_conv_wgrad(const T* x, const T* dy, float* dw, ConvGeom g, cudaStream_t st) {
     int Mrows = g.k * g.k * g.Cin;
     long long P = (long long)g.N * g.Ho * g.Wo;
+    {
+        constexpr int VW1 = VecWidth<T>::value;
+        const int nv = g.Cin % VW1 == 0 ? g.Cin / VW1 : 0;
+        if (g.k == 1 && g.s == 1 && g.Cout <= 4 && nv >= 1 && nv <= 256 && 256 % nv == 0) {      // 1x1 thin-output head
+            const size_t npix = (size_t)P;
+            const int ppb = 256 / nv;
+            long long want = (long long)((npix + ppb - 1) / ppb);
+            const int blocks = (int)(want < 148 * 4 ? want : 148 * 4);
+            conv1x1_thin_wgrad<T, VW1><<<blocks, 256, 0, st>>>(x, dy, dw, npix, g.Cin, g.Cout);
+            CG_LAUNCH_CHECK();
+            return CG_OK;
+        }
+    }
     if (g.Cout <= 4 && g.Cin % VecWidth<T>::value == 0 && g.k * (g.Cin / VecWidth<T>::value) <= 1024) {
         const int threads = ((g.k * (g.Cin / VecWidth<T>::value) + 31) / 32) * 32;
         int per_sm = 2048 / threads;

@@ -446,13 +446,21 @@ static int step_body(cg_trainer_t tr, int B, int H, int W, bool train, cudaStrea
         return CG_OK;
     }
     CG_TRY(net_backward(&tr->F1, tr->params[0], seedF1, nullptr, tr->grads[0], 0, 2 * B, st));
+    if (tr->comm && !skip_ar && sy == st) {     // theta_AB is final: its all-reduce runs under g_BA's last backward call
+        if (tr->ev_bucket.empty()) { cg_set_error("communicator without events"); return CG_ERR_STATE; }
+        CG_CUDA(cudaEventRecord(tr->ev_bucket[0], st));
+        CG_CUDA(cudaStreamWaitEvent(tr->comm_stream, tr->ev_bucket[0], 0));
+        CG_NCCL(g_nccl.AllReduce(tr->grads[0], tr->grads[0], (size_t)tr->net[0]->n_params, 7, 0, tr->comm, tr->comm_stream));
+    }
     CG_TRY(net_backward(&tr->F2, tr->params[1], seedF2, nullptr, tr->grads[1], 0, 2 * B, sy));
+    const bool ab_reduced = sy == st;
     CG_TRY(join(6));
     if (tr->comm && !skip_ar) {
         CG_CUDA(cudaEventRecord(tr->ev_g, st));
         CG_CUDA(cudaStreamWaitEvent(tr->comm_stream, tr->ev_g, 0));
         CG_NCCL(g_nccl.GroupStart());
-        CG_NCCL(g_nccl.AllReduce(tr->grads[0], tr->grads[0], (size_t)tr->net[0]->n_params, 7, 0, tr->comm, tr->comm_stream));
+        if (!ab_reduced)
+            CG_NCCL(g_nccl.AllReduce(tr->grads[0], tr->grads[0], (size_t)tr->net[0]->n_params, 7, 0, tr->comm, tr->comm_stream));
         CG_NCCL(g_nccl.AllReduce(tr->grads[1], tr->grads[1], (size_t)tr->net[1]->n_params, 7, 0, tr->comm, tr->comm_stream));
         CG_NCCL(g_nccl.GroupEnd());
         CG_CUDA(cudaEventRecord(tr->ev_done, tr->comm_stream));

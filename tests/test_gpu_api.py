@@ -19,8 +19,13 @@ pytestmark = pytest.mark.gpu
 
 
 def _gan(folder, new=True, mode="fp32"):
-    mc = C.model_config(C.SMALL_RESNET, C.SMALL_SIMPLE)
-    mc.location, mc.name, mc.new = folder, "m", new
+    if new:
+        mc = C.model_config(C.SMALL_RESNET, C.SMALL_SIMPLE)
+        mc.location, mc.name, mc.new = folder, "m", True
+    else:       # the reference's resume flow: train.py is pointed at the model_config.yaml that train() wrote (new: false,
+        from cyclegan_cat_b200.model_processing.load_model import yaml2namespace      # current_epoch: n; model.py:262-266)
+        mc = yaml2namespace(os.path.join(folder, "m", "model_config.yaml"))
+        assert mc.new is False and mc.current_epoch == 2
     tc = C.train_config(batch_size=2)
     tc.epochs = 2
     tc.summary = dict(samples=2, images=1, model=1)
