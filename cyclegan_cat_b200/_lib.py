@@ -57,6 +57,7 @@ SIGNATURES = {
     "cg_optimizer_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_i64, c_void_p]),
     "cg_trainer_get_iterations": (c_int, [c_void_p, ctypes.POINTER(c_i64 * 4)]),
     "cg_trainer_set_iterations": (c_int, [c_void_p, ctypes.POINTER(c_i64 * 4)]),
+    "cg_trainer_plan_count": (c_int, [c_void_p, ctypes.POINTER(c_i64), ctypes.POINTER(c_int)]),
     "cg_trainer_fetch_image": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "cg_comm_unique_id": (c_int, [ctypes.c_char * 128]),
     "cg_trainer_comm_init": (c_int, [c_void_p, ctypes.c_char * 128, c_int, c_int]),

@@ -203,8 +203,14 @@ static constexpr int TMEM_COLS = 512;
 // per K step; ~2100 cycles per 3-step tile even with loads and epilogue switched off) bounds the SM, not the tensor pipe;
 // two resident CTAs overlap their chains.
 // WIN: window mode (TcConvArgs::win_*): the MMA warp patches the image-row edges of every A tile before issuing.
-template <bool BK16, bool DUAL, bool WIN = false>
-__global__ void __launch_bounds__(DUAL ? TC_THREADS : CONV_THREADS, DUAL ? 2 : 1)
+// EPI: epilogue variant.  0 = as described above.
+//   1 = TWO groups of epilogue warps, one per TMEM accumulator (18 warps, or 10 per CTA with DUAL): tiles alternate between
+//       the groups, so the epilogue of tile i+1 starts while tile i's is still running.  For the layers whose main loop is
+//       shorter than the epilogue of a tile (few K steps, narrow N), where the epilogue warps are the critical path.
+// (A low-shared-memory variant -- rows stored straight from registers, statistics by warp shuffles -- was measured slower
+// on the trunk convs: forward 4.43 -> 4.70 ms, fold-mode data gradient 4.81 -> 7.92 ms per step.)
+template <bool BK16, bool DUAL, bool WIN = false, int EPI = 0>
+__global__ void __launch_bounds__((DUAL ? TC_THREADS : CONV_THREADS) + (EPI == 1 ? (DUAL ? 128 : 256) : 0), DUAL ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                bf16* __restrict__ out, const float* __restrict__ bias, const TcConvArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -361,11 +367,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
     } else {
         const int q = warp & 3;                   // TMEM lane quarter this warp may read
-        const int half = (warp - 2) >> 2;         // two warps per quarter: even / odd 32-column chunks (DUAL: one warp, all chunks)
+        const int half = DUAL ? 0 : ((warp - 2) >> 2) & 1;   // two warps per quarter: even / odd 32-column chunks (DUAL: one warp, all chunks)
+        const int grp = EPI == 1 ? (warp - 2) / (DUAL ? 4 : EPI_WARPS) : 0;      // EPI 1: this warp's accumulator
         float* tr = stat_sm + (warp - 2) * (32 * 17);
         int it = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
+            if (EPI == 1 && acc != grp) continue;
             const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
             const int nblk = t % a.n_blocks_n, mt = t / a.n_blocks_n;
             const int img = mt / a.tiles_per_img, ti = mt % a.tiles_per_img;      // img relative to the output base
@@ -394,6 +402,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int c0 = half * 32; c0 < a.bn; c0 += (DUAL ? 32 : 64)) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
+                if (a.dbg & 1) continue;
                 const int cols = (BK16 || WIN) ? min(32, a.bn - c0) : 32;          // 16 when the N tile is not a multiple of 32
                 if (bias) {
 #pragma unroll
@@ -431,7 +440,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     }
                     __syncwarp();
                 }
-                if (a.stats) {
+                if (a.stats && !(a.dbg & 2)) {
                     // fused instance-norm statistics: per-channel sum and sum of squares over this warp's 32 rows, 16
                     // columns per pass through a padded shared-memory transpose (conflict-free both ways): lanes 0-15 sum
                     // rows 0-15 of column `lane`, lanes 16-31 rows 16-31 of column `lane-16`; one shuffle joins the halves
@@ -818,6 +827,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             for (int c0 = 0; c0 < a.bn; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
+                if (a.dbg & 1) continue;
                 if (valid) {
                     uint32_t pk[16];
 #pragma unroll
@@ -1635,7 +1645,9 @@ int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, const CUten
     // measured on B200 (profiles/r01_tc_kernels.md): the pair kernel lowers L2 traffic (lts 49 % -> 37 %) but not the
     // duration (119 us vs 117 us at the C3 trunk shape), so the 1-CTA kernel stays the default
     if (g_use_2cta < 0) { const char* e = getenv("CG_ENABLE_2CTA"); g_use_2cta = (e && e[0] == '1') ? 1 : 0; }
-    if (g_use_2cta && mapB2 && !a.stats && !a.bk16 && a.bn >= 32 && ((a.nb * a.tiles_per_img) % 2 == 0)) {
+    static const int dbg = [] { const char* e = getenv("CG_TC_DBG"); return e ? atoi(e) : 0; }();      // measurement only
+    a.dbg = dbg;
+    if (g_use_2cta && mapB2 && (!a.stats || (dbg & 1)) && !a.bk16 && a.bn >= 32 && ((a.nb * a.tiles_per_img) % 2 == 0)) {
         const int stage = A_TILE_BYTES + (a.bn / 2) * 128;
         int s2 = (227 * 1024 - 2048) / stage;
         a.stages = s2 > 8 ? 8 : s2;
@@ -1655,13 +1667,24 @@ int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, const CUten
         return CG_OK;
     }
     const int stage_b = a.bk16 ? (a.tps > 1 ? a.tps * a.cin16 : a.groups) * (4096 + a.bn * 32) : (A_TILE_BYTES + a.bn * 128);
-    const bool dual = a.bn <= 128 && 2 * stage_b + 1024 + 256 + EPI_SCRATCH / 2 <= 110 * 1024;
+    // epilogue variant (see conv_tc_kernel): two epilogue groups for the short main loops; CG_EPI1=0 switches them off (A/B),
+    // CG_EPI1_KS moves the K-step threshold
+    static const int epi1_ks = [] { const char* e = getenv("CG_EPI1"); if (e && e[0] == '0') return -1;
+                                    const char* k = getenv("CG_EPI1_KS"); return k ? atoi(k) : 4; }();
+    const int ksteps = a.n_taps * a.cchunks;
+    const bool plain = !a.bk16 && a.win_C == 0;
+    int epi = 0;
+    if (plain && ksteps <= epi1_ks) epi = 1;
+    const int scratch_w = 32 * 17 * 4;                       // per epilogue warp
+    const bool dual = a.bn <= 128 && 2 * stage_b + 1024 + 256 + (epi == 1 ? 8 : 4) * scratch_w <= 110 * 1024;
+    const int epi_warps = (dual ? 4 : EPI_WARPS) * (epi == 1 ? 2 : 1);
+    const int scratch = epi_warps * scratch_w;
     {
-        int sN = ((dual ? 110 : 227) * 1024 - 1024 - 256 - (dual ? EPI_SCRATCH / 2 : EPI_SCRATCH)) / stage_b;
+        int sN = ((dual ? 110 : 227) * 1024 - 1024 - 256 - scratch) / stage_b;
         a.stages = sN > 8 ? 8 : sN;
     }
     a.idesc = make_idesc(128, a.bn, 0, 0);
-    const size_t smem = (size_t)a.stages * stage_b + 1024 + 256 + (dual ? EPI_SCRATCH / 2 : EPI_SCRATCH);
+    const size_t smem = (size_t)a.stages * stage_b + 1024 + 256 + scratch;
     static std::atomic<unsigned long long> attr_set{0};
     if (cg_first_on_device(attr_set)) {
         CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1670,20 +1693,25 @@ int tc_conv_launch(const CUtensorMap* mapA, const CUtensorMap* mapB, const CUten
         CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     }
     const int total = a.nb * a.tiles_per_img * a.n_blocks_n;
     const int slots = (dual ? 2 : 1) * num_sms();
     int grid = total < slots ? total : slots;
+    const dim3 threads((2 + epi_warps) * 32);
     int pi = prof_begin(st);
     if (a.win_C > 0) {
-        if (dual) launch_pdl(conv_tc_kernel<false, true, true>, dim3(grid), dim3(TC_THREADS), smem, st, *mapA, *mapB, out, bias, a);
-        else launch_pdl(conv_tc_kernel<false, false, true>, dim3(grid), dim3(CONV_THREADS), smem, st, *mapA, *mapB, out, bias, a);
+        if (dual) launch_pdl(conv_tc_kernel<false, true, true>, dim3(grid), threads, smem, st, *mapA, *mapB, out, bias, a);
+        else launch_pdl(conv_tc_kernel<false, false, true>, dim3(grid), threads, smem, st, *mapA, *mapB, out, bias, a);
     } else if (dual) {
-        if (a.bk16) launch_pdl(conv_tc_kernel<true, true>, dim3(grid), dim3(TC_THREADS), smem, st, *mapA, *mapB, out, bias, a);
-        else launch_pdl(conv_tc_kernel<false, true>, dim3(grid), dim3(TC_THREADS), smem, st, *mapA, *mapB, out, bias, a);
+        if (a.bk16) launch_pdl(conv_tc_kernel<true, true>, dim3(grid), threads, smem, st, *mapA, *mapB, out, bias, a);
+        else if (epi == 1) launch_pdl(conv_tc_kernel<false, true, false, 1>, dim3(grid), threads, smem, st, *mapA, *mapB, out, bias, a);
+        else launch_pdl(conv_tc_kernel<false, true>, dim3(grid), threads, smem, st, *mapA, *mapB, out, bias, a);
     } else {
-        if (a.bk16) launch_pdl(conv_tc_kernel<true, false>, dim3(grid), dim3(CONV_THREADS), smem, st, *mapA, *mapB, out, bias, a);
-        else launch_pdl(conv_tc_kernel<false, false>, dim3(grid), dim3(CONV_THREADS), smem, st, *mapA, *mapB, out, bias, a);
+        if (a.bk16) launch_pdl(conv_tc_kernel<true, false>, dim3(grid), threads, smem, st, *mapA, *mapB, out, bias, a);
+        else if (epi == 1) launch_pdl(conv_tc_kernel<false, false, false, 1>, dim3(grid), threads, smem, st, *mapA, *mapB, out, bias, a);
+        else launch_pdl(conv_tc_kernel<false, false>, dim3(grid), threads, smem, st, *mapA, *mapB, out, bias, a);
     }
     prof_end(pi, st, flops, prof_key(a.win_C > 0 ? 5 : 1, a.n_taps, a.cchunks, a.bn, a.tiles_per_img, a.nb));
     CG_LAUNCH_CHECK();

@@ -15,6 +15,7 @@ struct TcConvArgs {
     int stages;
     uint32_t idesc;
     int bk16, groups, cin16;                    // 16-channel K groups (SWIZZLE_32B): `groups` per K step, cin16 = Cin/16 in total
+    int dbg;                                    // measurement only (CG_TC_DBG): 1 = epilogue reads TMEM and stores nothing, 2 = no fused statistics
     int tps;                                    // bk16, Cin <= 64: filter taps per K step (each its own A box, ONE B box)
     float* stats;                               // nullable: [N][Cout][2] running (sum, sum of squares) of the outputs
     // fold mode (data gradient that feeds the adjoint of a reflection pad): output pixels inside the pad border go straight

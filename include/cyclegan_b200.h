@@ -192,6 +192,10 @@ int cg_optimizer_apply(const cg_adam_cfg* cfg, float* params_dev, const float* g
                        float* slot_v_dev, size_t n, int64_t iterations, void* stream);
 int cg_trainer_get_iterations(cg_trainer_t tr, int64_t iters[4]);   /* optimizer.iterations (model.py:314-315)  */
 int cg_trainer_set_iterations(cg_trainer_t tr, const int64_t iters[4]);
+/* The trainer keeps the plans (buffer layout, TMA descriptors, captured CUDA graphs) of the last few batch shapes it has
+ * seen, so the ragged last batch of an epoch (model.py:197, `dataset.batch(batch_size)` without drop_remainder) switches
+ * plans instead of re-planning.  plans_built = layouts computed so far, parked = plans kept besides the current one. */
+int cg_trainer_plan_count(cg_trainer_t tr, int64_t* plans_built, int* parked);
 /* pointer to an image the last step produced, for tests: 0 fake_b 1 same_b 2 fake_a 3 same_a 4 cycled_a 5 cycled_b */
 int cg_trainer_fetch_image(cg_trainer_t tr, int which, float* out_dev, void* stream);
 

@@ -117,6 +117,37 @@ def test_cuda_graph_replay_matches_eager_steps(mode):
         shutil.rmtree(folder, ignore_errors=True)
 
 
+def test_ragged_last_batch_switches_plans_and_keeps_graphs():
+    """model.py:197: `train_dataset.batch(batch_size)` keeps the ragged last batch, so every epoch alternates between two batch
+    shapes.  The trainer keeps one plan (layout, TMA descriptors, captured CUDA graphs) per shape instead of re-planning:
+    three epochs of (2, 2, 1)-sized batches build exactly two plans, and the steps equal those of an eager trainer."""
+    import ctypes
+    folder = tempfile.mkdtemp(prefix="cg_b200_")
+    try:
+        data = _dataset(5, size=32, seed=4)
+        batches = [(np.stack([t[0] for t in data[i:i + 2]]), np.stack([t[1] for t in data[i:i + 2]])) for i in (0, 2, 4)]
+        assert [x[0].shape[0] for x in batches] == [2, 2, 1]
+        runs = []
+        for disable in ("0", "1"):
+            os.environ["CG_DISABLE_GRAPH"] = disable
+            try:
+                gan = _gan(folder)
+                for i, n in enumerate((gan.g_AB, gan.g_BA, gan.d_A, gan.d_B)):
+                    n.initialize(11 + i)
+                ms = [{k: float(v) for k, v in gan.train_step(a, b).items()} for _ in range(3) for a, b in batches]
+                built, parked = ctypes.c_int64(), ctypes.c_int()
+                _lib.check(_lib.load().cg_trainer_plan_count(gan._trainer, ctypes.byref(built), ctypes.byref(parked)), "plan_count")
+                assert built.value == 2 and parked.value == 1, (built.value, parked.value)
+                runs.append(ms)
+            finally:
+                os.environ.pop("CG_DISABLE_GRAPH", None)
+        for k, (m1, m2) in enumerate(zip(*runs)):
+            for key in m1:      # same drift model as test_cuda_graph_replay_matches_eager_steps (Adam + atomics' summation order)
+                assert abs(m1[key] - m2[key]) <= (2e-4 if k <= 1 else 3e-3) * max(1.0, abs(m2[key])), (k, key, m1[key], m2[key])
+    finally:
+        shutil.rmtree(folder, ignore_errors=True)
+
+
 def test_predict_path_like_predict_py():
     """predict.py:20-39: uint8 image -> normalize -> model(x)[0] -> (y+1)*127.5 -> uint8."""
     g = create_model(C.FIX_RESNET, mode="bf16")
