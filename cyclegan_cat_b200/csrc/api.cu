@@ -199,6 +199,23 @@ extern "C" int cg_net_create(const cg_layer_desc* layers, int n_layers, int mode
             }
         }
     }
+    // zero-copy concat: see LayerInfo::cat_layer (CG_DISABLE_CATFUSE=1: plain slice copies, the A/B and test hook)
+    {
+        const char* off = getenv("CG_DISABLE_CATFUSE");
+        if (!(off && off[0] == '1'))
+            for (int j = 0; j < n_layers; ++j) {
+                LayerInfo& Cc = net->layers[j];
+                if (Cc.skipped || Cc.d.op != CG_OP_CONCAT || Cc.d.in0 == Cc.d.in1) continue;
+                for (int i = 0; i < j; ++i) {
+                    LayerInfo& L = net->layers[i];
+                    if (L.skipped || L.cat_layer >= 0) continue;
+                    if (L.d.op == CG_OP_AVGPOOL && L.d.in0 == Cc.d.in0 && Cc.cat_in0_pool < 0) { L.cat_layer = j; Cc.cat_in0_pool = i; }
+                    if (L.d.op == CG_OP_UPSAMPLE && L.out_t == Cc.d.in1 && net->n_consumers[L.out_t] == 1 && Cc.cat_in1_up < 0) {
+                        L.cat_layer = j; Cc.cat_in1_up = i;
+                    }
+                }
+            }
+    }
     // A conv / transposed-conv bias that feeds ONLY an instance norm has an identically zero gradient: the norm subtracts
     // the per-(sample, channel) mean, so sum_pixels dL/dy == 0 ('zero-by-construction gradients').  The
     // reference computes rounding noise there; this library writes the exact value 0 and skips the reduction.

@@ -54,10 +54,16 @@ template <typename T> int k_add(const T* a, const T* b, T* y, size_t n, cudaStre
 template <typename T> int k_copy_acc(const T* src, T* dst, size_t n, int accumulate, cudaStream_t st);
 template <typename T> int k_slice_copy(const T* src, int Cs, int so, T* dst, int Cd, int doff, int Cc, size_t npix,
                                        int accumulate, cudaStream_t st);
-template <typename T> int k_avgpool_fwd(const T* x, T* y, int N, int H, int W, int C, cudaStream_t st);
-template <typename T> int k_avgpool_bwd(const T* dy, T* dx, int N, int H, int W, int C, int accumulate, cudaStream_t st);
-template <typename T> int k_upsample_fwd(const T* x, T* y, int N, int H, int W, int C, cudaStream_t st);
-template <typename T> int k_upsample_bwd(const T* dy, T* dx, int N, int H, int W, int C, int accumulate, cudaStream_t st);
+// `cat` (nullable): zero-copy concat -- the concat tensor / its gradient with cat_c channels, slice at channel cat_off
+// (avgpool: the skip copy written / the skip slice added in the same pass; upsample: writes to / gathers from its slice)
+template <typename T> int k_avgpool_fwd(const T* x, T* y, int N, int H, int W, int C, cudaStream_t st, T* cat = nullptr,
+                                        int cat_c = 0, int cat_off = 0);
+template <typename T> int k_avgpool_bwd(const T* dy, T* dx, int N, int H, int W, int C, int accumulate, cudaStream_t st,
+                                        const T* dcat = nullptr, int cat_c = 0, int cat_off = 0);
+template <typename T> int k_upsample_fwd(const T* x, T* y, int N, int H, int W, int C, cudaStream_t st, T* cat = nullptr,
+                                         int cat_c = 0, int cat_off = 0);
+template <typename T> int k_upsample_bwd(const T* dy, T* dx, int N, int H, int W, int C, int accumulate, cudaStream_t st,
+                                         const T* dcat = nullptr, int cat_c = 0, int cat_off = 0);
 
 // ---- losses (value + gradient seed in one pass), Adam ----
 // sum_out += sum_i L(d_i, target); correct_out += #{(d_i > 0.5) == target}; grad_i = grad_scale * dL/dd_i

@@ -680,9 +680,15 @@ template <typename T> int k_slice_copy(const T* src, int Cs, int so, T* dst, int
 // 2x2 average pooling / nearest x2 upsampling and their adjoints.  MODE: 0 pool fwd, 1 pool bwd,
 // 2 upsample fwd, 3 upsample bwd.  (H, W) is always the LARGE grid; the small one is H/2 x W/2.
 // ------------------------------------------------------------------------------------------
+// Zero-copy concat (unet.py:109, `Concatenate()([skip, x])`): `cat` is the concat tensor (or its gradient) with `cat_cv`
+// channel vectors per pixel, the slice of interest starting at vector `cat_ov`.
+//   MODE 0 + cat : the pool also writes the copy of its input (the skip) into the concat tensor -- it reads all of it anyway
+//   MODE 1 + cat : the pool's backward adds the skip slice of the concat gradient, so dSkip is written in one pass
+//   MODE 2 + cat : the upsample writes straight into its slice of the concat tensor (`out` unused)
+//   MODE 3 + cat : the upsample's backward gathers from its slice of the concat gradient (`in` unused)
 template <typename T, int VEC, int MODE>
 __global__ void resample_kernel(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int Cv,
-                                int accumulate) {
+                                int accumulate, T* __restrict__ cat, int cat_cv, int cat_ov) {
     const int Hs = H / 2, Ws = W / 2;
     const bool out_small = (MODE == 0 || MODE == 3);
     const int Ho = out_small ? Hs : H, Wo = out_small ? Ws : W;
@@ -700,7 +706,10 @@ __global__ void resample_kernel(const T* __restrict__ in, T* __restrict__ out, i
             for (int a = 0; a < 2; ++a)
                 for (int b = 0; b < 2; ++b) {
                     float v[VEC];
-                    load_vec<T, VEC>(in + ((((size_t)n * H + 2 * h + a) * W + 2 * w + b) * Cv + cv) * VEC, v);
+                    const size_t pix = ((size_t)n * H + 2 * h + a) * W + 2 * w + b;
+                    if (MODE == 3 && cat) load_vec<T, VEC>(cat + (pix * cat_cv + cat_ov + cv) * VEC, v);
+                    else load_vec<T, VEC>(in + (pix * Cv + cv) * VEC, v);
+                    if (MODE == 0 && cat) store_vec<T, VEC>(cat + (pix * cat_cv + cat_ov + cv) * VEC, v);
 #pragma unroll
                     for (int j = 0; j < VEC; ++j) acc[j] += v[j];
                 }
@@ -713,7 +722,17 @@ __global__ void resample_kernel(const T* __restrict__ in, T* __restrict__ out, i
             if (MODE == 1) {
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) acc[j] *= 0.25f;
+                if (cat) {
+                    float v[VEC];
+                    load_vec<T, VEC>(cat + ((r * Wo + w) * cat_cv + cat_ov + cv) * VEC, v);      // r = n * Ho + h
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) acc[j] += v[j];
+                }
             }
+        }
+        if (MODE == 2 && cat) {
+            store_vec<T, VEC>(cat + ((r * Wo + w) * cat_cv + cat_ov + cv) * VEC, acc);
+            continue;
         }
         if (accumulate) {
             float o[VEC];
@@ -725,28 +744,34 @@ __global__ void resample_kernel(const T* __restrict__ in, T* __restrict__ out, i
     }
 }
 template <typename T, int MODE>
-static int resample_launch(const T* in, T* out, int N, int H, int W, int C, int accumulate, cudaStream_t st) {
+static int resample_launch(const T* in, T* out, int N, int H, int W, int C, int accumulate, cudaStream_t st,
+                           T* cat = nullptr, int cat_c = 0, int cat_off = 0) {
     constexpr int VW = VecWidth<T>::value;
     const bool out_small = (MODE == 0 || MODE == 3);
     size_t total = (size_t)N * (out_small ? (H / 2) * (W / 2) : H * W) * C;
-    if (C % VW == 0)
-        resample_kernel<T, VW, MODE><<<ew_blocks(total / VW), EW_THREADS, 0, st>>>(in, out, N, H, W, C / VW, accumulate);
-    else resample_kernel<T, 1, MODE><<<ew_blocks(total), EW_THREADS, 0, st>>>(in, out, N, H, W, C, accumulate);
+    if (C % VW == 0 && cat_c % VW == 0 && cat_off % VW == 0)
+        resample_kernel<T, VW, MODE><<<ew_blocks(total / VW), EW_THREADS, 0, st>>>(in, out, N, H, W, C / VW, accumulate, cat,
+                                                                                  cat_c / VW, cat_off / VW);
+    else resample_kernel<T, 1, MODE><<<ew_blocks(total), EW_THREADS, 0, st>>>(in, out, N, H, W, C, accumulate, cat, cat_c, cat_off);
     CG_LAUNCH_CHECK();
     return CG_OK;
 }
 // H, W are the INPUT sizes of the forward op
-template <typename T> int k_avgpool_fwd(const T* x, T* y, int N, int H, int W, int C, cudaStream_t st) {
-    return resample_launch<T, 0>(x, y, N, H, W, C, 0, st);
+template <typename T> int k_avgpool_fwd(const T* x, T* y, int N, int H, int W, int C, cudaStream_t st, T* cat, int cat_c,
+                                        int cat_off) {
+    return resample_launch<T, 0>(x, y, N, H, W, C, 0, st, cat, cat_c, cat_off);
 }
-template <typename T> int k_avgpool_bwd(const T* dy, T* dx, int N, int H, int W, int C, int accumulate, cudaStream_t st) {
-    return resample_launch<T, 1>(dy, dx, N, H, W, C, accumulate, st);
+template <typename T> int k_avgpool_bwd(const T* dy, T* dx, int N, int H, int W, int C, int accumulate, cudaStream_t st,
+                                        const T* dcat, int cat_c, int cat_off) {
+    return resample_launch<T, 1>(dy, dx, N, H, W, C, accumulate, st, const_cast<T*>(dcat), cat_c, cat_off);
 }
-template <typename T> int k_upsample_fwd(const T* x, T* y, int N, int H, int W, int C, cudaStream_t st) {
-    return resample_launch<T, 2>(x, y, N, 2 * H, 2 * W, C, 0, st);
+template <typename T> int k_upsample_fwd(const T* x, T* y, int N, int H, int W, int C, cudaStream_t st, T* cat, int cat_c,
+                                         int cat_off) {
+    return resample_launch<T, 2>(x, y, N, 2 * H, 2 * W, C, 0, st, cat, cat_c, cat_off);
 }
-template <typename T> int k_upsample_bwd(const T* dy, T* dx, int N, int H, int W, int C, int accumulate, cudaStream_t st) {
-    return resample_launch<T, 3>(dy, dx, N, 2 * H, 2 * W, C, accumulate, st);
+template <typename T> int k_upsample_bwd(const T* dy, T* dx, int N, int H, int W, int C, int accumulate, cudaStream_t st,
+                                         const T* dcat, int cat_c, int cat_off) {
+    return resample_launch<T, 3>(dy, dx, N, 2 * H, 2 * W, C, accumulate, st, const_cast<T*>(dcat), cat_c, cat_off);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -876,10 +901,10 @@ int k_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, f
     template int k_add<T>(const T*, const T*, T*, size_t, cudaStream_t);                                        \
     template int k_copy_acc<T>(const T*, T*, size_t, int, cudaStream_t);                                        \
     template int k_slice_copy<T>(const T*, int, int, T*, int, int, int, size_t, int, cudaStream_t);             \
-    template int k_avgpool_fwd<T>(const T*, T*, int, int, int, int, cudaStream_t);                              \
-    template int k_avgpool_bwd<T>(const T*, T*, int, int, int, int, int, cudaStream_t);                         \
-    template int k_upsample_fwd<T>(const T*, T*, int, int, int, int, cudaStream_t);                             \
-    template int k_upsample_bwd<T>(const T*, T*, int, int, int, int, int, cudaStream_t);                        \
+    template int k_avgpool_fwd<T>(const T*, T*, int, int, int, int, cudaStream_t, T*, int, int);                \
+    template int k_avgpool_bwd<T>(const T*, T*, int, int, int, int, int, cudaStream_t, const T*, int, int);     \
+    template int k_upsample_fwd<T>(const T*, T*, int, int, int, int, cudaStream_t, T*, int, int);               \
+    template int k_upsample_bwd<T>(const T*, T*, int, int, int, int, int, cudaStream_t, const T*, int, int);    \
     template int k_adv_loss<T>(const T*, size_t, float, int, float, T*, float*, float*, cudaStream_t);          \
     template int k_l1_loss<T>(const T*, const T*, size_t, float, T*, int, float*, cudaStream_t);
 INSTANTIATE(float)

@@ -718,6 +718,8 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
     const cg_net_s* net = c->net;
     const int N = c->N;
     std::vector<char> stats_done(net->layers.size() + 1, 0), fused_done(net->layers.size() + 1, 0);
+    std::vector<char> cat_done(net->layers.size() + 1, 0);      // CONCAT layer: bit 0 / 1 = in0 / in1 already in place
+    bool upsample_fused = false;
     c->live.assign(net->layers.size() + 1, 0);
     c->live[0] = 1;
     // every statistics table of this call is zeroed by ONE memset (they are accumulated into by atomics)
@@ -873,12 +875,27 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
             case CG_OP_CONCAT: {
                 int ca = net->chan[d.in0], cb = net->chan[d.in1];
                 size_t npix = (size_t)N * h * w;
-                CG_TRY(k_slice_copy<T>(x, ca, 0, y, ca + cb, 0, ca, npix, 0, st));
-                CG_TRY(k_slice_copy<T>((const T*)c->act(d.in1), cb, 0, y, ca + cb, ca, cb, npix, 0, st));
+                // zero-copy halves: the pool that reads the skip / the upsample that produces x have already written them
+                if (!(cat_done[i] & 1)) CG_TRY(k_slice_copy<T>(x, ca, 0, y, ca + cb, 0, ca, npix, 0, st));
+                if (!(cat_done[i] & 2)) CG_TRY(k_slice_copy<T>((const T*)c->act(d.in1), cb, 0, y, ca + cb, ca, cb, npix, 0, st));
                 break;
             }
-            case CG_OP_AVGPOOL: CG_TRY(k_avgpool_fwd<T>(x, y, N, h, w, d.cin, st)); break;
-            case CG_OP_UPSAMPLE: CG_TRY(k_upsample_fwd<T>(x, y, N, h, w, d.cin, st)); break;
+            case CG_OP_AVGPOOL:
+                if (L.cat_layer >= 0) {        // also writes the copy of its input into the concat tensor (channels [0, cin))
+                    const LayerInfo& Cc = net->layers[L.cat_layer];
+                    CG_TRY(k_avgpool_fwd<T>(x, y, N, h, w, d.cin, st, (T*)c->act(Cc.out_t), net->chan[Cc.out_t], 0));
+                    cat_done[L.cat_layer] |= 1;
+                } else CG_TRY(k_avgpool_fwd<T>(x, y, N, h, w, d.cin, st));
+                break;
+            case CG_OP_UPSAMPLE:
+                if (L.cat_layer >= 0) {        // writes straight into its slice of the concat tensor; its own tensor is not materialised
+                    const LayerInfo& Cc = net->layers[L.cat_layer];
+                    CG_TRY(k_upsample_fwd<T>(x, (T*)nullptr, N, h, w, d.cin, st, (T*)c->act(Cc.out_t), net->chan[Cc.out_t],
+                                             net->chan[Cc.d.in0]));
+                    cat_done[L.cat_layer] |= 2;
+                    upsample_fused = true;
+                } else CG_TRY(k_upsample_fwd<T>(x, y, N, h, w, d.cin, st));
+                break;
             case CG_OP_DROPOUT: {
                 const int grp = c->bn_group > 0 ? c->bn_group : N;
                 if (N % grp || N / grp > 4) { cg_set_error("dropout: batch %d / call size %d", N, grp); return CG_ERR_INVALID; }
@@ -887,7 +904,8 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
             }
             default: cg_set_error("unknown op %d", d.op); return CG_ERR_INVALID;
         }
-        if (d.op != CG_OP_INORM && d.op != CG_OP_RPAD && d.op != CG_OP_ADD) c->live[tout] = 1;
+        if (d.op != CG_OP_INORM && d.op != CG_OP_RPAD && d.op != CG_OP_ADD) c->live[tout] = upsample_fused ? 0 : 1;
+        upsample_fused = false;
     }
     c->forwarded = true;
     return CG_OK;
@@ -917,6 +935,9 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
         return (T*)(c->arena + c->grad_off[t]);
     };
     std::vector<char> written(nl + 1, 0), fold_done(nl + 1, 0);
+    std::vector<int> pend_pool(nl, -1);       // AVGPOOL layer -> CONCAT layer whose skip slice its backward adds (zero-copy concat)
+    std::vector<int> up_src(nl, -1);          // UPSAMPLE layer -> CONCAT layer whose gradient slice it gathers from
+    bool defer_written = false;
     auto need = [&](int t) -> bool { return dx_in != nullptr || (t != 0 && net->dep_params[t]); };
     // the backward sums of every instance norm of this call are cleared by ONE memset (sub-batch relative tables)
     if (c->sums_bytes) CG_TRY(zero_region(c->arena + c->scratch_off, c->sums_bytes, st));
@@ -941,8 +962,16 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
         if (L.skipped) continue;
         const cg_layer_desc& d = L.d;
         const int tin = d.in0, tout = L.out_t;
-        if (!need(tout) && tout != nl) continue;
-        if (!written[tout] && tout != nl) continue;       // nothing downstream asked for it
+        if ((!need(tout) || !written[tout]) && tout != nl) {      // nothing downstream asked for it
+            if (d.op == CG_OP_AVGPOOL && pend_pool[i] >= 0 && need(d.in0)) {     // ... but a concat left its skip slice to this pool
+                const LayerInfo& Cc = net->layers[pend_pool[i]];
+                const int ca = net->chan[d.in0];
+                CG_TRY(k_slice_copy<T>(G(Cc.out_t), net->chan[Cc.out_t], 0, G(d.in0), ca, 0, ca,
+                                       (size_t)nb * c->th[d.in0] * c->tw[d.in0], (int)written[d.in0], st));
+                written[d.in0] = 1;
+            }
+            continue;
+        }
         const T* dy = G(tout);
         const int h = c->th[tin], w = c->tw[tin], oh = c->th[tout], ow = c->tw[tout];
         const bool want_dx = need(tin);
@@ -1201,19 +1230,39 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
             case CG_OP_CONCAT: {
                 int ca = net->chan[d.in0], cb = net->chan[d.in1];
                 size_t npix = (size_t)nb * h * w;
-                if (want_dx) CG_TRY(k_slice_copy<T>(dy, ca + cb, 0, dx, ca, 0, ca, npix, acc, st));
+                const bool plain_grads = c->grad_halo[tout] == 0 && c->grad_halo[tin] == 0 && c->grad_halo[d.in1] == 0;
+                if (want_dx) {
+                    if (L.cat_in0_pool >= 0 && plain_grads) {      // the pool's backward adds this slice when it writes dSkip
+                        pend_pool[L.cat_in0_pool] = i;
+                        defer_written = true;
+                    } else CG_TRY(k_slice_copy<T>(dy, ca + cb, 0, dx, ca, 0, ca, npix, acc, st));
+                }
                 if (need(d.in1)) {
-                    CG_TRY(k_slice_copy<T>(dy, ca + cb, ca, G(d.in1), cb, 0, cb, npix,
-                                           (int)written[d.in1] || (d.in1 == tin && want_dx), st));
+                    if (L.cat_in1_up >= 0 && plain_grads && !written[d.in1])      // the upsample's backward gathers from the slice in place
+                        up_src[L.cat_in1_up] = i;
+                    else
+                        CG_TRY(k_slice_copy<T>(dy, ca + cb, ca, G(d.in1), cb, 0, cb, npix,
+                                               (int)written[d.in1] || (d.in1 == tin && want_dx), st));
                     written[d.in1] = 1;
                 }
                 break;
             }
             case CG_OP_AVGPOOL:
-                if (want_dx) CG_TRY(k_avgpool_bwd<T>(dy, dx, nb, h, w, d.cin, acc, st));
+                if (want_dx) {
+                    if (pend_pool[i] >= 0) {
+                        const LayerInfo& Cc = net->layers[pend_pool[i]];
+                        CG_TRY(k_avgpool_bwd<T>(dy, dx, nb, h, w, d.cin, acc, st, G(Cc.out_t), net->chan[Cc.out_t], 0));
+                    } else CG_TRY(k_avgpool_bwd<T>(dy, dx, nb, h, w, d.cin, acc, st));
+                }
                 break;
             case CG_OP_UPSAMPLE:
-                if (want_dx) CG_TRY(k_upsample_bwd<T>(dy, dx, nb, h, w, d.cin, acc, st));
+                if (want_dx) {
+                    if (up_src[i] >= 0) {
+                        const LayerInfo& Cc = net->layers[up_src[i]];
+                        CG_TRY(k_upsample_bwd<T>((const T*)nullptr, dx, nb, h, w, d.cin, acc, st, G(Cc.out_t), net->chan[Cc.out_t],
+                                                 net->chan[Cc.d.in0]));
+                    } else CG_TRY(k_upsample_bwd<T>(dy, dx, nb, h, w, d.cin, acc, st));
+                }
                 break;
             case CG_OP_DROPOUT:
                 if (want_dx) {
@@ -1226,7 +1275,8 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                 break;
             default: cg_set_error("unknown op %d", d.op); return CG_ERR_INVALID;
         }
-        if (want_dx) written[tin] = 1;
+        if (want_dx && !defer_written) written[tin] = 1;
+        defer_written = false;
         if (hook) CG_TRY(hook(hook_user, i));
     }
     return CG_OK;

@@ -41,6 +41,10 @@ struct LayerInfo {
     bool bias_grad_zero = false;   // the conv output feeds ONLY an instance norm: d(loss)/d(bias) == 0 exactly
     bool batch = false;            // INORM that is a BatchNormalization: statistics pooled over the samples of one call
     long long mm_off = -1, mv_off = -1;   // BatchNormalization: offsets (floats) of moving_mean / moving_variance in the state
+    // zero-copy concat (unet.py:109 `Concatenate()([skip, x])`): AVGPOOL whose input is in0 of concat layer `cat_layer` (the
+    // pool also writes the skip copy / its backward adds the skip slice), UPSAMPLE whose only consumer is that concat as in1
+    // (it writes into / gathers from its slice); on the CONCAT layer: the pool / upsample layer serving each input, or -1
+    int cat_layer = -1, cat_in0_pool = -1, cat_in1_up = -1;
     int drop_index = -1;           // DROPOUT: ordinal among the net's dropout layers (part of the mask key)
     int tc = 0;             // TC_* kind: which convs run on the tcgen05 kernels in bf16 mode
     long long pk_f = 0, pk_d = 0;   // byte offsets of the packed bf16 weights ([tap][Cout][Cin] / [tap][Cin][Cout])
