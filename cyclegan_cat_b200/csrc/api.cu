@@ -442,16 +442,17 @@ extern "C" int cg_net_forward(cg_net_t net, const float* params, const float* x,
 }
 
 // shared by cg_net_fetch_tensor / cg_trainer_fetch_tensor: copy tensor `t` of a planned, forwarded call out as float32 NHWC
-int fetch_tensor(const CallCtx* c, int t, float* out, int* shape4, cudaStream_t st) {
+int fetch_tensor(const CallCtx* c, int t, float* out, int* shape4, cudaStream_t st, int n0 = 0, int nb = -1) {
+    if (nb < 0) nb = c->N - n0;        // samples [n0, n0 + nb) of the planned batch
     const cg_net_s* net = c->net;
     if (!net || t < 0 || t > net->out_tensor()) { cg_set_error("fetch_tensor: tensor id %d out of range", t); return CG_ERR_INVALID; }
-    if (shape4) { shape4[0] = c->N; shape4[1] = c->th.empty() ? 0 : c->th[t]; shape4[2] = c->tw.empty() ? 0 : c->tw[t]; shape4[3] = net->chan[t]; }
+    if (shape4) { shape4[0] = nb; shape4[1] = c->th.empty() ? 0 : c->th[t]; shape4[2] = c->tw.empty() ? 0 : c->tw[t]; shape4[3] = net->chan[t]; }
     const bool live = c->forwarded && t < (int)c->live.size() && c->live[t] && (t == 0 || net->has_buffer[t]);
     if (!out) return live ? CG_OK : 1;            // query form: 0 = materialised by the last forward, 1 = not (fused away)
     if (!live) { cg_set_error("fetch_tensor: tensor %d was not materialised by the last forward", t); return CG_ERR_STATE; }
-    const size_t n = (size_t)c->N * c->sample_elems(t);
-    if (net->mode == CG_MODE_BF16) return k_convert_out<bf16>((const bf16*)c->act(t), out, n, st);
-    return k_convert_out<float>((const float*)c->act(t), out, n, st);
+    const size_t n = (size_t)nb * c->sample_elems(t), o = (size_t)n0 * c->sample_elems(t);
+    if (net->mode == CG_MODE_BF16) return k_convert_out<bf16>((const bf16*)c->act(t) + o, out, n, st);
+    return k_convert_out<float>((const float*)c->act(t) + o, out, n, st);
 }
 
 extern "C" int cg_net_fetch_tensor(cg_net_t net, int tensor, float* out, int shape4[4], void* stream) {

@@ -977,6 +977,9 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
         const bool want_dx = need(tin);
         T* dx = want_dx ? G(tin) : nullptr;
         const int acc = want_dx ? (int)written[tin] : 0;
+        // samples whose gradient w.r.t. `tin` anyone reads: all of them when a parameter lies upstream of tin, else only the
+        // first dx_nb the caller asked for (CallCtx::dx_nb; used by the 7x7 stem and the reflection pad in front of it)
+        const int nbx = (c->dx_nb > 0 && n0 == 0 && c->dx_nb < nb && !net->dep_params[tin]) ? c->dx_nb : nb;
         switch (d.op) {
             case CG_OP_CONV: {
                 ConvGeom g = conv_geom(d, nb, h, w, oh, ow);
@@ -1074,9 +1077,9 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                         if (want_dx) {
                             const TcConvLaunch& tl = c->tc[i].dgrad[0];
                             TcConvArgs a = tl.a;
-                            a.nb = nb;
-                            CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, big, nullptr, a, fl, st));
-                            CG_TRY(sp_diag_sum(big, nullptr, (bf16*)dx, nb, h, w, ow, d.k, d.cin, -1, st));
+                            a.nb = nbx;
+                            CG_TRY(tc_conv_launch(&tl.mapA, &tl.mapB, &tl.mapB2, big, nullptr, a, fl * nbx / nb, st));
+                            CG_TRY(sp_diag_sum(big, nullptr, (bf16*)dx, nbx, h, w, ow, d.k, d.cin, -1, st));
                         }
                     } else {
                         CG_TRY(sp_unfold_w((const bf16*)dy, big, nb, oh, ow, d.cout, oh + 2, w, d.k, -1, st));
@@ -1192,8 +1195,8 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                     CG_TRY(k_act_bwd<T>(A(tout), dy, dx, (size_t)nb * c->sample_elems(tin), d.act, d.slope, acc, st));
                 break;
             case CG_OP_RPAD:
-                if (want_dx && fold_done[i]) CG_TRY(k_rpad_bwd_border<T>(dy, dx, nb, h, w, d.cin, d.pad, st));
-                else if (want_dx) CG_TRY(k_rpad_bwd<T>(dy, dx, nb, h, w, d.cin, d.pad, acc, st));
+                if (want_dx && fold_done[i]) CG_TRY(k_rpad_bwd_border<T>(dy, dx, nbx, h, w, d.cin, d.pad, st));
+                else if (want_dx) CG_TRY(k_rpad_bwd<T>(dy, dx, nbx, h, w, d.cin, d.pad, acc, st));
                 break;
             case CG_OP_ADD: {
                 size_t n = (size_t)nb * c->sample_elems(tin);

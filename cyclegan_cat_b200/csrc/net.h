@@ -88,6 +88,8 @@ struct CallCtx {
     char* base = nullptr;               // activations workspace
     char* arena = nullptr;              // gradient arena (may be shared between calls)
     void* ext_input = nullptr;          // if set, tensor 0 lives here instead of at act_off[0]
+    int dx_nb = 0;                      // > 0: the caller reads dLoss/d(input) of the first dx_nb samples only (the layers that
+                                        // have no parameter upstream may skip the data gradient of the rest)
     bool forwarded = false;
     char* packed = nullptr;             // packed bf16 weights of this net (net_pack)
     char* tcs = nullptr;                // scratch for the unfolded tensors of the 7x7 stem / head (conv_special.cu)

@@ -200,7 +200,8 @@ int cg_trainer_plan_count(cg_trainer_t tr, int64_t* plans_built, int* parked);
 int cg_trainer_fetch_image(cg_trainer_t tr, int which, float* out_dev, void* stream);
 
 /* the same probe as cg_net_fetch_tensor for one of the six model calls of the last step:
- * call 0 g_AB([a;b]) 1 g_BA([b;a]) 2 g_BA(fake_b) 3 g_AB(fake_a) 4 d_A([a;fake_a]) 5 d_B([b;fake_b])  (model.py:93-106) */
+ * call 0 g_AB([a;b]) 1 g_BA([b;a]) 2 g_BA(fake_b) 3 g_AB(fake_a) 4 d_A([a;fake_a]) 5 d_B([b;fake_b])  (model.py:93-106).
+ * Calls 1 and 2 are executed as ONE g_BA launch sequence over [fake_b; b; a]; the probe returns each call's sample range. */
 int cg_trainer_fetch_tensor(cg_trainer_t tr, int call, int tensor, float* out_dev, int shape4[4], void* stream);
 
 /* ---- input pipeline (transform/data_load.py:20-34, predict.py:20-27), all HBM-bound streaming kernels ---------- */
