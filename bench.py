@@ -250,21 +250,31 @@ def run_infer(args, wl):
     sampler.start()
     lib.cg_launch_count(None, 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof_range = os.environ.get("CG_PROFILE_STEP") == "1"      # ncu --profile-from-start off: capture exactly the timed calls
+    if prof_range:
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(args.steps):
         g(x_dev)
     e1.record()
+    if prof_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop()
     launches = ctypes.c_int64()
     lib.cg_launch_count(ctypes.byref(launches), 0)
     # tensor-core share: one extra, instrumented call (CUDA-event pairs around every tensor-core launch)
+    keep = os.environ.get("CG_KEEP_PROF")             # per-launch CSV of that call (tools/prof_layers.py reads it)
+    if keep:
+        os.environ["CG_PROF_DUMP"] = keep
     lib.cg_prof_enable(1)
     g(x_dev)
     pms, pl, pfl = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
     lib.cg_prof_read(ctypes.byref(pms), ctypes.byref(pl), ctypes.byref(pfl))
     lib.cg_prof_enable(0)
+    os.environ.pop("CG_PROF_DUMP", None)
     for _ in range(2):
         e2e_once()
     barrier()

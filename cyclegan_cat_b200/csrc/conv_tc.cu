@@ -70,6 +70,19 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// One lane of a CONVERGED warp (elect.sync).  The MMA-issuing code is written as `if (elect_one()) { tcgen05.mma ... }` inside
+// warp-uniform control flow: operands that are uniform by data flow then stay in uniform registers.  Under `if (lane == 0)`
+// the compiler cannot prove uniformity and wraps every tcgen05 instruction in an ELECT / BRA.U.ANY loop (~25 instructions per
+// MMA; ncu showed the MMA warp of the narrow window layers executing instructions 100 % of the time, ~3000 cycles per tile).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 // arrive on an mbarrier when all MMAs issued so far by this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -250,32 +263,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // bk16: cchunks = K steps per tap (blocks of `groups` 16-channel groups), or several taps per K step
     const int ksteps = (BK16 && a.tps > 1) ? (a.n_taps + a.tps - 1) / a.tps : a.n_taps * a.cchunks;
 
-    if (warp == 0) {
-        if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int nblk = t % a.n_blocks_n, mt = t / a.n_blocks_n;
-                const int img = a.n0 + mt / a.tiles_per_img, ti = mt % a.tiles_per_img;
-                const int w0 = (ti % a.tiles_w) * a.Wb, h0 = (ti / a.tiles_w) * a.Hb;
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    if constexpr (BK16) {
-                        if (a.tps > 1) {        // Cin <= 64: `tps` taps per K step, one A box each, ONE B box of tps*bn weight rows
-                            const int t0 = ks * a.tps, nt = min(a.tps, a.n_taps - t0);
-                            mbar_wait(empty(s), ph ^ 1u);
-                            const uint32_t sa = smem0 + s * stage_bytes;
+    if (warp == 0) {        // TMA producer: the whole warp runs the loop (uniform control flow), one elected lane issues
+        int s = 0; uint32_t ph = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int nblk = t % a.n_blocks_n, mt = t / a.n_blocks_n;
+            const int img = a.n0 + mt / a.tiles_per_img, ti = mt % a.tiles_per_img;
+            const int w0 = (ti % a.tiles_w) * a.Wb, h0 = (ti / a.tiles_w) * a.Hb;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                if constexpr (BK16) {
+                    if (a.tps > 1) {        // Cin <= 64: `tps` taps per K step, one A box each, ONE B box of tps*bn weight rows
+                        const int t0 = ks * a.tps, nt = min(a.tps, a.n_taps - t0);
+                        mbar_wait(empty(s), ph ^ 1u);
+                        const uint32_t sa = smem0 + s * stage_bytes;
+                        if (elect_one()) {
                             mbar_expect_tx(full(s), (uint32_t)(nt * a.cin16) * 4096u + kg * (uint32_t)a.bn * 32u);
                             for (int j = 0; j < nt; ++j)
                                 tma_load_5d(sa + (uint32_t)(j * a.cin16) * 4096u, &mapA, full(s), 0, w0 + a.dw[t0 + j], h0 + a.dh[t0 + j],
                                             0, img);
                             tma_load_3d(sa + a_bytes, &mapB, full(s), 0, a.tb[t0] * a.b_rows_per_tap, 0);
-                            if (++s == S) { s = 0; ph ^= 1u; }
-                            continue;
                         }
+                        __syncwarp();
+                        if (++s == S) { s = 0; ph ^= 1u; }
+                        continue;
                     }
-                    const int tap = ks / a.cchunks, cc = ks - tap * a.cchunks;
-                    mbar_wait(empty(s), ph ^ 1u);
+                }
+                const int tap = ks / a.cchunks, cc = ks - tap * a.cchunks;
+                mbar_wait(empty(s), ph ^ 1u);
+                const uint32_t sa = smem0 + s * stage_bytes;
+                if (elect_one()) {
                     mbar_expect_tx(full(s), stage_bytes);
-                    const uint32_t sa = smem0 + s * stage_bytes;
                     if constexpr (BK16) {       // one box = `groups` 16-channel groups of this tap (out-of-range groups are zero-filled)
                         tma_load_5d(sa, &mapA, full(s), 0, w0 + a.dw[tap], h0 + a.dh[tap], cc * a.groups, img);
                         tma_load_3d(sa + a_bytes, &mapB, full(s), 0, a.tb[tap] * a.b_rows_per_tap + nblk * a.bn, cc * a.groups);
@@ -283,8 +299,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         tma_load_5d(sa, &mapA, full(s), cc * 64 + a.dc[tap], w0 + a.dw[tap], a.dp[tap], h0 + a.dh[tap], img);
                         tma_load_2d(sa + A_TILE_BYTES, &mapB, full(s), cc * 64, a.tb[tap] * a.b_rows_per_tap + nblk * a.bn);
                     }
-                    if (++s == S) { s = 0; ph ^= 1u; }
                 }
+                __syncwarp();
+                if (++s == S) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
@@ -303,8 +320,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const uint32_t sa = smem0 + s * stage_bytes;
                     win_fix(sa, a.Wb, a.Hb, w0, a.win_W, a.win_C, a.win_k, a.win_pl, a.dc[ks], lane);
                     __syncwarp();
-                    if (lane == 0) {
-                        tc_fence_after();
+                    tc_fence_after();
+                    if (elect_one()) {
                         const uint64_t adesc = make_smem_desc(sa, 16, 1024);
                         const uint64_t bdesc = make_smem_desc(sa + A_TILE_BYTES, 16, 1024);
 #pragma unroll
@@ -312,15 +329,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), a.idesc,
                                       (uint32_t)((ks | k) != 0));
                         umma_commit(empty(s));
+                        if (ks == ksteps - 1) umma_commit(tfull(acc));
                     }
                     __syncwarp();
                     if (++s == S) { s = 0; ph ^= 1u; }
                 }
-                if (lane == 0) umma_commit(tfull(acc));
-                __syncwarp();
             }
-        } else
-        if (lane == 0) {
+        } else {        // MMA issuer: uniform control flow for the whole warp, one elected lane issues (see elect_one)
             int s = 0; uint32_t ph = 0;
             int it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -333,36 +348,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     mbar_wait(full(s), ph);
                     tc_fence_after();
                     const uint32_t sa = smem0 + s * stage_bytes;
-                    if constexpr (BK16) {       // one K = 16 MMA per 16-channel group
-                        if (a.tps > 1) {
-                            const int nt = min(a.tps, a.n_taps - ks * a.tps);
-                            for (int j = 0; j < nt; ++j)
-                                for (int cg = 0; cg < a.cin16; ++cg)
-                                    umma_bf16(d_tmem, make_smem_desc32(sa + (uint32_t)(j * a.cin16 + cg) * 4096u),
-                                              make_smem_desc32(sa + a_bytes + (uint32_t)(cg * a.tps + j) * (uint32_t)a.bn * 32u), a.idesc,
-                                              (uint32_t)((ks | j | cg) != 0));
-                            umma_commit(empty(s));
-                            if (++s == S) { s = 0; ph ^= 1u; }
-                            continue;
-                        }
-                        const int cc = ks % a.cchunks;
-                        const int ng = min(a.groups, a.cin16 - cc * a.groups);
-                        for (int gq = 0; gq < ng; ++gq)
-                            umma_bf16(d_tmem, make_smem_desc32(sa + (uint32_t)gq * 4096u),
-                                      make_smem_desc32(sa + a_bytes + (uint32_t)gq * (uint32_t)a.bn * 32u), a.idesc,
-                                      (uint32_t)((ks | gq) != 0));
-                    } else {
-                        const uint64_t adesc = make_smem_desc(sa, 16, 1024);
-                        const uint64_t bdesc = make_smem_desc(sa + A_TILE_BYTES, 16, 1024);
+                    if (elect_one()) {
+                        if constexpr (BK16) {       // one K = 16 MMA per 16-channel group
+                            if (a.tps > 1) {
+                                const int nt = min(a.tps, a.n_taps - ks * a.tps);
+                                for (int j = 0; j < nt; ++j)
+                                    for (int cg = 0; cg < a.cin16; ++cg)
+                                        umma_bf16(d_tmem, make_smem_desc32(sa + (uint32_t)(j * a.cin16 + cg) * 4096u),
+                                                  make_smem_desc32(sa + a_bytes + (uint32_t)(cg * a.tps + j) * (uint32_t)a.bn * 32u), a.idesc,
+                                                  (uint32_t)((ks | j | cg) != 0));
+                            } else {
+                                const int cc = ks % a.cchunks;
+                                const int ng = min(a.groups, a.cin16 - cc * a.groups);
+                                for (int gq = 0; gq < ng; ++gq)
+                                    umma_bf16(d_tmem, make_smem_desc32(sa + (uint32_t)gq * 4096u),
+                                              make_smem_desc32(sa + a_bytes + (uint32_t)gq * (uint32_t)a.bn * 32u), a.idesc,
+                                              (uint32_t)((ks | gq) != 0));
+                            }
+                        } else {
+                            const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+                            const uint64_t bdesc = make_smem_desc(sa + A_TILE_BYTES, 16, 1024);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)     // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle row
-                            umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), a.idesc,
-                                      (uint32_t)((ks | k) != 0));
+                            for (int k = 0; k < 4; ++k)     // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle row
+                                umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), a.idesc,
+                                          (uint32_t)((ks | k) != 0));
+                        }
+                        umma_commit(empty(s));
+                        if (ks == ksteps - 1) umma_commit(tfull(acc));
                     }
-                    umma_commit(empty(s));
+                    __syncwarp();
                     if (++s == S) { s = 0; ph ^= 1u; }
                 }
-                umma_commit(tfull(acc));
             }
         }
     } else {
@@ -491,6 +507,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 // shared-memory tile (descriptor start + kh * 16 rows): (8 + k - 1) / (8 k) of the A traffic (0.34 for k = 4, 0.25 for
 // k = 7) and one barrier round trip per k K-steps.  Same warp roles and epilogue as conv_tc_kernel.
 // ------------------------------------------------------------------------------------------
+// (A second group of four epilogue warps for the DUAL instance -- one group per TMEM accumulator, as in conv_tc_kernel<EPI 1> --
+// was measured neutral on C2 and slower on C5 (7.73 -> 8.23 ms per 32-image call): these layers are not epilogue-bound.)
 template <bool DUAL>
 __global__ void __launch_bounds__(DUAL ? TC_THREADS : CONV_THREADS, DUAL ? 2 : 1)
 convw_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -529,21 +547,22 @@ convw_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
     const int total_tiles = a.nb * a.tiles_per_img;
 
-    if (warp == 0) {
-        if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int img = a.n0 + t / a.tiles_per_img, ti = t % a.tiles_per_img;
-                const int w0 = (ti % a.tiles_w) * a.Wb, h0 = (ti / a.tiles_w) * a.Hb;
-                for (int j = 0; j < nch; ++j) {
-                    mbar_wait(empty(s), ph ^ 1u);
+    if (warp == 0) {        // uniform control flow for the whole warp, one elected lane issues (see elect_one)
+        int s = 0; uint32_t ph = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int img = a.n0 + t / a.tiles_per_img, ti = t % a.tiles_per_img;
+            const int w0 = (ti % a.tiles_w) * a.Wb, h0 = (ti / a.tiles_w) * a.Hb;
+            for (int j = 0; j < nch; ++j) {
+                mbar_wait(empty(s), ph ^ 1u);
+                const uint32_t sa = smem0 + s * stage_bytes;
+                if (elect_one()) {
                     mbar_expect_tx(full(s), stage_bytes);
-                    const uint32_t sa = smem0 + s * stage_bytes;
                     tma_load_5d(sa, &mapA, full(s), 64 * j, w0, 0, h0 - a.win_pt, img);
                     for (int kh = 0; kh < k; ++kh)
                         tma_load_2d(sa + a_bytes + (uint32_t)kh * b_tile, &mapB, full(s), 0, (kh * nch + j) * a.bn);
-                    if (++s == S) { s = 0; ph ^= 1u; }
                 }
+                __syncwarp();
+                if (++s == S) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
@@ -561,8 +580,8 @@ convw_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 const uint32_t sa = smem0 + s * stage_bytes;
                 win_fix(sa, a.Wb, halo_h, w0, a.win_W, a.win_C, k, a.win_pl, 64 * j, lane);
                 __syncwarp();
-                if (lane == 0) {
-                    tc_fence_after();
+                tc_fence_after();
+                if (elect_one()) {
                     for (int kh = 0; kh < k; ++kh) {
                         const uint64_t adesc = make_smem_desc(sa + (uint32_t)(kh * a.Wb) * 128u, 16, 1024);
                         const uint64_t bdesc = make_smem_desc(sa + a_bytes + (uint32_t)kh * b_tile, 16, 1024);
@@ -572,12 +591,11 @@ convw_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                                       (uint32_t)((j | kh | kk) != 0));
                     }
                     umma_commit(empty(s));
+                    if (j == nch - 1) umma_commit(tfull(acc));
                 }
                 __syncwarp();
                 if (++s == S) { s = 0; ph ^= 1u; }
             }
-            if (lane == 0) umma_commit(tfull(acc));
-            __syncwarp();
         }
     } else {
         const int q = warp & 3;
@@ -908,17 +926,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     const int x_boxes = a.transposed ? nb_boxes : 2, y_boxes = a.transposed ? 2 : nb_boxes;
     const uint32_t x_off = a.transposed ? 2 * 8192u : 0u, y_off = a.transposed ? 0u : 2 * 8192u;
 
-    if (warp == 0) {
-        if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            for (int q = q_begin; q < q_end; ++q) {
-                const int img = q / a.chunks_per_img, r = q % a.chunks_per_img;
-                const int w0 = (r % a.chunks_w) * a.Wk, h0 = (r / a.chunks_w) * a.Hk;
-                mbar_wait(empty(s), ph ^ 1u);
+    if (warp == 0) {        // uniform control flow for the whole warp, one elected lane issues (see elect_one)
+        int s = 0; uint32_t ph = 0;
+        for (int q = q_begin; q < q_end; ++q) {
+            const int img = q / a.chunks_per_img, r = q % a.chunks_per_img;
+            const int w0 = (r % a.chunks_w) * a.Wk, h0 = (r / a.chunks_w) * a.Hk;
+            mbar_wait(empty(s), ph ^ 1u);
+            const uint32_t sa = smem0 + s * stage_bytes;
+            if (elect_one()) {
                 mbar_expect_tx(full(s), stage_bytes);
-                const uint32_t sa = smem0 + s * stage_bytes;
-                // (measured: every TMA instruction costs ~115 cycles of the K step on top of the MMA time, so dense
-                // operands are fetched with ONE grouped box instead of one box per 64 channels)
+                // dense operands are fetched with ONE grouped box instead of one box per 64 channels
                 if (a.x_grouped)
                     tma_load_5d(sa + x_off, &mapX, full(s), 0, w0 + a.dw[tap], h0 + a.dh[tap], x_c0 / 64, a.n0 + img);
                 else if (a.stack2)      // 64-channel X: the two 64-row halves of the A tile are two different taps
@@ -935,28 +952,32 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                     for (int b = 0; b < y_boxes; ++b)
                         tma_load_5d(sa + y_off + b * 8192u, &mapDY, full(s), y_c0 + b * 64, w0 + a.dy_off, 0, h0 + a.dy_off,
                                     a.y_n0 + img);
-                if (++s == S) { s = 0; ph ^= 1u; }
             }
+            __syncwarp();
+            if (++s == S) { s = 0; ph ^= 1u; }
         }
     } else if (warp == 1) {
-        if (lane == 0 && nq > 0) {
+        if (nq > 0) {
             int s = 0; uint32_t ph = 0;
             for (int i = 0; i < nq; ++i) {
                 mbar_wait(full(s), ph);
                 tc_fence_after();
                 const uint32_t sa = smem0 + s * stage_bytes;
-                // MN-major canonical layout: 64 channels contiguous (128 B), pixels (K) at 128 B, 8-pixel groups at
-                // SBO = 1024 B, next 64-channel group at LBO = 8192 B.  One MMA consumes K = 16 pixels = 2048 B.
-                const uint64_t adesc = make_smem_desc(sa, 8192, 1024);
-                const uint64_t bdesc = make_smem_desc(sa + 2 * 8192u, 8192, 1024);
+                if (elect_one()) {
+                    // MN-major canonical layout: 64 channels contiguous (128 B), pixels (K) at 128 B, 8-pixel groups at
+                    // SBO = 1024 B, next 64-channel group at LBO = 8192 B.  One MMA consumes K = 16 pixels = 2048 B.
+                    const uint64_t adesc = make_smem_desc(sa, 8192, 1024);
+                    const uint64_t bdesc = make_smem_desc(sa + 2 * 8192u, 8192, 1024);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), a.idesc,
-                              (uint32_t)((i | k) != 0));
-                umma_commit(empty(s));
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), a.idesc,
+                                  (uint32_t)((i | k) != 0));
+                    umma_commit(empty(s));
+                    if (i == nq - 1) umma_commit(tfull);
+                }
+                __syncwarp();
                 if (++s == S) { s = 0; ph ^= 1u; }
             }
-            umma_commit(tfull);
         }
     } else if (nq > 0) {
         const int q = warp & 3;
@@ -1052,39 +1073,43 @@ wgrad16_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     const int rows_total = a.n_taps * a.Cin;
     const int nslots = min(8, (rows_total - mb * 128 + 15) / 16);      // live 16-row slots of this block
 
-    if (warp == 0) {
-        if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            for (int q = q_begin; q < q_end; ++q) {
-                const int img = q / a.chunks_per_img, r = q % a.chunks_per_img;
-                const int w0 = (r % a.chunks_w) * a.Wk, h0 = (r / a.chunks_w) * a.Hk;
-                mbar_wait(empty(s), ph ^ 1u);
+    if (warp == 0) {        // uniform control flow for the whole warp, one elected lane issues (see elect_one)
+        int s = 0; uint32_t ph = 0;
+        for (int q = q_begin; q < q_end; ++q) {
+            const int img = q / a.chunks_per_img, r = q % a.chunks_per_img;
+            const int w0 = (r % a.chunks_w) * a.Wk, h0 = (r / a.chunks_w) * a.Hk;
+            mbar_wait(empty(s), ph ^ 1u);
+            const uint32_t sa = smem0 + s * stage_bytes;
+            if (elect_one()) {
                 mbar_expect_tx(full(s), (uint32_t)(nslots + ygroups) * 2048u);
-                const uint32_t sa = smem0 + s * stage_bytes;
                 for (int j = 0; j < nslots; ++j) {
                     const int row0 = (mb * 8 + j) * 16;
                     const int tap = row0 / a.Cin, cg = (row0 - tap * a.Cin) / 16;
                     tma_load_5d(sa + (uint32_t)j * 2048u, &mapX, full(s), 0, w0 + a.dw[tap], h0 + a.dh[tap], cg, a.n0 + img);
                 }
                 tma_load_5d(sa + 8u * 2048u, &mapDY, full(s), 0, w0, h0, 0, a.y_n0 + img);
-                if (++s == S) { s = 0; ph ^= 1u; }
             }
+            __syncwarp();
+            if (++s == S) { s = 0; ph ^= 1u; }
         }
     } else if (warp == 1) {
-        if (lane == 0 && nq > 0) {
+        if (nq > 0) {
             int s = 0; uint32_t ph = 0;
             for (int i = 0; i < nq; ++i) {
                 mbar_wait(full(s), ph);
                 tc_fence_after();
                 const uint32_t sa = smem0 + s * stage_bytes;
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)       // K = 16 pixels = 512 bytes inside each 2 KB group
-                    umma_bf16(tmem_base, make_smem_desc32_mn(sa + (uint32_t)k * 512u, 2048),
-                              make_smem_desc32_mn(sa + 8u * 2048u + (uint32_t)k * 512u, 2048), a.idesc, (uint32_t)((i | k) != 0));
-                umma_commit(empty(s));
+                    for (int k = 0; k < 4; ++k)       // K = 16 pixels = 512 bytes inside each 2 KB group
+                        umma_bf16(tmem_base, make_smem_desc32_mn(sa + (uint32_t)k * 512u, 2048),
+                                  make_smem_desc32_mn(sa + 8u * 2048u + (uint32_t)k * 512u, 2048), a.idesc, (uint32_t)((i | k) != 0));
+                    umma_commit(empty(s));
+                    if (i == nq - 1) umma_commit(tfull);
+                }
+                __syncwarp();
                 if (++s == S) { s = 0; ph ^= 1u; }
             }
-            umma_commit(tfull);
         }
     } else if (nq > 0) {
         const int q = warp & 3;
@@ -1170,20 +1195,21 @@ wgradw_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     const int nhalf = min(halves, a.steps - step0);          // live 64-row halves of this unit
     const int npair = (nhalf + 1) / 2;
 
-    if (warp == 0) {
-        if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            for (int q = q_begin; q < q_end; ++q) {
-                const int img = q / a.chunks_per_img, r = q % a.chunks_per_img;
-                const int w0 = (r % a.chunks_w) * a.Wk, h0 = (r / a.chunks_w) * a.Hk;
-                mbar_wait(empty(s), ph ^ 1u);
+    if (warp == 0) {        // uniform control flow for the whole warp, one elected lane issues (see elect_one)
+        int s = 0; uint32_t ph = 0;
+        for (int q = q_begin; q < q_end; ++q) {
+            const int img = q / a.chunks_per_img, r = q % a.chunks_per_img;
+            const int w0 = (r % a.chunks_w) * a.Wk, h0 = (r / a.chunks_w) * a.Hk;
+            mbar_wait(empty(s), ph ^ 1u);
+            const uint32_t sa = smem0 + s * stage_bytes;
+            if (elect_one()) {
                 mbar_expect_tx(full(s), (uint32_t)nhalf * 8192u + (uint32_t)ygroups * 2048u);
-                const uint32_t sa = smem0 + s * stage_bytes;
                 for (int b = 0; b < nhalf; ++b)
                     tma_load_5d(sa + (uint32_t)b * 8192u, &mapX, full(s), a.dc[step0 + b], w0, 0, h0 + a.dh[step0 + b], a.n0 + img);
                 tma_load_5d(sa + a_bytes, &mapDY, full(s), 0, w0, h0, 0, a.y_n0 + img);
-                if (++s == S) { s = 0; ph ^= 1u; }
             }
+            __syncwarp();
+            if (++s == S) { s = 0; ph ^= 1u; }
         }
     } else if (warp == 1) {
         if (nq > 0) {
@@ -1196,8 +1222,8 @@ wgradw_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 for (int b = 0; b < nhalf; ++b)
                     win_fix(sa + (uint32_t)b * 8192u, a.Wk, a.Hk, w0, a.W, a.C, a.k, a.pl, a.dc[step0 + b], lane);
                 __syncwarp();
-                if (lane == 0) {
-                    tc_fence_after();
+                tc_fence_after();
+                if (elect_one()) {
                     // A: MN-major SWIZZLE_128B (64 elements contiguous, pixels at 128 B, 8-pixel groups at SBO = 1 KB, the second
                     // 64-row half at LBO = 8 KB); B: MN-major SWIZZLE_32B 16-channel groups at LBO = 2 KB.  K = 16 pixels per MMA.
                     for (int pi = 0; pi < npair; ++pi) {
@@ -1208,11 +1234,11 @@ wgradw_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                                       make_smem_desc32_mn(sa + a_bytes + (uint32_t)k * 512u, 2048), a.idesc, (uint32_t)((i | k) != 0));
                     }
                     umma_commit(empty(s));
+                    if (i == nq - 1) umma_commit(tfull);
                 }
                 __syncwarp();
                 if (++s == S) { s = 0; ph ^= 1u; }
             }
-            if (lane == 0) umma_commit(tfull);
         }
     } else if (nq > 0) {
         const int q = warp & 3;
@@ -1303,19 +1329,20 @@ wgradh_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     const int q_end = min(total_chunks, q_begin + per);
     const int nq = q_end - q_begin;
 
-    if (warp == 0) {
-        if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            for (int q = q_begin; q < q_end; ++q) {
-                const int img = q / a.chunks_per_img, r = q % a.chunks_per_img;
-                const int w0 = (r % a.chunks_w) * a.Wk, h0 = (r / a.chunks_w) * a.Hk;
-                mbar_wait(empty(s), ph ^ 1u);
+    if (warp == 0) {        // uniform control flow for the whole warp, one elected lane issues (see elect_one)
+        int s = 0; uint32_t ph = 0;
+        for (int q = q_begin; q < q_end; ++q) {
+            const int img = q / a.chunks_per_img, r = q % a.chunks_per_img;
+            const int w0 = (r % a.chunks_w) * a.Wk, h0 = (r / a.chunks_w) * a.Hk;
+            mbar_wait(empty(s), ph ^ 1u);
+            const uint32_t sa = smem0 + s * stage_bytes;
+            if (elect_one()) {
                 mbar_expect_tx(full(s), stage_bytes);
-                const uint32_t sa = smem0 + s * stage_bytes;
                 tma_load_5d(sa, &mapX, full(s), 64 * j, w0, 0, h0 - a.pt, a.n0 + img);
                 tma_load_5d(sa + a_bytes, &mapDY, full(s), 0, w0, h0, 0, a.y_n0 + img);
-                if (++s == S) { s = 0; ph ^= 1u; }
             }
+            __syncwarp();
+            if (++s == S) { s = 0; ph ^= 1u; }
         }
     } else if (warp == 1) {
         if (nq > 0) {
@@ -1327,8 +1354,8 @@ wgradh_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 const uint32_t sa = smem0 + s * stage_bytes;
                 win_fix(sa, a.Wk, halo_h, w0, a.W, a.C, k, a.pl, 64 * j, lane);
                 __syncwarp();
-                if (lane == 0) {
-                    tc_fence_after();
+                tc_fence_after();
+                if (elect_one()) {
                     for (int pi = 0; pi < npair; ++pi) {
                         // rows 0-63 = kernel row 2*pi, rows 64-127 = kernel row 2*pi+1: the same halo one image row further down
                         const uint64_t adesc = make_smem_desc(sa + (uint32_t)(2 * pi * a.Wk) * 128u, (uint32_t)a.Wk * 128u, 1024);
@@ -1338,11 +1365,11 @@ wgradh_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                                       make_smem_desc32_mn(sa + a_bytes + (uint32_t)kk * 512u, 2048), a.idesc, (uint32_t)((i | kk) != 0));
                     }
                     umma_commit(empty(s));
+                    if (i == nq - 1) umma_commit(tfull);
                 }
                 __syncwarp();
                 if (++s == S) { s = 0; ph ^= 1u; }
             }
-            if (lane == 0) umma_commit(tfull);
         }
     } else if (nq > 0) {
         const int q = warp & 3;

@@ -95,7 +95,7 @@ def test_c3_full_size_gradients(mode):
 def test_c3_batch16_fp32_losses_and_edge_gradients():
     """C3 at the benchmark batch (16 pairs per step) in fp32 check mode, free running against the torch-CPU fp32 oracle:
     the four losses and g_AB's first and last kernel gradient.  (No forcing here -- 16 x the tensors would not fit a
-    test -- so the gradient gate carries the ReLU-flip noise of two fp32 implementations: a few 1e-3 at this size.)"""
+    test -- so the gradient gates carry the ReLU-flip noise of two free-running fp32 implementations.)"""
     from cyclegan_cat_b200.cyclegan.model import CycleGan
     gan = CycleGan(C.model_config(C.RESNET64, C.SIMPLE_D4), C.train_config(), mode="fp32")
     o = OracleCycleGan(C.RESNET64, C.SIMPLE_D4, dtype=torch.float32)
@@ -108,10 +108,14 @@ def test_c3_batch16_fp32_losses_and_edge_gradients():
     for k in ("gAB_loss", "gBA_loss", "dA_loss", "dB_loss"):
         errs[k] = abs(float(m[k]) - ref_m[k]) / max(1.0, abs(ref_m[k]))
         assert errs[k] <= 5e-4, (k, float(m[k]), ref_m[k])
+    # The stem kernel's gradient sums every ReLU flip of the whole net: between runs of the SAME build it measures 5e-3 ... 2.1e-2
+    # here (the instance-norm statistics are accumulated with atomics, so the flips differ from run to run); the head
+    # kernel's gradient has no ReLU downstream and stays at a few 1e-4.  The tight, deterministic evidence for this
+    # geometry is test_c3_full_size_gradients (teacher forced); this test only guards the batch-16 plumbing.
     first, last = 0, len(g["g_AB"]) - 2
-    for i in (first, last):
+    for i, gate in ((first, 6e-2), (last, 5e-3)):
         errs[f"g_AB[{i}]"] = C.rel_l2(g["g_AB"][i], ref_g["g_AB"][i].numpy())
-        assert errs[f"g_AB[{i}]"] <= 2e-2, (i, errs)
+        assert errs[f"g_AB[{i}]"] <= gate, (i, errs)
     LW.record("step/C3/256x16/fp32/free-running", dict(mode="fp32", errors=errs))
 
 
