@@ -31,9 +31,11 @@ template <typename T> int k_in_stats_stream(const T* x, float* sums, int N, int 
 template <typename T> int k_in_bwd_reduce_stream(const T* x, const T* dy, const float* stats, const float* gamma,
                                                  const float* beta, float* sums, int act, float slope, int N, int P, int C,
                                                  cudaStream_t st);
+// dgamma / dbeta (nullable): the affine parameter gradients are added by the kernel itself (one CTA per image)
 template <typename T> int k_in_bwd_apply_stream(const T* x, const T* dy, T* dx, const float* stats, const float* sums,
                                                 const float* gamma, const float* beta, int act, float slope, int N, int P,
-                                                int C, int W, int halo, cudaStream_t st);
+                                                int C, int W, int halo, cudaStream_t st, float* dgamma = nullptr,
+                                                float* dbeta = nullptr);
 template <typename T> int k_in_bwd(const T* x, const T* dy, T* dx, const float* stats, const float* gamma,
                                    const float* beta, float* dgamma, float* dbeta, float* scratch, int act,
                                    float slope, int N, int P, int C, int accumulate, cudaStream_t st,

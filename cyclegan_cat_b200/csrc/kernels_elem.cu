@@ -409,12 +409,17 @@ template <typename T> int k_in_bwd(const T* x, const T* dy, T* dx, const float* 
         CG_LAUNCH_CHECK();
     }
     if (bn_group > 0) CG_TRY(k_bn_pool_sums(scratch, N, C, bn_group, st));
-    if (dgamma) {
+    const bool stream_apply = dx && stream && !accumulate && (halo == 0 || (W > 0 && P % W == 0));
+    // the streaming apply adds d gamma / d beta itself (instance norm only: pooled batch-norm sums hold the GROUP mean in
+    // every sample's slot, which the separate kernel divides out by summing -- keep it there)
+    const bool fold_pg = dgamma && gamma && stream_apply && bn_group <= 0;
+    if (dgamma && !fold_pg) {
         in_param_grad_kernel<<<cdiv(C, 128), 128, 0, st>>>(scratch, dgamma, dbeta, N, C);
         CG_LAUNCH_CHECK();
     }
-    if (dx && stream && !accumulate && (halo == 0 || (W > 0 && P % W == 0))) {
-        CG_TRY(k_in_bwd_apply_stream<T>(x, dy, dx, stats, scratch, gamma, beta, act, slope, N, P, C, W, halo, st));
+    if (stream_apply) {
+        CG_TRY(k_in_bwd_apply_stream<T>(x, dy, dx, stats, scratch, gamma, beta, act, slope, N, P, C, W, halo, st,
+                                        fold_pg ? dgamma : nullptr, fold_pg ? dbeta : nullptr));
     } else if (dx && fast_cv_ok(C, VecWidth<T>::value) && (halo == 0 || (!accumulate && W > 0 && P % W == 0))) {
         constexpr int VW = VecWidth<T>::value;
         const int Wd = halo > 0 ? W : P, Hd = halo > 0 ? P / W : 1;     // halo == 0: treat the plane as one row

@@ -44,6 +44,8 @@ struct StreamArgs {
     int pad;                  // MODE 0: > 0 writes the reflection-padded [H+2p][W+2p] tensor (ReflectionPadding2D fused in)
     float invP;
     int stages, tiles_per_img;
+    float* dgamma;            // MODE 2, affine: d gamma / d beta += the per-image backward sums (one CTA per image adds them,
+    float* dbeta;             // so the separate in_param_grad_kernel launch disappears)
 };
 
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(ST_CONSUMERS) : "memory"); }
@@ -98,6 +100,13 @@ __global__ void __launch_bounds__(ST_THREADS, (MODE == 0 || MODE == 4) ? 3 : 2) 
 
     // ---- consumers ----
     const int C = a.C, CV = C / VEC;
+    if constexpr (MODE == 2 && AFFINE) {
+        if (a.dgamma && blockIdx.x == 0)          // d beta = sum g, d gamma = sum g * xhat over the images: one CTA per image adds its sums
+            for (int c = tid; c < C; c += ST_CONSUMERS) {
+                atomicAdd(a.dbeta + c, a.sums_in[((size_t)n * C + c) * 2]);
+                atomicAdd(a.dgamma + c, a.sums_in[((size_t)n * C + c) * 2 + 1]);
+            }
+    }
     const int cv = tid % CV, prow = tid / CV, rows = ST_CONSUMERS / CV;      // a tile holds 2*rows pixels
     float k0[VEC], k1[VEC], k2[MODE == 2 ? VEC : 1], k3[MODE == 2 ? VEC : 1], k4[MODE == 2 ? VEC : 1];
     float kg[(AFFINE && !FWD) ? VEC : 1], ke[(AFFINE && !FWD) ? VEC : 1];
@@ -341,8 +350,9 @@ template <typename T> int k_in_bwd_reduce_stream(const T* x, const T* dy, const 
 
 template <typename T> int k_in_bwd_apply_stream(const T* x, const T* dy, T* dx, const float* stats, const float* sums,
                                                 const float* gamma, const float* beta, int act, float slope, int N, int P,
-                                                int C, int W, int halo, cudaStream_t st) {
+                                                int C, int W, int halo, cudaStream_t st, float* dgamma, float* dbeta) {
     StreamArgs<T> a{};
+    a.dgamma = gamma ? dgamma : nullptr; a.dbeta = dbeta;
     a.x = x; a.dy = dy; a.out = dx; a.stats = stats; a.sums_in = sums; a.gamma = gamma; a.beta = beta; a.act = act;
     a.slope = slope; a.P = P; a.C = C; a.W = halo > 0 ? W : P; a.halo = halo; a.invP = 1.f / (float)P;
     return gamma ? launch_stream<T, 2, true>(a, N, st) : launch_stream<T, 2, false>(a, N, st);
@@ -356,6 +366,6 @@ template <typename T> int k_in_bwd_apply_stream(const T* x, const T* dy, T* dx, 
     template int k_in_bwd_reduce_stream<T>(const T*, const T*, const float*, const float*, const float*, float*, int,      \
                                            float, int, int, int, cudaStream_t);                                            \
     template int k_in_bwd_apply_stream<T>(const T*, const T*, T*, const float*, const float*, const float*, const float*,  \
-                                          int, float, int, int, int, int, int, cudaStream_t);
+                                          int, float, int, int, int, int, int, cudaStream_t, float*, float*);
 INSTANTIATE(float)
 INSTANTIATE(bf16)

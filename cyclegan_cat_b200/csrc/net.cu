@@ -1025,8 +1025,8 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                             CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
                     }
                     if (want_dx) {
-                        if (acc || c->tc[i].dgrad.empty()) {
-                            CG_TRY(k_conv_dgrad<T>(dy, params + L.w_off, nullptr, dx, g, acc, st));
+                        if (acc || c->tc[i].dgrad.empty()) {     // image-side layer: only the samples whose dx is read (dx_nb)
+                            CG_TRY(k_conv_dgrad<T>(dy, params + L.w_off, nullptr, dx, conv_geom(d, nbx, h, w, oh, ow), acc, st));
                         } else {
                             const TcConvLaunch& tl = c->tc[i].dgrad[0];
                             TcConvArgs a = tl.a;
@@ -1147,7 +1147,7 @@ static int backward_T(CallCtx* c, const float* params, const T* dy_out, T* dx_in
                     CG_TRY(k_conv_wgrad<T>(A(tin), dy, grads + L.w_off, g, st));
                     if (L.b_off >= 0 && !L.bias_grad_zero) CG_TRY(k_colsum<T>(dy, grads + L.b_off, (size_t)nb * oh * ow, d.cout, st));
                 }
-                if (want_dx) CG_TRY(k_conv_dgrad<T>(dy, params + L.w_off, nullptr, dx, g, acc, st));
+                if (want_dx) CG_TRY(k_conv_dgrad<T>(dy, params + L.w_off, nullptr, dx, conv_geom(d, nbx, h, w, oh, ow), acc, st));
                 break;
             }
             case CG_OP_CONVT: {
