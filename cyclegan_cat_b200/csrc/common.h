@@ -141,6 +141,14 @@ __device__ __forceinline__ void in_scale_shift(float mean, float rstd, float ga,
     sh = __fmaf_rn(-mean, sc, be);
 }
 __device__ __forceinline__ float in_pre(float v, float sc, float sh) { return __fmaf_rn(v, sc, sh); }
+// (sum x, sum x^2) over P elements -> (mean, rstd), biased variance (TFA InstanceNormalization / Keras moments).  ONE
+// definition with explicit roundings: in_finalize_kernel and the streaming apply kernels that finalize on the fly must
+// produce the same bits, because the backward kernels rebuild the forward's activation masks from the stored pair.
+__device__ __forceinline__ void in_mean_rstd(float s0, float s1, float invP, float eps, float& mean, float& rstd) {
+    mean = __fmul_rn(s0, invP);
+    const float var = fmaxf(__fmaf_rn(-mean, mean, __fmul_rn(s1, invP)), 0.f);
+    rstd = rsqrtf(__fadd_rn(var, eps));
+}
 
 // derivative expressed through the activation OUTPUT y (all four are invertible enough for that)
 __device__ __forceinline__ float act_grad_from_out(float y, int act, float slope) {

@@ -17,16 +17,18 @@ template <typename T> int k_colsum(const T* dy, float* db, size_t rows, int C, c
 // ---- instance norm ----
 template <typename T> int k_in_stats(const T* x, float* stats, int N, int P, int C, float eps, cudaStream_t st,
                                      bool zeroed = false);      // zeroed: the caller has already cleared `stats`
-int k_in_finalize(float* stats, int NC, int P, float eps, cudaStream_t st);
+int k_in_finalize(const float* raw, float* stats, int NC, int P, float eps, cudaStream_t st);      // raw may equal stats (in place)
 template <typename T> int k_in_apply(const T* x, T* y, const float* stats, const float* gamma, const float* beta,
                                      int act, float slope, int N, int P, int C, cudaStream_t st);
 // bulk-copy pipelined variants (kernels_stream.cu); k_in_stream_ok says whether a (P, C) plane qualifies
 template <typename T> bool k_in_stream_ok(const void* p0, const void* p1, const void* p2, int P, int C);
 // y (nullable) = act(norm(x)) [+ res]; ypad (nullable, pad > 0) = the same values as the reflection-padded
 // [N][H+2p][W+2p][C] tensor (P = H*W)
-template <typename T> int k_in_apply_stream(const T* x, const T* res, T* y, T* ypad, const float* stats, const float* gamma,
+// raw (nullable): `stats` has not been finalized yet -- the kernel computes (mean, rstd) from the raw (sum x, sum x^2) table
+// itself and one CTA per image stores them into `stats` for the backward (no in_finalize_kernel launch)
+template <typename T> int k_in_apply_stream(const T* x, const T* res, T* y, T* ypad, float* stats, const float* gamma,
                                             const float* beta, int act, float slope, int N, int P, int C, int W, int pad,
-                                            cudaStream_t st);
+                                            cudaStream_t st, const float* raw = nullptr, float eps = 0.f);
 template <typename T> int k_in_stats_stream(const T* x, float* sums, int N, int P, int C, cudaStream_t st);
 template <typename T> int k_in_bwd_reduce_stream(const T* x, const T* dy, const float* stats, const float* gamma,
                                                  const float* beta, float* sums, int act, float slope, int N, int P, int C,

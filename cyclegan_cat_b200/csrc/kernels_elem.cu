@@ -106,15 +106,15 @@ __global__ void __launch_bounds__(256) in_reduce_kernel(const T* __restrict__ x,
     }
 }
 
-__global__ void in_finalize_kernel(float* __restrict__ stats, int NC, float invP, float eps) {
+__global__ void in_finalize_kernel(const float* in, float* out, int NC, float invP, float eps) {
     griddep_launch();        // PDL: see ptx_async.h
     griddep_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NC) return;
-    float mean = stats[2 * i] * invP;
-    float var = fmaxf(stats[2 * i + 1] * invP - mean * mean, 0.f);
-    stats[2 * i] = mean;
-    stats[2 * i + 1] = rsqrtf(var + eps);
+    float mean, rstd;
+    in_mean_rstd(in[2 * i], in[2 * i + 1], invP, eps, mean, rstd);
+    out[2 * i] = mean;
+    out[2 * i + 1] = rstd;
 }
 
 static inline void in_reduce_grid(int N, int P, int C, dim3& grid, int& pchunk) {
@@ -127,8 +127,8 @@ static inline void in_reduce_grid(int N, int P, int C, dim3& grid, int& pchunk) 
     grid = dim3(cb, ps, N);
 }
 
-int k_in_finalize(float* stats, int NC, int P, float eps, cudaStream_t st) {
-    launch_pdl(in_finalize_kernel, dim3(cdiv(NC, 256)), dim3(256), 0, st, stats, NC, 1.f / (float)P, eps);
+int k_in_finalize(const float* raw, float* stats, int NC, int P, float eps, cudaStream_t st) {
+    launch_pdl(in_finalize_kernel, dim3(cdiv(NC, 256)), dim3(256), 0, st, raw, stats, NC, 1.f / (float)P, eps);
     CG_LAUNCH_CHECK();
     return CG_OK;
 }
@@ -145,7 +145,7 @@ template <typename T> int k_in_stats_raw(const T* x, float* stats, int N, int P,
 }
 template <typename T> int k_in_stats(const T* x, float* stats, int N, int P, int C, float eps, cudaStream_t st, bool zeroed) {
     CG_TRY(k_in_stats_raw<T>(x, stats, N, P, C, st, zeroed));
-    return k_in_finalize(stats, N * C, P, eps, st);
+    return k_in_finalize(stats, stats, N * C, P, eps, st);
 }
 
 // y = act((x - mean) * rstd * gamma + beta); grid.y = sample, x-dimension strides over P*C/VEC
@@ -292,7 +292,7 @@ template <typename T> int k_in_apply(const T* x, T* y, const float* stats, const
     constexpr int VW = VecWidth<T>::value;
     size_t PC = (size_t)P * C;
     if (k_in_stream_ok<T>(x, y, nullptr, P, C))
-        return k_in_apply_stream<T>(x, nullptr, y, nullptr, stats, gamma, beta, act, slope, N, P, C, 0, 0, st);
+        return k_in_apply_stream<T>(x, nullptr, y, nullptr, const_cast<float*>(stats), gamma, beta, act, slope, N, P, C, 0, 0, st);
     if (fast_cv_ok(C, VW)) {
         dim3 grid(fast_blocks(P, C, VW, N), N);
         in_apply_fast_kernel<T, VW><<<grid, 256, 0, st>>>(x, y, stats, gamma, beta, act, slope, P, C);

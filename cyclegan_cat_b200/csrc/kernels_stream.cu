@@ -44,6 +44,9 @@ struct StreamArgs {
     int pad;                  // MODE 0: > 0 writes the reflection-padded [H+2p][W+2p] tensor (ReflectionPadding2D fused in)
     float invP;
     int stages, tiles_per_img;
+    const float* raw;         // forward modes: raw (sum x, sum x^2) table to finalize on the fly (null: `stats` is final)
+    float* stats_w;           //   ... and where one CTA per image stores the finalized (mean, rstd)
+    float eps;
     float* dgamma;            // MODE 2, affine: d gamma / d beta += the per-image backward sums (one CTA per image adds them,
     float* dbeta;             // so the separate in_param_grad_kernel launch disappears)
 };
@@ -114,7 +117,17 @@ __global__ void __launch_bounds__(ST_THREADS, (MODE == 0 || MODE == 4) ? 3 : 2) 
     for (int j = 0; j < VEC; ++j) {
         if constexpr (MODE == 4) { k0[j] = k1[j] = 0.f; continue; }
         const int c = cv * VEC + j;
-        const float mean = a.stats[((size_t)n * C + c) * 2], rstd = a.stats[((size_t)n * C + c) * 2 + 1];
+        float mean, rstd;
+        if (FWD && a.raw) {
+            in_mean_rstd(a.raw[((size_t)n * C + c) * 2], a.raw[((size_t)n * C + c) * 2 + 1], a.invP, a.eps, mean, rstd);
+            if (blockIdx.x == 0 && prow == 0) {
+                a.stats_w[((size_t)n * C + c) * 2] = mean;
+                a.stats_w[((size_t)n * C + c) * 2 + 1] = rstd;
+            }
+        } else {
+            mean = a.stats[((size_t)n * C + c) * 2];
+            rstd = a.stats[((size_t)n * C + c) * 2 + 1];
+        }
         const float ga = AFFINE ? a.gamma[c] : 1.f, be = AFFINE ? a.beta[c] : 0.f;
         if constexpr (FWD) {
             in_scale_shift(mean, rstd, ga, be, k0[j], k1[j]);      // y = act(v*k0 + k1)
@@ -323,10 +336,11 @@ template <typename T> bool k_in_stream_ok(const void* p0, const void* p1, const 
     return !(((uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2) & 15);
 }
 
-template <typename T> int k_in_apply_stream(const T* x, const T* res, T* y, T* ypad, const float* stats, const float* gamma,
+template <typename T> int k_in_apply_stream(const T* x, const T* res, T* y, T* ypad, float* stats, const float* gamma,
                                             const float* beta, int act, float slope, int N, int P, int C, int W, int pad,
-                                            cudaStream_t st) {
+                                            cudaStream_t st, const float* raw, float eps) {
     StreamArgs<T> a{};
+    a.raw = raw; a.stats_w = stats; a.eps = eps;
     a.x = x; a.dy = res; a.out = y; a.out2 = ypad; a.stats = stats; a.gamma = gamma; a.beta = beta; a.act = act; a.slope = slope;
     a.P = P; a.C = C; a.W = (ypad && pad > 0) ? W : P; a.pad = ypad ? pad : 0; a.halo = 0; a.invP = 1.f / (float)P;
     if (res) return gamma ? launch_stream<T, 3, true>(a, N, st) : launch_stream<T, 3, false>(a, N, st);
@@ -361,8 +375,8 @@ template <typename T> int k_in_bwd_apply_stream(const T* x, const T* dy, T* dx, 
 #define INSTANTIATE(T)                                                                                                     \
     template int k_in_stats_stream<T>(const T*, float*, int, int, int, cudaStream_t);                                      \
     template bool k_in_stream_ok<T>(const void*, const void*, const void*, int, int);                                      \
-    template int k_in_apply_stream<T>(const T*, const T*, T*, T*, const float*, const float*, const float*, int, float,    \
-                                      int, int, int, int, int, cudaStream_t);                                              \
+    template int k_in_apply_stream<T>(const T*, const T*, T*, T*, float*, const float*, const float*, int, float,          \
+                                      int, int, int, int, int, cudaStream_t, const float*, float);                                              \
     template int k_in_bwd_reduce_stream<T>(const T*, const T*, const float*, const float*, const float*, float*, int,      \
                                            float, int, int, int, cudaStream_t);                                            \
     template int k_in_bwd_apply_stream<T>(const T*, const T*, T*, const float*, const float*, const float*, const float*,  \

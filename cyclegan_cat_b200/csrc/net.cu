@@ -99,6 +99,7 @@ int net_plan(const cg_net_s* net, int N, int H, int W, bool bwd, CallCtx* ctx) {
         off += align_up((size_t)N * ctx->sample_elems((int)t) * es, 256);
     }
     ctx->stat_off.assign(nl, 0);
+    ctx->raw_off.assign(nl, 0);
     ctx->bstat_off.assign(nl, 0);
     ctx->stat_begin = off;
     size_t max_nc = 1;
@@ -110,6 +111,9 @@ int net_plan(const cg_net_s* net, int N, int H, int W, bool bwd, CallCtx* ctx) {
             if ((size_t)N * d.cin > max_nc) max_nc = (size_t)N * d.cin;
             if (net->layers[i].batch) {      // per-group batch statistics (at most N groups)
                 ctx->bstat_off[i] = off;
+                off += align_up((size_t)N * d.cin * 2 * sizeof(float), 256);
+            } else {                         // raw sums of a fused-statistics conv (see CallCtx::raw_off)
+                ctx->raw_off[i] = off;
                 off += align_up((size_t)N * d.cin * 2 * sizeof(float), 256);
             }
         }
@@ -737,7 +741,8 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
         const bool long_k = L.tc != TC_STEM && L.tc != TC_IM2COL;
         const bool bn_infer = i + 1 < net->layers.size() && net->layers[i + 1].batch && !c->training;
         if (c->tc[i].on && L.feeds_in && L.tc != TC_HEAD && long_k && i + 1 < net->layers.size() && !bn_infer) {
-            fused_stats = (float*)(c->base + c->stat_off[i + 1]);
+            // plain instance norm: the raw sums go to their own table and the streaming apply finalizes them on the fly
+            fused_stats = (float*)(c->base + (net->layers[i + 1].batch ? c->stat_off[i + 1] : c->raw_off[i + 1]));
             stats_done[i + 1] = 1;
         }
         T* y = (T*)c->act(tout);
@@ -819,8 +824,16 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
                     } else {
                         CG_TRY(k_bn_fill(stats, mm, mv, N, d.cin, d.eps, st));
                     }
-                } else if (stats_done[i]) CG_TRY(k_in_finalize(stats, N * d.cin, h * w, d.eps, st));
-                else CG_TRY(k_in_stats<T>(x, stats, N, h * w, d.cin, d.eps, st, /*zeroed=*/true));
+                } else if (!stats_done[i]) CG_TRY(k_in_stats<T>(x, stats, N, h * w, d.cin, d.eps, st, /*zeroed=*/true));
+                // raw sums from the conv epilogue (plain instance norm): the streaming apply kernels finalize them themselves
+                // (and store (mean, rstd) for the backward); every other path runs the finalize kernel first
+                const float* raw = (!L.batch && stats_done[i]) ? (const float*)(c->base + c->raw_off[i]) : nullptr;
+                auto finalize_now = [&]() -> int {
+                    if (!raw) return CG_OK;
+                    const int rc = k_in_finalize(raw, stats, N * d.cin, h * w, d.eps, st);
+                    raw = nullptr;
+                    return rc;
+                };
                 const float* gam = L.g_off >= 0 ? params + L.g_off : nullptr;
                 const float* bet = L.be_off >= 0 ? params + L.be_off : nullptr;
                 if (L.fuse_rpad >= 0) {
@@ -828,7 +841,7 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
                     T* yp = (T*)c->act(R.out_t);
                     if (R.d.pad < h && R.d.pad < w && k_in_stream_ok<T>(x, yp, nullptr, h * w, d.cin)) {
                         CG_TRY(k_in_apply_stream<T>(x, nullptr, nullptr, yp, stats, gam, bet, L.fused_act, L.fused_slope, N, h * w,
-                                                    d.cin, w, R.d.pad, st));
+                                                    d.cin, w, R.d.pad, st, raw, d.eps));
                         fused_done[L.fuse_rpad] = 1;
                         c->live[R.out_t] = 1;
                         break;
@@ -847,16 +860,20 @@ static int forward_T(CallCtx* c, const float* params, cudaStream_t st) {
                     }
                     if (other <= (int)i && k_in_stream_ok<T>(x, res, ys, h * w, d.cin) && !((uintptr_t)yp & 15)) {
                         CG_TRY(k_in_apply_stream<T>(x, res, ys, yp, stats, gam, bet, L.fused_act, L.fused_slope, N, h * w, d.cin, w,
-                                                    pad, st));
+                                                    pad, st, raw, d.eps));
                         fused_done[L.fuse_add] = 1;
                         c->live[Ad.out_t] = 1;
                         if (yp) { fused_done[Ad.fuse_rpad] = 1; c->live[net->layers[Ad.fuse_rpad].out_t] = 1; }
                         break;
                     }
                 }
-                CG_TRY(k_in_apply<T>(x, y, stats, L.g_off >= 0 ? params + L.g_off : nullptr,
-                                     L.be_off >= 0 ? params + L.be_off : nullptr, L.fused_act, L.fused_slope, N,
-                                     h * w, d.cin, st));
+                if (raw && k_in_stream_ok<T>(x, y, nullptr, h * w, d.cin)) {
+                    CG_TRY(k_in_apply_stream<T>(x, nullptr, y, nullptr, stats, gam, bet, L.fused_act, L.fused_slope, N, h * w,
+                                                d.cin, 0, 0, st, raw, d.eps));
+                } else {
+                    CG_TRY(finalize_now());
+                    CG_TRY(k_in_apply<T>(x, y, stats, gam, bet, L.fused_act, L.fused_slope, N, h * w, d.cin, st));
+                }
                 c->live[tout] = 1;
                 break;
             }

@@ -77,7 +77,9 @@ struct CallCtx {
     bool bwd = false;
     std::vector<int> th, tw;            // spatial size per tensor
     std::vector<size_t> act_off;        // byte offsets into `base` (activations)
-    std::vector<size_t> stat_off;       // per layer: INORM statistics [N][C][2] float
+    std::vector<size_t> stat_off;       // per layer: INORM statistics [N][C][2] float: (mean, rstd) once finalized
+    std::vector<size_t> raw_off;        // per layer (plain instance norm): the raw (sum x, sum x^2) table a conv epilogue fills;
+                                        // the streaming forward apply turns it into stat_off's (mean, rstd) on the fly
     size_t act_bytes = 0;
     size_t stat_begin = 0;              // the INORM statistics tables are one contiguous region [stat_begin, act_bytes)
     std::vector<size_t> grad_off;       // byte offsets into the shared gradient arena
