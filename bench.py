@@ -640,7 +640,7 @@ def run_gpu(args, wl):
                          d2h_bytes_per_step=24, ms_per_step=ms_e2e / args.steps))
     if not args.no_cpu_baseline:
         c1 = WORKLOADS[args.workload]
-        r = time_oracle(c1, steps=2, warmup=1, budget_s=60.0)
+        r = time_oracle(c1, steps=8, warmup=1, budget_s=20.0)       # a bounded sample: ~10-20 s of CPU work (8 batch-1 steps of C3)
         line["cpu_baseline"] = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"],
                                     ms_per_step=r["ms_per_step"])
     if extra:
