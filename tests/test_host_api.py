@@ -158,6 +158,34 @@ def test_native_planner_agrees_with_host(built_lib):
         assert built_lib.cg_net_workspace_bytes(h, 2, 64, 96, 1, ctypes.byref(nbytes)) == 0 and nbytes.value > 0
 
 
+def test_trainer_plans_without_a_gpu(built_lib):
+    """cg_trainer_create / cg_trainer_workspace_bytes are host planning too.  The step is laid out as five model calls
+    (g_AB([a;b]), ONE g_BA call over [fake_b; b; a], g_AB(fake_a), d_A, d_B): the workspace grows linearly with the
+    batch, the headline configuration fits a B200 at the benchmark batch (16) and at BASELINE's global batch (64),
+    and the fetch probe refuses to run before a step."""
+    from cyclegan_cat_b200.cyclegan.model import CycleGan
+    gan = CycleGan(C.model_config(C.RESNET64, C.SIMPLE_D4), C.train_config(), mode="bf16")
+    cfg = ir.TrainCfg()
+    cfg.loss = gan.loss_obj.kind
+    for i, o in enumerate(gan._opts()):
+        cfg.adam[i] = ir.AdamCfg(o.learning_rate, o.beta_1, o.beta_2, o.epsilon, o.kind)
+    tr = ctypes.c_void_p()
+    nets = gan._nets()
+    assert built_lib.cg_trainer_create(nets[0].handle(), nets[1].handle(), nets[2].handle(), nets[3].handle(),
+                                       ctypes.byref(cfg), ctypes.byref(tr)) == 0
+    sizes = {}
+    for B in (1, 2, 16, 64):
+        n = ctypes.c_size_t()
+        assert built_lib.cg_trainer_workspace_bytes(tr, B, 256, 256, ctypes.byref(n)) == 0
+        sizes[B] = n.value
+    assert sizes[2] < 2.2 * sizes[1] and abs(sizes[64] / sizes[16] - 4.0) < 0.05
+    assert sizes[16] < 40 * 2 ** 30 and sizes[64] < 150 * 2 ** 30          # of the 180 GB per GPU
+    assert built_lib.cg_trainer_workspace_bytes(tr, 1, 250, 250, ctypes.byref(n)) != 0       # 250 % 4 != 0
+    shape = (ctypes.c_int * 4)()
+    assert built_lib.cg_trainer_fetch_tensor(tr, 1, 0, None, ctypes.byref(shape), None) != 0   # no step yet
+    built_lib.cg_trainer_destroy(tr)
+
+
 def test_native_rejects_bad_graphs_and_shapes(built_lib):
     h = ctypes.c_void_p()
     bad = (ir.LayerDesc * 1)(ir.LayerDesc(ir.OP_CONV, 0, -1, 3, 8, 3, 3, 1, 1, 0, 0, 0, 1e-3, 0.2))   # stride 3
