@@ -138,9 +138,15 @@ __global__ void __launch_bounds__(128) conv_fwd_skinny(const T* __restrict__ x, 
     const int wpairs = (g.Wo + 1) / 2;
     const long long total = (long long)g.N * g.Ho * wpairs;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int wp = (int)(idx % wpairs);
-        long long r = idx / wpairs;
-        const int oh = (int)(r % g.Ho), n = (int)(r / g.Ho);
+        int wp, oh, n;          // 32-bit index arithmetic whenever it fits: a 64-bit divide is ~100 emulated instructions, more
+        if (total <= 0x7fffffffLL) {       // than the 16 x 8 FMAs of a 1x1 head pixel pair
+            const int i32 = (int)idx, r = i32 / wpairs;
+            wp = i32 - r * wpairs; n = r / g.Ho; oh = r - n * g.Ho;
+        } else {
+            wp = (int)(idx % wpairs);
+            const long long r = idx / wpairs;
+            oh = (int)(r % g.Ho); n = (int)(r / g.Ho);
+        }
         const int ow0 = wp * 2;
         const bool second = ow0 + 1 < g.Wo;
         float acc[2][4] = {};
@@ -403,20 +409,27 @@ __global__ void __launch_bounds__(128) conv_dgrad_skinny(const T* __restrict__ d
     __syncthreads();
     const long long total = (long long)g.N * g.Hi * g.Wi;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int iw = (int)(idx % g.Wi);
-        long long r = idx / g.Wi;
-        const int ih = (int)(r % g.Hi), n = (int)(r / g.Hi);
+        int iw, ih, n;          // 32-bit index arithmetic whenever it fits (see conv_fwd_skinny)
+        if (total <= 0x7fffffffLL) {
+            const int i32 = (int)idx, r = i32 / g.Wi;
+            iw = i32 - r * g.Wi; n = r / g.Hi; ih = r - n * g.Hi;
+        } else {
+            iw = (int)(idx % g.Wi);
+            const long long r = idx / g.Wi;
+            ih = (int)(r % g.Hi); n = (int)(r / g.Hi);
+        }
+        const bool s1 = g.s == 1;          // stride 1: no divisibility test / divide per tap
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         const T* dyn = dy + (size_t)n * g.Ho * g.Wo * g.Cout;
         for (int kh = 0; kh < g.k; ++kh) {
             const int th = ih + g.pt - kh;
-            if (th < 0 || th % g.s) continue;
-            const int oh = th / g.s;
+            if (th < 0 || (!s1 && th % g.s)) continue;
+            const int oh = s1 ? th : th / g.s;
             if (oh >= g.Ho) continue;
             for (int kw = 0; kw < g.k; ++kw) {
                 const int tw = iw + g.pl - kw;
-                if (tw < 0 || tw % g.s) continue;
-                const int ow = tw / g.s;
+                if (tw < 0 || (!s1 && tw % g.s)) continue;
+                const int ow = s1 ? tw : tw / g.s;
                 if (ow >= g.Wo) continue;
                 const T* p = dyn + ((size_t)oh * g.Wo + ow) * g.Cout;
                 const float4* wr = wsm + (kh * g.k + kw) * g.Cout;
