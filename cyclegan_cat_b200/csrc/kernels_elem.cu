@@ -410,8 +410,8 @@ template <typename T> int k_in_bwd(const T* x, const T* dy, T* dx, const float* 
     }
     if (bn_group > 0) CG_TRY(k_bn_pool_sums(scratch, N, C, bn_group, st));
     const bool stream_apply = dx && stream && !accumulate && (halo == 0 || (W > 0 && P % W == 0));
-    // the streaming apply adds d gamma / d beta itself (instance norm only: pooled batch-norm sums hold the GROUP mean in
-    // every sample's slot, which the separate kernel divides out by summing -- keep it there)
+    // the streaming apply adds d gamma / d beta itself; BatchNormalization (pooled sums spread over the samples of a group)
+    // and the non-streaming fallbacks keep the separate kernel
     const bool fold_pg = dgamma && gamma && stream_apply && bn_group <= 0;
     if (dgamma && !fold_pg) {
         in_param_grad_kernel<<<cdiv(C, 128), 128, 0, st>>>(scratch, dgamma, dbeta, N, C);
